@@ -1,0 +1,93 @@
+// api.cu -- C-ABI entry points of libpconv_b200.so for the convolution itself (validation + dispatch between
+// the tcgen05 tensor-core kernels and the shape-general kernels), error string, launch counter.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "pcb_common.cuh"
+
+static thread_local char g_err[1024] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int pcb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+void pcb_count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+
+extern "C" __attribute__((visibility("default"))) const char *pcb_last_error(void) { return g_err; }
+extern "C" __attribute__((visibility("default"))) int pcb_version(void) { return 1; }
+extern "C" __attribute__((visibility("default"))) unsigned long long pcb_launch_count(void) { return g_launches.load(); }
+
+static int validate(const pcb_conv *c, bool need_x) {
+    PCB_CHECK(c != nullptr, "null pcb_conv");
+    PCB_CHECK(c->dtype == PCB_F32 || c->dtype == PCB_BF16, "bad dtype %d", c->dtype);
+    PCB_CHECK(c->n > 0 && c->h > 0 && c->w > 0 && c->cin > 0 && c->cout > 0 && c->kh > 0 && c->kw > 0, "non-positive dimension");
+    PCB_CHECK(c->stride > 0 && c->dil > 0 && c->pad_h >= 0 && c->pad_w >= 0, "bad stride/dilation/padding");
+    PCB_CHECK(c->groups > 0 && c->cin % c->groups == 0 && c->cout % c->groups == 0, "groups must divide cin and cout");
+    const int ho = (c->h + 2 * c->pad_h - c->dil * (c->kh - 1) - 1) / c->stride + 1;
+    const int wo = (c->w + 2 * c->pad_w - c->dil * (c->kw - 1) - 1) / c->stride + 1;
+    PCB_CHECK(ho == c->ho && wo == c->wo && ho > 0 && wo > 0, "output size mismatch: expected %dx%d, got %dx%d", ho, wo, c->ho, c->wo);
+    PCB_CHECK(c->nparts >= 1 && c->nparts <= PCB_MAX_PARTS, "nparts out of range");
+    int tot = 0;
+    for (int p = 0; p < c->nparts; ++p) {
+        const pcb_part &pt = c->parts[p];
+        PCB_CHECK(pt.c > 0 && pt.x_cstride >= pt.c, "part %d: bad channel counts", p);
+        PCB_CHECK((pt.x_up == 0 || pt.x_up == 1) && (pt.mask_up == 0 || pt.mask_up == 1), "part %d: bad upsample factor", p);
+        PCB_CHECK(!(pt.x_up || pt.mask_up) || (c->h % 2 == 0 && c->w % 2 == 0), "part %d: upsampled source needs even h, w", p);
+        PCB_CHECK(!need_x || pt.x != nullptr, "part %d: null x", p);
+        tot += pt.c;
+    }
+    PCB_CHECK(tot == c->cin, "parts cover %d channels, cin is %d", tot, c->cin);
+    PCB_CHECK(!(c->no_guard && c->groups != 1), "PartialConvNoHoles requires groups == 1");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_conv_uses_tensor_cores(const pcb_conv *c) { return (c && pcb_tc_forward_eligible(c)) ? 1 : 0; }
+
+extern "C" __attribute__((visibility("default"))) size_t pcb_pconv_workspace(const pcb_conv *c) {
+    if (!c || !pcb_tc_forward_eligible(c)) return 0;
+    return pcb_tc_forward_workspace(c);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_pconv_forward(const pcb_conv *c, const void *w, const float *bias, void *y, float *msum, uint8_t *newmask,
+                                 void *workspace, pcb_stream_t stream) {
+    if (int rc = validate(c, true)) return rc;
+    PCB_CHECK(w && y && msum && newmask, "pcb_pconv_forward: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
+    if (pcb_tc_forward_eligible(c)) {
+        PCB_CHECK(workspace != nullptr, "pcb_pconv_forward: workspace required for the tensor-core path");
+        PCB_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "w / y must be 16-byte aligned");
+        return pcb_tc_forward_ws(c, w, bias, y, msum, static_cast<uint32_t *>(workspace), st);
+    }
+    return pcb_generic_forward(c, w, bias, y, msum, newmask, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, const void *w_krsc, const void *w_crsk, void *dx,
+                                       pcb_stream_t stream) {
+    if (int rc = validate(c, false)) return rc;
+    PCB_CHECK(dc && w_krsc && dx, "pcb_pconv_backward_data: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (w_crsk && pcb_tc_dgrad_eligible(c) && (reinterpret_cast<uintptr_t>(dc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0)
+        return pcb_tc_dgrad(c, dc, w_crsk, dx, st);
+    return pcb_generic_dgrad(c, dc, w_krsc, dx, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, float *dw, void *workspace, pcb_stream_t stream) {
+    if (int rc = validate(c, true)) return rc;
+    PCB_CHECK(dc && dw, "pcb_pconv_backward_weight: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pcb_tc_wgrad_eligible(c) && workspace && (reinterpret_cast<uintptr_t>(dc) & 15) == 0)
+        return pcb_tc_wgrad(c, dc, dw, workspace, st);
+    return pcb_generic_wgrad(c, dc, dw, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_debug_pipeline_status(int *code) {
+    PCB_CHECK(code != nullptr, "null code");
+    return pcb_tc_read_abort_flag(code);
+}

@@ -1,0 +1,737 @@
+// conv_tc.cu -- partial convolution as implicit GEMM on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// Replaces (per layer) the reference's pair of dense convolutions + ~9 elementwise passes
+// (models/partial_convolution.py:49-80): `feature_conv(x*mask)`, the all-ones `mask_conv`, `==0`,
+// `masked_fill_`, `(out-b)/mask_sum+b`, `masked_fill_`, `ones_like`+`masked_fill_`.
+//
+// Forward / data-gradient kernel (one kernel, MODE template):
+//   GEMM view   M = output pixels (n*ho*wo) [fwd]  or input pixels (n*h*w) [dgrad]
+//               N = cout [fwd] / cin [dgrad],  K = taps * channels, walked tap-major in 64-channel blocks
+//   A operand   im2col rows gathered by 4 producer warps with 16-byte cp.async (LDGSTS), zero-filled where
+//               the tap falls on padding or on a HOLE (x*mask folded into the load: no masked copy of x
+//               is ever materialised), across up to PCB_MAX_PARTS concatenated / 2x-nearest-upsampled
+//               sources (torch.cat + DoubleUpSample become index math).  Written straight into the
+//               128B-swizzled K-major layout UMMA reads.
+//   B operand   weights [N][K] bf16, TMA 2D tiles (SWIZZLE_128B), one elected thread.
+//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BLOCK_N x K=16, fp32 accumulators in TMEM,
+//               issued by one thread; smem stages recycled through tcgen05.commit -> mbarrier.
+//   epilogue    TMEM -> registers (tcgen05.ld 32x32b), fwd: y = hole ? 0 : acc / s + bias (s = mask box
+//               sum), dgrad: dx = acc * input-mask; bf16 NHWC stores.
+//
+// Weight-gradient kernel: D[ci][co] (+)= sum_pixels x_gathered[p][ci] * dc[p][co] per tap: both operands
+// are "pixel-row x 128-byte channel chunk" tiles, i.e. MN-major UMMA operands with the same swizzled smem
+// image as above; split-K over pixels with fp32 red.global.add.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pcb_common.cuh"
+#include "pcb_ptx.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;
+constexpr int NUM_PRODUCER_THREADS = 128;
+constexpr int TC_THREADS = 192;             // 4 producer/epilogue warps + TMA warp + MMA warp
+constexpr int TC_MAX_PARTS = 2;        // U-Net inputs are cat([upsampled, skip]) at most
+
+struct TcPart {
+    const bf16 *x;            // first channel of the part (fwd / wgrad gather source)
+    const uint32_t *tapmask;  // [m_total] bit t = tap t is in-bounds and not a hole (fwd / wgrad)
+    const uint8_t *mask;      // input hole plane (dgrad epilogue), may be null
+    int c, choff, cstride, xup, mup;
+};
+
+struct TcParams {
+    int n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil, ho, wo;
+    int m_total;              // GEMM M
+    int nparts;
+    int no_guard;
+    TcPart parts[TC_MAX_PARTS];
+    const float *bias;        // fwd
+    const float *msum;        // fwd: [m_total]
+    bf16 *out;                // y (fwd) / dx (dgrad)
+    int *abort_flag;
+};
+
+__device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
+
+// -------------------------------------------------------------------------------------------------
+// forward (MODE 0) / dgrad (MODE 1)
+// -------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, (BLOCK_N <= 128) ? 2 : 1)
+pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w) {
+    constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
+    const uint32_t sA = smem_base;
+    const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
+    const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;          // 8-byte barriers
+    const uint32_t bar_full_a = sBar;                           // [STAGES]
+    const uint32_t bar_full_b = sBar + 8 * STAGES;              // [STAGES]
+    const uint32_t bar_empty = sBar + 16 * STAGES;              // [STAGES]
+    const uint32_t bar_tmem_full = sBar + 24 * STAGES;          // [1]
+    const uint32_t s_tmem_ptr = bar_tmem_full + 8;              // u32
+    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
+
+    const int taps = P.kh * P.kw;
+    const int kchan = (MODE == 0) ? P.cin : P.cout;             // channels per tap along K
+    const int kb_per_tap = kchan / BLOCK_K;
+    const int num_kb = taps * kb_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS);
+            ptx::mbar_init(bar_full_b + 8 * s, 1);
+            ptx::mbar_init(bar_empty + 8 * s, 1);
+        }
+        ptx::mbar_init(bar_tmem_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tmap_w);
+    if (warp == 5) {
+        ptx::tmem_alloc<BLOCK_N>(s_tmem_ptr);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    if (warp < 4) {
+        // =========================== A producers: im2col gather ===========================
+        const int t = threadIdx.x;
+        const int chunk = t & 7;                    // 16-byte chunk inside the 128-byte row
+        const int r0 = t >> 3;                      // rows r0 + 16*i
+        const uint32_t sw = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);   // (r & 7) == (r0 & 7) for all i
+
+        int pn[8], ph[8], pw[8];                    // per-row pixel coordinates (pre-scaled)
+        bool prow[8];
+        const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
+        const int pwid = (MODE == 0) ? P.wo : P.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + r0 + 16 * i;
+            prow[i] = m < P.m_total;
+            const int mm = prow[i] ? m : 0;
+            const int nn = mm / plane, rem = mm - nn * plane;
+            const int hh = rem / pwid, ww = rem - hh * pwid;
+            pn[i] = nn;
+            if (MODE == 0) { ph[i] = hh * P.stride - P.pad_h; pw[i] = ww * P.stride - P.pad_w; }
+            else           { ph[i] = hh + P.pad_h;            pw[i] = ww + P.pad_w; }
+        }
+
+        // per-row tap-validity bits (bounds + holes), loaded once per tile: the k-loop issues no mask loads
+        uint32_t tmv[TC_MAX_PARTS][8];
+        if (MODE == 0) {
+#pragma unroll
+            for (int p = 0; p < TC_MAX_PARTS; ++p)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    tmv[p][i] = (p < P.nparts && prow[i]) ? __ldg(P.parts[p].tapmask + m0 + r0 + 16 * i) : 0u;
+        }
+
+        int kb = 0;
+        bool dead = false;
+        for (int tap = 0; tap < taps && !dead; ++tap) {
+            const int tr = tap / P.kw, tc = tap - tr * P.kw;
+            const int np = (MODE == 0) ? P.nparts : 1;
+#pragma unroll
+            for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                if (p >= np || dead) break;
+                const TcPart &pt = P.parts[p];
+                const bf16 *src[8];
+                bool ok[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int hi, wi;
+                    bool v = prow[i];
+                    if (MODE == 0) {
+                        hi = ph[i] + tr * P.dil;
+                        wi = pw[i] + tc * P.dil;
+                        v = (tmv[p][i] >> tap) & 1u;      // bounds + hole (0 for rows past m_total)
+                        hi >>= pt.xup; wi >>= pt.xup;
+                        const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
+                        src[i] = pt.x + (static_cast<long long>(pn[i] * hp + (v ? hi : 0)) * wp + (v ? wi : 0)) * pt.cstride + chunk * 8;
+                    } else {
+                        const int th = ph[i] - tr * P.dil, tw = pw[i] - tc * P.dil;
+                        hi = th / P.stride; wi = tw / P.stride;
+                        v = v && th >= 0 && tw >= 0 && (hi * P.stride == th) && (wi * P.stride == tw) && hi < P.ho && wi < P.wo;
+                        src[i] = pt.x + (static_cast<long long>(pn[i] * P.ho + (v ? hi : 0)) * P.wo + (v ? wi : 0)) * pt.cstride + chunk * 8;
+                    }
+                    ok[i] = v;
+                }
+                const int nb = ((MODE == 0) ? pt.c : P.cout) / BLOCK_K;
+                for (int cb = 0; cb < nb; ++cb, ++kb) {
+                    const int s = kb % STAGES;
+                    const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
+                    if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 101)) { dead = true; break; }
+                    const uint32_t dst = sA + s * A_STAGE_BYTES + r0 * 128 + sw;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), src[i] + cb * BLOCK_K, ok[i]);
+                    ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
+                    ptx::mbar_arrive(bar_full_a + 8 * s);
+                }
+            }
+        }
+        ptx::cp_async_wait<0>();
+
+        // =========================== epilogue ===========================
+        if (!dead && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 102)) {
+            ptx::tc_fence_after();
+            const int row = warp * 32 + lane;
+            const int m = m0 + row;
+            const bool rvalid = m < P.m_total;
+            float inv = 0.f;
+            bool hole = false;
+            if (MODE == 0 && rvalid) {
+                const float s = P.msum[m];
+                hole = (s == 0.f) && !P.no_guard;
+                inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
+            }
+            int en = 0, eh = 0, ew = 0;
+            if (MODE == 1 && rvalid) {
+                en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
+            }
+            const int ncols_total = (MODE == 0) ? P.cout : P.cin;
+            bf16 *orow = P.out + static_cast<long long>(rvalid ? m : 0) * ncols_total + n0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+                ptx::tmem_ld_wait();
+                float scale = inv;
+                if (MODE == 1) {
+                    // dx = acc * input mask of the part this channel chunk belongs to
+                    scale = 1.f;
+                    const int ch = n0 + c0;
+                    for (int p = 0; p < P.nparts; ++p) {
+                        const TcPart &pt = P.parts[p];
+                        if (ch >= pt.choff && ch < pt.choff + pt.c && pt.mask != nullptr && rvalid)
+                            scale = pt.mask[(static_cast<long long>(en) * (P.h >> pt.mup) + (eh >> pt.mup)) * (P.w >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
+                    }
+                }
+                if (rvalid && n0 + c0 < ncols_total) {
+                    uint4 o[4];
+                    __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(o);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+                        if (MODE == 0) {
+                            const float b0 = P.bias ? P.bias[n0 + c0 + 2 * j] : 0.f;
+                            const float b1 = P.bias ? P.bias[n0 + c0 + 2 * j + 1] : 0.f;
+                            a = hole ? 0.f : a * scale + b0;
+                            b = hole ? 0.f : b * scale + b1;
+                        } else {
+                            a *= scale; b *= scale;
+                        }
+                        ob[j] = __floats2bfloat162_rn(a, b);
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = o[j];
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =========================== B producer: TMA weight tiles ===========================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
+                if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 103)) break;
+                ptx::mbar_arrive_expect_tx(bar_full_b + 8 * s, B_STAGE_BYTES);
+                ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &tmap_w, kb * BLOCK_K, n0, bar_full_b + 8 * s);
+            }
+        }
+    } else {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            bool dead = false;
+            for (int kb = 0; kb < num_kb && !dead; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t parity = (kb / STAGES) & 1;
+                if (!ptx::mbar_wait(bar_full_a + 8 * s, parity, P.abort_flag, 104) ||
+                    !ptx::mbar_wait(bar_full_b + 8 * s, parity, P.abort_flag, 105)) { dead = true; break; }
+                ptx::fence_proxy_async_smem();
+                ptx::tc_fence_after();
+                const uint64_t da = ptx::make_smem_desc(sA + s * A_STAGE_BYTES, 16, 1024);
+                const uint64_t db = ptx::make_smem_desc(sB + s * B_STAGE_BYTES, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k)       // +32 bytes per K=16 step inside the swizzle row
+                    ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                ptx::umma_commit(bar_empty + 8 * s);
+            }
+            if (!dead) ptx::umma_commit(bar_tmem_full);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<BLOCK_N>(tmem_base);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight gradient
+// -------------------------------------------------------------------------------------------------
+struct WgParams {
+    int n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil, ho, wo;
+    int m_total;              // n*ho*wo : the reduction (K) extent
+    int nparts;
+    TcPart parts[TC_MAX_PARTS];
+    int taps_per_cta;         // T
+    int tap_groups;
+    int ci_tiles;             // ceil(cin / 128)
+    int kb_per_split;
+    float *dw;                // [cout][taps][cin] fp32, pre-zeroed
+    int *abort_flag;
+};
+
+template <int BLOCK_N, int T, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant__ CUtensorMap tmap_dc) {
+    constexpr int B_STAGE_BYTES = BLOCK_N * 128;            // [64 px][BLOCK_N co] as BLOCK_N/64 blocks of 8 KB
+    constexpr int A_TAP_BYTES = 16384;                      // [64 px][128 ci] as 2 blocks of 8 KB
+    constexpr int A_STAGE = T * A_TAP_BYTES;
+    constexpr int TMEM_COLS = (T * BLOCK_N <= 64) ? 64 : (T * BLOCK_N <= 128) ? 128 : (T * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(T * BLOCK_N <= 512, "TMEM overflow");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
+    const uint32_t sA = smem_base;
+    const uint32_t sB = sA + STAGES * A_STAGE;
+    const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;
+    const uint32_t bar_full_a = sBar, bar_full_b = sBar + 8 * STAGES, bar_empty = sBar + 16 * STAGES;
+    const uint32_t bar_tmem_full = sBar + 24 * STAGES;
+    const uint32_t s_tmem_ptr = bar_tmem_full + 8;
+    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // blockIdx.x = ((co_tile * tap_groups) + tap_group) * ci_tiles + ci_tile ; blockIdx.y = K split
+    int bx = blockIdx.x;
+    const int ci_tile = bx % P.ci_tiles; bx /= P.ci_tiles;
+    const int tap_group = bx % P.tap_groups;
+    const int co_tile = bx / P.tap_groups;
+    const int taps = P.kh * P.kw;
+    const int tap0 = tap_group * T;
+    const int ntap = min(T, taps - tap0);
+    const int n0 = co_tile * BLOCK_N;
+    const int total_kb = (P.m_total + 63) / 64;
+    const int kb_begin = blockIdx.y * P.kb_per_split;
+    const int kb_end = min(total_kb, kb_begin + P.kb_per_split);
+    const int num_kb = max(0, kb_end - kb_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS);
+            ptx::mbar_init(bar_full_b + 8 * s, 1);
+            ptx::mbar_init(bar_empty + 8 * s, 1);
+        }
+        ptx::mbar_init(bar_tmem_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tmap_dc);
+    if (warp == 5) {
+        ptx::tmem_alloc<TMEM_COLS>(s_tmem_ptr);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    if (warp < 4) {
+        // ============ A producers: gather x rows (K = pixels) for each tap, 2 x 64-channel blocks ============
+        const int t = threadIdx.x;
+        const int chunk = t & 7, r0 = t >> 3;
+        const uint32_t sw = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);
+        // the two 64-channel blocks of this ci tile -> (part, channel offset inside the part)
+        int blk_part[2], blk_off[2];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            const int ch = ci_tile * 128 + hb * 64;
+            blk_part[hb] = -1; blk_off[hb] = 0;
+            for (int p = 0; p < P.nparts; ++p)
+                if (ch >= P.parts[p].choff && ch < P.parts[p].choff + P.parts[p].c) { blk_part[hb] = p; blk_off[hb] = ch - P.parts[p].choff; }
+        }
+        const int plane = P.ho * P.wo;
+        bool dead = false;
+        // tap-validity words are prefetched one k-block ahead so their latency hides behind the barrier wait
+        uint32_t tm_next[4][2];
+        auto load_tm = [&](int kb, uint32_t (&dst)[4][2]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = kb * 64 + r0 + 16 * i;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb)
+                    dst[i][hb] = (m < P.m_total && blk_part[hb] >= 0) ? __ldg(P.parts[blk_part[hb]].tapmask + m) : 0u;
+            }
+        };
+        if (num_kb > 0) load_tm(kb_begin, tm_next);
+        for (int it = 0; it < num_kb && !dead; ++it) {
+            const int kb = kb_begin + it;
+            const int s = it % STAGES;
+            const uint32_t parity = ((it / STAGES) & 1) ^ 1;
+            uint32_t tm_cur[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { tm_cur[i][0] = tm_next[i][0]; tm_cur[i][1] = tm_next[i][1]; }
+            if (it + 1 < num_kb) load_tm(kb + 1, tm_next);
+            if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 201)) { dead = true; break; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + 16 * i;
+                const int m = kb * 64 + r;
+                const bool rv = m < P.m_total;
+                const int mm = rv ? m : 0;
+                const int nn = mm / plane, rem = mm - nn * plane;
+                const int oh = rem / P.wo, ow = rem - oh * P.wo;
+                const uint32_t tm[2] = {tm_cur[i][0], tm_cur[i][1]};
+                for (int tl = 0; tl < ntap; ++tl) {
+                    const int tap = tap0 + tl;
+                    const int tr = tap / P.kw, tc = tap - tr * P.kw;
+                    const int hi = oh * P.stride - P.pad_h + tr * P.dil, wi = ow * P.stride - P.pad_w + tc * P.dil;
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        const bool v = (tm[hb] >> tap) & 1u;
+                        const int p = blk_part[hb] >= 0 ? blk_part[hb] : 0;
+                        const TcPart &pt = P.parts[p];
+                        const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
+                        const bf16 *src = pt.x + (static_cast<long long>(nn * hp + (v ? (hi >> pt.xup) : 0)) * wp + (v ? (wi >> pt.xup) : 0)) * pt.cstride + blk_off[hb] + chunk * 8;
+                        const uint32_t dst = sA + s * A_STAGE + tl * A_TAP_BYTES + hb * 8192 + r * 128 + sw;
+                        ptx::cp_async_16(dst, src, v);
+                    }
+                }
+            }
+            ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
+            ptx::mbar_arrive(bar_full_a + 8 * s);
+        }
+        ptx::cp_async_wait<0>();
+
+        // ============ epilogue: D[ci][co] per tap -> red.global.add into dw[co][tap][ci] ============
+        if (!dead && num_kb > 0 && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 202)) {
+            ptx::tc_fence_after();
+            const int row = warp * 32 + lane;
+            const int ci = ci_tile * 128 + row;
+            for (int tl = 0; tl < ntap; ++tl) {
+                const int tap = tap0 + tl;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + tl * BLOCK_N + c0, r);
+                    ptx::tmem_ld_wait();
+                    if (ci < P.cin) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = n0 + c0 + j;
+                            if (co < P.cout)
+                                atomicAdd(P.dw + (static_cast<long long>(co) * taps + tap) * P.cin + ci, __uint_as_float(r[j]));
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ============ B producer: dc tiles [64 px][BLOCK_N co] via TMA, BLOCK_N/64 boxes of {64 co, 64 px} ============
+        if (lane == 0) {
+            for (int it = 0; it < num_kb; ++it) {
+                const int kb = kb_begin + it;
+                const int s = it % STAGES;
+                const uint32_t parity = ((it / STAGES) & 1) ^ 1;
+                if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 203)) break;
+                ptx::mbar_arrive_expect_tx(bar_full_b + 8 * s, B_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                    ptx::tma_load_2d(sB + s * B_STAGE_BYTES + j * 8192, &tmap_dc, n0 + j * 64, kb * 64, bar_full_b + 8 * s);
+            }
+        }
+    } else {
+        // ============ MMA issuer: both operands MN-major ============
+        if (lane == 0 && num_kb > 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N, 1, 1);
+            bool dead = false;
+            for (int it = 0; it < num_kb && !dead; ++it) {
+                const int s = it % STAGES;
+                const uint32_t parity = (it / STAGES) & 1;
+                if (!ptx::mbar_wait(bar_full_a + 8 * s, parity, P.abort_flag, 204) ||
+                    !ptx::mbar_wait(bar_full_b + 8 * s, parity, P.abort_flag, 205)) { dead = true; break; }
+                ptx::fence_proxy_async_smem();
+                ptx::tc_fence_after();
+                for (int tl = 0; tl < ntap; ++tl) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {     // 16 pixels (2 atoms of 8 k-rows = 2048 bytes) per step
+                        const uint64_t da = ptx::make_smem_desc(sA + s * A_STAGE + tl * A_TAP_BYTES + k * 2048, 8192, 1024);
+                        const uint64_t db = ptx::make_smem_desc(sB + s * B_STAGE_BYTES + k * 2048, 8192, 1024);
+                        ptx::umma_bf16(tmem_base + tl * BLOCK_N, da, db, idesc, (it | k) != 0);
+                    }
+                }
+                ptx::umma_commit(bar_empty + 8 * s);
+            }
+            if (!dead) ptx::umma_commit(bar_tmem_full);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// tap-validity bitmasks: bit t of tapmask[p][m] = tap t of output pixel m is in bounds and not a hole
+// -------------------------------------------------------------------------------------------------
+struct TapMaskParams {
+    int n, h, w, kh, kw, stride, pad_h, pad_w, dil, ho, wo, m_total, nparts;
+    const uint8_t *mask[TC_MAX_PARTS];
+    int mup[TC_MAX_PARTS];
+    uint32_t *out;   // [nparts][m_total]
+};
+
+__global__ void tapmask_kernel(const TapMaskParams P) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.m_total) return;
+    const int plane = P.ho * P.wo;
+    const int nn = m / plane, rem = m - nn * plane, oh = rem / P.wo, ow = rem - oh * P.wo;
+    for (int p = 0; p < P.nparts; ++p) {
+        uint32_t bits = 0;
+        int tap = 0;
+        for (int tr = 0; tr < P.kh; ++tr)
+            for (int tc = 0; tc < P.kw; ++tc, ++tap) {
+                const int hi = oh * P.stride - P.pad_h + tr * P.dil, wi = ow * P.stride - P.pad_w + tc * P.dil;
+                bool v = hi >= 0 && hi < P.h && wi >= 0 && wi < P.w;
+                if (v && P.mask[p]) {
+                    const int u = P.mup[p];
+                    v = P.mask[p][(static_cast<long long>(nn) * (P.h >> u) + (hi >> u)) * (P.w >> u) + (wi >> u)] != 0;
+                }
+                bits |= (v ? 1u : 0u) << tap;
+            }
+        P.out[static_cast<long long>(p) * P.m_total + m] = bits;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D bf16 row-major [rows][cols] tensor, box {64 cols (128 bytes), box_rows}, SWIZZLE_128B
+int make_tmap_2d(CUtensorMap *tm, const void *base, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    PCB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d base=%p", (int)r, rows,
+              cols, box_rows, base);
+    return 0;
+}
+
+int *abort_flag_ptr() {
+    static int *flag = nullptr;
+    if (!flag) {
+        if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(flag, 0, sizeof(int));
+    }
+    return flag;
+}
+
+bool parts_ok_for_tc(const pcb_conv *c) {
+    if (c->nparts < 1 || c->nparts > TC_MAX_PARTS) return false;
+    for (int p = 0; p < c->nparts; ++p) {
+        const pcb_part &pt = c->parts[p];
+        if (pt.c % 64 != 0 || pt.x_cstride % 8 != 0) return false;
+        if (pt.x && (reinterpret_cast<uintptr_t>(pt.x) & 15)) return false;
+    }
+    return true;
+}
+
+bool common_ok(const pcb_conv *c) {
+    return c->dtype == PCB_BF16 && c->groups == 1 && c->kh * c->kw <= 32 && c->cin % 64 == 0 && c->cout % 64 == 0 &&
+           parts_ok_for_tc(c);
+}
+
+void fill_parts(const pcb_conv *c, TcPart *out, const uint32_t *tapmask, long long m_total) {
+    int off = 0;
+    for (int p = 0; p < c->nparts; ++p) {
+        out[p].x = static_cast<const bf16 *>(c->parts[p].x);
+        out[p].tapmask = tapmask ? tapmask + static_cast<long long>(p) * m_total : nullptr;
+        out[p].mask = c->parts[p].mask;
+        out[p].c = c->parts[p].c;
+        out[p].choff = off;
+        out[p].cstride = c->parts[p].x_cstride;
+        out[p].xup = c->parts[p].x_up;
+        out[p].mup = c->parts[p].mask_up;
+        off += c->parts[p].c;
+    }
+}
+
+int launch_tapmask(const pcb_conv *c, uint32_t *out, cudaStream_t st) {
+    TapMaskParams T;
+    T.n = c->n; T.h = c->h; T.w = c->w; T.kh = c->kh; T.kw = c->kw; T.stride = c->stride; T.pad_h = c->pad_h;
+    T.pad_w = c->pad_w; T.dil = c->dil; T.ho = c->ho; T.wo = c->wo; T.m_total = c->n * c->ho * c->wo; T.nparts = c->nparts;
+    for (int p = 0; p < c->nparts; ++p) { T.mask[p] = c->parts[p].mask; T.mup[p] = c->parts[p].mask_up; }
+    T.out = out;
+    tapmask_kernel<<<(T.m_total + 255) / 256, 256, 0, st>>>(T);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BLOCK_N, int STAGES, int MODE>
+int launch_fwd(const TcParams &P, const CUtensorMap &tm, int ncols, cudaStream_t st) {
+    constexpr size_t smem = 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
+    auto kern = pconv_tc_kernel<BLOCK_N, STAGES, MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
+    kern<<<grid, TC_THREADS, smem, st>>>(P, tm);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// ---- eligibility ---------------------------------------------------------------------------------
+bool pcb_tc_forward_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
+bool pcb_tc_dgrad_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
+bool pcb_tc_wgrad_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
+
+size_t pcb_tc_forward_workspace(const pcb_conv *c) {
+    return static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint32_t);
+}
+
+int pcb_tc_forward_ws(const pcb_conv *c, const void *w, const float *bias, void *y, const float *msum, uint32_t *tapmask,
+                      cudaStream_t st) {
+    int *flag = abort_flag_ptr();
+    PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
+    const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
+    PCB_CHECK(m_total < (1ll << 31), "problem too large");
+    if (int rc = launch_tapmask(c, tapmask, st)) return rc;
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
+    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = (int)m_total;
+    P.nparts = c->nparts; P.no_guard = c->no_guard;
+    fill_parts(c, P.parts, tapmask, m_total);
+    P.bias = bias; P.msum = msum; P.out = static_cast<bf16 *>(y); P.abort_flag = flag;
+    CUtensorMap tm;
+    const int bn = (c->cout % 128 == 0) ? 128 : 64;
+    if (int rc = make_tmap_2d(&tm, w, c->cout, static_cast<long long>(c->kh) * c->kw * c->cin, bn)) return rc;
+    if (bn == 128) return launch_fwd<128, 3, 0>(P, tm, c->cout, st);
+    return launch_fwd<64, 4, 0>(P, tm, c->cout, st);
+}
+
+int pcb_tc_dgrad(const pcb_conv *c, const void *dc, const void *wt, void *dx, cudaStream_t st) {
+    int *flag = abort_flag_ptr();
+    PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
+    const long long m_total = static_cast<long long>(c->n) * c->h * c->w;
+    PCB_CHECK(m_total < (1ll << 31), "problem too large");
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
+    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = (int)m_total;
+    P.nparts = c->nparts;
+    fill_parts(c, P.parts, nullptr, 0);
+    // the gather source of dgrad is dc itself: overwrite part 0's x fields (mask/choff/c of the parts stay for the epilogue)
+    P.parts[0].x = static_cast<const bf16 *>(dc);
+    P.parts[0].cstride = c->cout;
+    P.out = static_cast<bf16 *>(dx); P.abort_flag = flag;
+    CUtensorMap tm;
+    const int bn = (c->cin % 128 == 0) ? 128 : 64;
+    if (int rc = make_tmap_2d(&tm, wt, c->cin, static_cast<long long>(c->kh) * c->kw * c->cout, bn)) return rc;
+    if (bn == 128) return launch_fwd<128, 3, 1>(P, tm, c->cin, st);
+    return launch_fwd<64, 4, 1>(P, tm, c->cin, st);
+}
+
+size_t pcb_tc_wgrad_workspace(const pcb_conv *c) { return pcb_tc_forward_workspace(c); }
+
+template <int BLOCK_N, int T, int STAGES>
+static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream_t st) {
+    constexpr size_t smem = 1024 + STAGES * (T * 16384 + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
+    auto kern = pconv_tc_wgrad_kernel<BLOCK_N, T, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int taps = P.kh * P.kw;
+    P.taps_per_cta = T;
+    P.tap_groups = (taps + T - 1) / T;
+    P.ci_tiles = (P.cin + 127) / 128;
+    const int co_tiles = cout / BLOCK_N;
+    const int base_ctas = co_tiles * P.tap_groups * P.ci_tiles;
+    const int total_kb = (P.m_total + 63) / 64;
+    int splits = (4 * pcb_num_sms() + base_ctas - 1) / base_ctas;      // aim at ~4 CTAs per SM worth of work
+    splits = max(1, min(splits, total_kb));
+    splits = min(splits, 65535);
+    P.kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
+    dim3 grid(base_ctas, splits);
+    kern<<<grid, TC_THREADS, smem, st>>>(P, tm);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+int pcb_tc_wgrad(const pcb_conv *c, const void *dc, float *dw, void *workspace, cudaStream_t st) {
+    int *flag = abort_flag_ptr();
+    PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
+    PCB_CHECK(workspace != nullptr, "pcb_tc_wgrad: workspace required");
+    const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
+    PCB_CHECK(m_total < (1ll << 31), "problem too large");
+    uint32_t *tapmask = static_cast<uint32_t *>(workspace);
+    if (int rc = launch_tapmask(c, tapmask, st)) return rc;
+    const size_t dw_bytes = sizeof(float) * c->cout * c->kh * c->kw * c->cin;
+    PCB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, st));
+    WgParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
+    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = (int)m_total;
+    P.nparts = c->nparts;
+    fill_parts(c, P.parts, tapmask, m_total);
+    P.dw = dw; P.abort_flag = flag;
+    CUtensorMap tm;
+    if (int rc = make_tmap_2d(&tm, dc, m_total, c->cout, 64)) return rc;
+    if (c->cout % 256 == 0) return launch_wgrad<256, 2, 3>(P, tm, c->cout, st);
+    if (c->cout % 128 == 0) return launch_wgrad<128, 3, 3>(P, tm, c->cout, st);
+    return launch_wgrad<64, 3, 3>(P, tm, c->cout, st);
+}
+
+// abort flag query used by api.cu after synchronising debug runs
+int pcb_tc_read_abort_flag(int *value) {
+    int *flag = abort_flag_ptr();
+    PCB_CHECK(flag != nullptr, "no abort flag");
+    PCB_CUDA(cudaMemcpy(value, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*value != 0) cudaMemset(flag, 0, sizeof(int));
+    return 0;
+}

@@ -1,0 +1,610 @@
+// elementwise.cu -- the HBM-bound companions of the convolution: BatchNorm statistics / apply (+activation,
+// +residual), their backward, the renormalisation backward, nearest-upsample + channel concat, mask format
+// conversion, weight re-layout, L1-mean loss and SGD.  All NHWC, 16/32-byte vector accesses, one pass each.
+#include "pcb_common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int ew_grid(long long work_items, int per_block) {
+    long long b = (work_items + per_block - 1) / per_block;
+    const long long cap = 16ll * pcb_num_sms();
+    return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel reductions over an NHWC tensor viewed as [count][c]; c % 8 == 0, c <= 2048.
+// Thread layout: tid -> (row-in-block r = tid / cv, channel vector v = tid % cv), cv = c / 8.
+// F(row, v, vals...) is evaluated per 8-vector; NRED fp32 partials per channel are block-reduced through
+// shared memory and flushed with fp64 atomics.
+// ---------------------------------------------------------------------------------------------
+template <int NRED>
+__device__ __forceinline__ void block_flush(float (&acc)[NRED][8], int cv, int rpb, int r, int v, double *const (&out)[NRED]) {
+    __shared__ float s_red[EW_THREADS][8];
+    for (int q = 0; q < NRED; ++q) {
+        __syncthreads();
+        if (r < rpb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_red[threadIdx.x][j] = acc[q][j];
+        }
+        __syncthreads();
+        if (r == 0 && v < cv) {
+            float tot[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tot[j] = 0.f;
+            for (int rr = 0; rr < rpb; ++rr)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tot[j] += s_red[rr * cv + v][j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(out[q] + v * 8 + j, static_cast<double>(tot[j]));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const T *__restrict__ x, long long count, int c, double *sum, double *sqsum) {
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    if (r < rpb) {
+        for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
+            float f[8];
+            Vec8<T>::load(x + row * c + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] += f[j] * f[j]; }
+        }
+    }
+    double *const outs[2] = {sum, sqsum};
+    block_flush<2>(acc, cv, rpb, r, v, outs);
+}
+
+// scalar fallback (any c): one block-wide pass, smem float atomics per channel (tiny tensors only)
+template <typename T>
+__global__ void bn_stats_scalar_kernel(const T *__restrict__ x, long long count, int c, double *sum, double *sqsum) {
+    for (int ch = blockIdx.x; ch < c; ch += gridDim.x) {
+        float a = 0.f, b = 0.f;
+        for (long long row = threadIdx.x; row < count; row += blockDim.x) {
+            const float f = to_f32(x[row * c + ch]);
+            a += f; b += f * f;
+        }
+        __shared__ float sa[32], sb[32];
+        a = warp_sum(a); b = warp_sum(b);
+        if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ta = 0, tb = 0;
+            for (int i = 0; i < (blockDim.x >> 5); ++i) { ta += sa[i]; tb += sb[i]; }
+            atomicAdd(sum + ch, ta); atomicAdd(sqsum + ch, tb);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void bn_finalize_kernel(const double *sum, const double *sqsum, long long count, int c, const float *gamma,
+                                   const float *beta, float *running_mean, float *running_var, long long *nbt, float momentum,
+                                   float eps, int training, float *scale, float *shift, float *save_mean, float *save_invstd) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch == 0 && training && nbt) *nbt += 1;
+    if (ch >= c) return;
+    float mean, invstd;
+    if (training) {
+        const double m = sum[ch] / static_cast<double>(count);
+        double var = sqsum[ch] / static_cast<double>(count) - m * m;     // biased (normalisation)
+        if (var < 0) var = 0;
+        mean = static_cast<float>(m);
+        invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        if (running_mean) {
+            const double unbiased = count > 1 ? var * static_cast<double>(count) / static_cast<double>(count - 1) : var;
+            running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+            running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+        }
+    } else {
+        mean = running_mean[ch];
+        invstd = 1.0f / sqrtf(running_var[ch] + eps);
+    }
+    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    scale[ch] = g * invstd;
+    shift[ch] = b - mean * g * invstd;
+    if (save_mean) save_mean[ch] = mean;
+    if (save_invstd) save_invstd[ch] = invstd;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const T *__restrict__ x, long long nvec, int c, const float *__restrict__ scale,
+                                                                const float *__restrict__ shift, int act, float slope,
+                                                                const T *__restrict__ residual, T *__restrict__ y) {
+    const int cv = c >> 3;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % cv) * 8;
+        float f[8], rres[8];
+        Vec8<T>::load(x + i * 8, f);
+        if (residual) Vec8<T>::load(residual + i * 8, rres);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float z = scale ? f[j] * scale[ch + j] + shift[ch + j] : f[j];
+            z = apply_act(z, act, slope);
+            if (residual) z += rres[j];
+            f[j] = z;
+        }
+        Vec8<T>::store(y + i * 8, f);
+    }
+}
+
+template <typename T>
+__global__ void bn_act_fwd_scalar_kernel(const T *x, long long numel, int c, const float *scale, const float *shift, int act,
+                                         float slope, const T *residual, T *y) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % c);
+        float z = to_f32(x[i]);
+        if (scale) z = z * scale[ch] + shift[ch];
+        z = apply_act(z, act, slope);
+        if (residual) z += to_f32(residual[i]);
+        y[i] = from_f32<T>(z);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
+                                                                   const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                   const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                                   int act, float slope, double *sum_g, double *sum_gx) {
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    if (r < rpb) {
+        float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = scale ? scale[v * 8 + j] : 1.f; sh[j] = shift ? shift[v * 8 + j] : 0.f;
+            mu[j] = mean ? mean[v * 8 + j] : 0.f; is[j] = invstd ? invstd[v * 8 + j] : 1.f;
+        }
+        for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
+            float g[8], f[8];
+            Vec8<T>::load(gy + row * c + v * 8, g);
+            Vec8<T>::load(x + row * c + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+                acc[0][j] += gz;
+                acc[1][j] += gz * (f[j] - mu[j]) * is[j];
+            }
+        }
+    }
+    double *const outs[2] = {sum_g, sum_gx};
+    block_flush<2>(acc, cv, rpb, r, v, outs);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long nvec, long long count, int c,
+                                                                  const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                  const float *__restrict__ mean, const float *__restrict__ invstd, int act,
+                                                                  float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
+                                                                  int training, T *__restrict__ dx) {
+    const int cv = c >> 3;
+    const float inv_count = 1.0f / static_cast<float>(count);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % cv) * 8;
+        float g[8], f[8];
+        Vec8<T>::load(gy + i * 8, g);
+        Vec8<T>::load(x + i * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float sc = scale ? scale[ch + j] : 1.f, sh = shift ? shift[ch + j] : 0.f;
+            const float gz = g[j] * act_grad(f[j] * sc + sh, act, slope);
+            float d;
+            if (!scale) d = gz;
+            else if (!training) d = sc * gz;
+            else {
+                const float xhat = (f[j] - mean[ch + j]) * invstd[ch + j];
+                d = sc * (gz - static_cast<float>(sum_g[ch + j]) * inv_count - xhat * static_cast<float>(sum_gx[ch + j]) * inv_count);
+            }
+            f[j] = d;
+        }
+        Vec8<T>::store(dx + i * 8, f);
+    }
+}
+
+__global__ void bn_param_grad_kernel(const double *sum_g, const double *sum_gx, int c, float *dgamma, float *dbeta) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    if (dgamma) dgamma[ch] = static_cast<float>(sum_gx[ch]);
+    if (dbeta) dbeta[ch] = static_cast<float>(sum_g[ch]);
+}
+
+// dc = dy * [s>0]/s ; dbias += sum dy*[s>0].  msum is [mg][count]; group of channel ch = ch / (c/mg).
+template <typename T>
+__global__ void renorm_bwd_kernel(const T *__restrict__ dy, const float *__restrict__ msum, long long count, int c, int mg, int no_guard,
+                                  T *__restrict__ dc, float *dbias) {
+    // scalar-general: thread per element (channels fastest) with a per-block smem bias reduction
+    extern __shared__ float s_db[];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) s_db[i] = 0.f;
+    __syncthreads();
+    const int cog = c / mg;
+    const long long numel = count * c;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / c;
+        const int ch = static_cast<int>(i - row * c);
+        const float s = msum[(mg == 1 ? 0 : (ch / cog)) * count + row];
+        const float g = to_f32(dy[i]);
+        float d, gb;
+        if (no_guard) { d = g / s; gb = g; }
+        else { const bool hole = (s == 0.f); d = hole ? 0.f : g / s; gb = hole ? 0.f : g; }
+        dc[i] = from_f32<T>(d);
+        if (dbias) atomicAdd(&s_db[ch], gb);
+    }
+    __syncthreads();
+    if (dbias)
+        for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, s_db[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// concat (+ nearest 2x upsample) forward / backward
+// ---------------------------------------------------------------------------------------------
+struct CatPart { const void *x; int c, choff, cstride, up; };
+struct CatParams { int n, h, w, ctot, nparts; CatPart parts[PCB_MAX_PARTS]; };
+
+template <typename T, int VEC>
+__global__ void concat_fwd_kernel(const CatParams P, T *__restrict__ y) {
+    const long long cv = P.ctot / VEC;
+    const long long total = static_cast<long long>(P.n) * P.h * P.w * cv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = i / cv;
+        const int ch = static_cast<int>(i - pix * cv) * VEC;
+        int p = 0;
+        while (p + 1 < P.nparts && ch >= P.parts[p].choff + P.parts[p].c) ++p;
+        const CatPart &pt = P.parts[p];
+        const int ww = static_cast<int>(pix % P.w);
+        const long long t = pix / P.w;
+        const int hh = static_cast<int>(t % P.h), nn = static_cast<int>(t / P.h);
+        const T *src = static_cast<const T *>(pt.x) +
+                       (static_cast<long long>(nn * (P.h >> pt.up) + (hh >> pt.up)) * (P.w >> pt.up) + (ww >> pt.up)) * pt.cstride + (ch - pt.choff);
+        if (VEC == 8) {
+            if (sizeof(T) == 2) *reinterpret_cast<uint4 *>(y + i * 8) = *reinterpret_cast<const uint4 *>(src);
+            else { reinterpret_cast<float4 *>(y + i * 8)[0] = reinterpret_cast<const float4 *>(src)[0];
+                   reinterpret_cast<float4 *>(y + i * 8)[1] = reinterpret_cast<const float4 *>(src)[1]; }
+        } else {
+            y[i] = src[0];
+        }
+    }
+}
+
+// gx[n, h>>up, w>>up, c] = sum over the up x up block of gy[..., choff + c]
+template <typename T, int VEC>
+__global__ void concat_bwd_kernel(const T *__restrict__ gy, int n, int h, int w, int ctot, int choff, int c, int up, T *__restrict__ gx) {
+    const int hs = h >> up, ws = w >> up, f = 1 << up;
+    const long long cv = c / VEC;
+    const long long total = static_cast<long long>(n) * hs * ws * cv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = i / cv;
+        const int ch = static_cast<int>(i - pix * cv) * VEC;
+        const int ww = static_cast<int>(pix % ws);
+        const long long t = pix / ws;
+        const int hh = static_cast<int>(t % hs), nn = static_cast<int>(t / hs);
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        for (int dy = 0; dy < f; ++dy)
+            for (int dx = 0; dx < f; ++dx) {
+                const T *src = gy + (static_cast<long long>(nn * h + hh * f + dy) * w + ww * f + dx) * ctot + choff + ch;
+                if (VEC == 8) {
+                    float v[8];
+                    Vec8<T>::load(src, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                } else acc[0] += to_f32(src[0]);
+            }
+        if (VEC == 8) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = acc[j];
+            Vec8<T>::store(gx + i * 8, o);
+        } else gx[i] = from_f32<T>(acc[0]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// masks, weights, loss, optimiser
+// ---------------------------------------------------------------------------------------------
+__global__ void mask_from_dense_kernel(const float *__restrict__ m, int n, int c, long long hw, uint8_t *__restrict__ planes) {
+    const long long total = static_cast<long long>(n) * c * hw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i % hw;
+        const long long t = i / hw;
+        const int ch = static_cast<int>(t % c), nn = static_cast<int>(t / c);
+        planes[(static_cast<long long>(ch) * n + nn) * hw + p] = m[i] != 0.f ? 1 : 0;
+    }
+}
+
+__global__ void mask_to_dense_kernel(const uint8_t *__restrict__ plane, int n, int h, int w, int up, float *__restrict__ dst, int ctot, int c0, int c) {
+    const long long hw = static_cast<long long>(h) * w;
+    const long long total = static_cast<long long>(n) * c * hw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i % hw;
+        const long long t = i / hw;
+        const int ch = static_cast<int>(t % c), nn = static_cast<int>(t / c);
+        const int hh = static_cast<int>(p / w), ww = static_cast<int>(p - static_cast<long long>(hh) * w);
+        const uint8_t v = plane[(static_cast<long long>(nn) * (h >> up) + (hh >> up)) * (w >> up) + (ww >> up)];
+        dst[(static_cast<long long>(nn) * ctot + c0 + ch) * hw + p] = v ? 1.f : 0.f;
+    }
+}
+
+template <typename T>
+__global__ void weight_prepare_kernel(const float *__restrict__ wm, int cout, int taps, int cig, T *__restrict__ w_krsc, T *__restrict__ w_crsk) {
+    const long long total = static_cast<long long>(cout) * taps * cig;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = wm[i];
+        if (w_krsc) w_krsc[i] = from_f32<T>(v);
+        if (w_crsk) {
+            const int ci = static_cast<int>(i % cig);
+            const long long t = i / cig;
+            const int tap = static_cast<int>(t % taps), co = static_cast<int>(t / taps);
+            w_crsk[(static_cast<long long>(ci) * taps + tap) * cout + co] = from_f32<T>(v);
+        }
+    }
+}
+
+template <typename T>
+__global__ void l1_sum_kernel(const T *__restrict__ x, long long numel, double *scratch) {
+    float a = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        a += fabsf(to_f32(x[i]));
+    a = warp_sum(a);
+    __shared__ float s[32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
+        atomicAdd(scratch, t);
+    }
+}
+__global__ void l1_finish_kernel(const double *scratch, long long numel, float *loss) { *loss = static_cast<float>(*scratch / static_cast<double>(numel)); }
+
+template <typename T>
+__global__ void l1_bwd_kernel(const T *__restrict__ x, long long numel, float gscale, T *__restrict__ gx) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = to_f32(x[i]);
+        gx[i] = from_f32<T>(v > 0.f ? gscale : (v < 0.f ? -gscale : 0.f));
+    }
+}
+
+__global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, long long numel, float lr, float mom,
+                           float wd, int nesterov, int first) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float d = g[i] + wd * p[i];
+        if (mom != 0.f) {
+            const float b = first ? d : mom * buf[i] + d;
+            buf[i] = b;
+            d = nesterov ? d + mom * b : b;
+        }
+        p[i] -= lr * d;
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_stats(const void *x, int dtype, long long count, int c, double *sum, double *sqsum, pcb_stream_t stream) {
+    PCB_CHECK(x && sum && sqsum && count > 0 && c > 0, "pcb_bn_stats: bad arguments");
+    PCB_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * c, ST));
+    PCB_CUDA(cudaMemsetAsync(sqsum, 0, sizeof(double) * c, ST));
+    if (c % 8 == 0 && c <= 2048) {
+        const int rpb = EW_THREADS / (c / 8);
+        const int grid = ew_grid(count, rpb * 16);
+        if (dtype == PCB_BF16) bn_stats_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sum, sqsum);
+        else bn_stats_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sum, sqsum);
+    } else {
+        if (dtype == PCB_BF16) bn_stats_scalar_kernel<bf16><<<min(c, 1024), 256, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sum, sqsum);
+        else bn_stats_scalar_kernel<float><<<min(c, 1024), 256, 0, ST>>>(static_cast<const float *>(x), count, c, sum, sqsum);
+    }
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_finalize(const double *sum, const double *sqsum, long long count, int c, const float *gamma, const float *beta,
+                               float *running_mean, float *running_var, long long *num_batches_tracked, float momentum, float eps,
+                               int training, float *scale, float *shift, float *save_mean, float *save_invstd, pcb_stream_t stream) {
+    PCB_CHECK(scale && shift && c > 0, "pcb_bn_finalize: bad arguments");
+    PCB_CHECK(training ? (sum && sqsum && count > 0) : (running_mean && running_var), "pcb_bn_finalize: missing statistics");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sum, sqsum, count, c, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                                       momentum, eps, training, scale, shift, save_mean, save_invstd);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_forward(const void *x, int dtype, long long count, int c, const float *scale, const float *shift, int act,
+                                  float slope, const void *residual, void *y, pcb_stream_t stream) {
+    PCB_CHECK(x && y && count > 0 && c > 0 && ((scale == nullptr) == (shift == nullptr)), "pcb_bn_act_forward: bad arguments");
+    const long long numel = count * c;
+    if (c % 8 == 0) {
+        const int grid = ew_grid(numel / 8, EW_THREADS * 4);
+        if (dtype == PCB_BF16) bn_act_fwd_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), numel / 8, c, scale, shift, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y));
+        else bn_act_fwd_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), numel / 8, c, scale, shift, act, slope, static_cast<const float *>(residual), static_cast<float *>(y));
+    } else {
+        const int grid = ew_grid(numel, EW_THREADS * 8);
+        if (dtype == PCB_BF16) bn_act_fwd_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), numel, c, scale, shift, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y));
+        else bn_act_fwd_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), numel, c, scale, shift, act, slope, static_cast<const float *>(residual), static_cast<float *>(y));
+    }
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                          const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                          double *sum_g, double *sum_gx, pcb_stream_t stream) {
+    PCB_CHECK(gy && x && sum_g && sum_gx && count > 0, "pcb_bn_act_backward_reduce: bad arguments");
+    PCB_CHECK(c % 8 == 0 && c <= 2048, "pcb_bn_act_backward_reduce: channels must be a multiple of 8 and <= 2048 (got %d)", c);
+    PCB_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(double) * c, ST));
+    PCB_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(double) * c, ST));
+    const int rpb = EW_THREADS / (c / 8);
+    const int grid = ew_grid(count, rpb * 16);
+    if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
+    else bn_bwd_reduce_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                         const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                         const double *sum_g, const double *sum_gx, int training, void *dx, float *dgamma, float *dbeta,
+                                         pcb_stream_t stream) {
+    PCB_CHECK(gy && x && dx && count > 0, "pcb_bn_act_backward_apply: bad arguments");
+    PCB_CHECK(c % 8 == 0, "pcb_bn_act_backward_apply: channels must be a multiple of 8 (got %d)", c);
+    PCB_CHECK(!(scale && training) || (mean && invstd && sum_g && sum_gx), "pcb_bn_act_backward_apply: training needs statistics");
+    const long long nvec = count * c / 8;
+    const int grid = ew_grid(nvec, EW_THREADS * 4);
+    if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
+    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
+    PCB_LAUNCH_CHECK();
+    if ((dgamma || dbeta) && sum_g && sum_gx) {
+        bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sum_g, sum_gx, c, dgamma, dbeta);
+        PCB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, const float *msum, void *dc, float *dbias, pcb_stream_t stream) {
+    PCB_CHECK(c && dy && msum && dc, "pcb_pconv_renorm_backward: bad arguments");
+    const long long count = static_cast<long long>(c->n) * c->ho * c->wo;
+    const int mg = (c->groups > 1 && !c->same_holes) ? c->groups : 1;
+    if (dbias) PCB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, ST));
+    const int grid = ew_grid(count * c->cout, EW_THREADS * 8);
+    const size_t smem = sizeof(float) * c->cout;
+    if (c->dtype == PCB_BF16) renorm_bwd_kernel<bf16><<<grid, EW_THREADS, smem, ST>>>(static_cast<const bf16 *>(dy), msum, count, c->cout, mg, c->no_guard, static_cast<bf16 *>(dc), dbias);
+    else renorm_bwd_kernel<float><<<grid, EW_THREADS, smem, ST>>>(static_cast<const float *>(dy), msum, count, c->cout, mg, c->no_guard, static_cast<float *>(dc), dbias);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_concat_forward(const pcb_part *parts, int nparts, int dtype, int n, int h, int w, void *y, pcb_stream_t stream) {
+    PCB_CHECK(parts && y && nparts >= 1 && nparts <= PCB_MAX_PARTS, "pcb_concat_forward: bad arguments");
+    CatParams P;
+    P.n = n; P.h = h; P.w = w; P.nparts = nparts;
+    int off = 0;
+    bool vec = true;
+    for (int p = 0; p < nparts; ++p) {
+        P.parts[p].x = parts[p].x; P.parts[p].c = parts[p].c; P.parts[p].choff = off; P.parts[p].cstride = parts[p].x_cstride;
+        P.parts[p].up = parts[p].x_up;
+        PCB_CHECK(parts[p].x != nullptr, "pcb_concat_forward: null part");
+        PCB_CHECK(parts[p].x_up == 0 || (h % 2 == 0 && w % 2 == 0), "pcb_concat_forward: upsampled part needs even h, w");
+        if (parts[p].c % 8 || off % 8 || parts[p].x_cstride % 8 || (reinterpret_cast<uintptr_t>(parts[p].x) & (dtype == PCB_BF16 ? 15 : 31))) vec = false;
+        off += parts[p].c;
+    }
+    P.ctot = off;
+    const long long numel = static_cast<long long>(n) * h * w * off;
+    if (vec) {
+        const int grid = ew_grid(numel / 8, EW_THREADS * 4);
+        if (dtype == PCB_BF16) concat_fwd_kernel<bf16, 8><<<grid, EW_THREADS, 0, ST>>>(P, static_cast<bf16 *>(y));
+        else concat_fwd_kernel<float, 8><<<grid, EW_THREADS, 0, ST>>>(P, static_cast<float *>(y));
+    } else {
+        const int grid = ew_grid(numel, EW_THREADS * 8);
+        if (dtype == PCB_BF16) concat_fwd_kernel<bf16, 1><<<grid, EW_THREADS, 0, ST>>>(P, static_cast<bf16 *>(y));
+        else concat_fwd_kernel<float, 1><<<grid, EW_THREADS, 0, ST>>>(P, static_cast<float *>(y));
+    }
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_concat_backward(const void *gy, const int32_t *c, const int32_t *up, int nparts, int dtype, int n, int h, int w,
+                                   void *const *gx, pcb_stream_t stream) {
+    PCB_CHECK(gy && c && up && gx && nparts >= 1 && nparts <= PCB_MAX_PARTS, "pcb_concat_backward: bad arguments");
+    int ctot = 0;
+    for (int p = 0; p < nparts; ++p) ctot += c[p];
+    int off = 0;
+    for (int p = 0; p < nparts; ++p) {
+        if (gx[p]) {
+            const bool vec = (c[p] % 8 == 0) && (off % 8 == 0) && (ctot % 8 == 0);
+            const long long numel = static_cast<long long>(n) * (h >> up[p]) * (w >> up[p]) * c[p];
+            if (vec) {
+                const int grid = ew_grid(numel / 8, EW_THREADS * 4);
+                if (dtype == PCB_BF16) concat_bwd_kernel<bf16, 8><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), n, h, w, ctot, off, c[p], up[p], static_cast<bf16 *>(gx[p]));
+                else concat_bwd_kernel<float, 8><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), n, h, w, ctot, off, c[p], up[p], static_cast<float *>(gx[p]));
+            } else {
+                const int grid = ew_grid(numel, EW_THREADS * 8);
+                if (dtype == PCB_BF16) concat_bwd_kernel<bf16, 1><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), n, h, w, ctot, off, c[p], up[p], static_cast<bf16 *>(gx[p]));
+                else concat_bwd_kernel<float, 1><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), n, h, w, ctot, off, c[p], up[p], static_cast<float *>(gx[p]));
+            }
+            PCB_LAUNCH_CHECK();
+        }
+        off += c[p];
+    }
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_upsample2x_forward(const void *x, int dtype, int n, int h, int w, int c, void *y, pcb_stream_t stream) {
+    pcb_part p;
+    p.x = x; p.mask = nullptr; p.c = c; p.x_cstride = c; p.x_up = 1; p.mask_up = 0;
+    return pcb_concat_forward(&p, 1, dtype, n, 2 * h, 2 * w, y, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_upsample2x_backward(const void *gy, int dtype, int n, int h, int w, int c, void *gx, pcb_stream_t stream) {
+    const int32_t cc = c, up = 1;
+    void *g = gx;
+    return pcb_concat_backward(gy, &cc, &up, 1, dtype, n, 2 * h, 2 * w, &g, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_mask_planes_from_dense(const float *mask_nchw, int n, int c, int h, int w, uint8_t *planes, pcb_stream_t stream) {
+    PCB_CHECK(mask_nchw && planes && n > 0 && c > 0, "pcb_mask_planes_from_dense: bad arguments");
+    const long long total = static_cast<long long>(n) * c * h * w;
+    mask_from_dense_kernel<<<ew_grid(total, EW_THREADS * 4), EW_THREADS, 0, ST>>>(mask_nchw, n, c, static_cast<long long>(h) * w, planes);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_mask_plane_to_dense(const uint8_t *plane, int n, int h, int w, int up, float *dst_nchw, int ctot, int c0, int c,
+                                       pcb_stream_t stream) {
+    PCB_CHECK(plane && dst_nchw && c0 >= 0 && c0 + c <= ctot, "pcb_mask_plane_to_dense: bad arguments");
+    const long long total = static_cast<long long>(n) * c * h * w;
+    mask_to_dense_kernel<<<ew_grid(total, EW_THREADS * 4), EW_THREADS, 0, ST>>>(plane, n, h, w, up, dst_nchw, ctot, c0, c);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_weight_prepare(const float *w_master_krsc, int cout, int kh, int kw, int cig, int dtype, void *w_krsc, void *w_crsk,
+                                  pcb_stream_t stream) {
+    PCB_CHECK(w_master_krsc && (w_krsc || w_crsk), "pcb_weight_prepare: bad arguments");
+    const long long total = static_cast<long long>(cout) * kh * kw * cig;
+    const int grid = ew_grid(total, EW_THREADS * 4);
+    if (dtype == PCB_BF16) weight_prepare_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(w_master_krsc, cout, kh * kw, cig, static_cast<bf16 *>(w_krsc), static_cast<bf16 *>(w_crsk));
+    else weight_prepare_kernel<float><<<grid, EW_THREADS, 0, ST>>>(w_master_krsc, cout, kh * kw, cig, static_cast<float *>(w_krsc), static_cast<float *>(w_crsk));
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_l1_mean_forward(const void *x, int dtype, long long numel, float *loss, double *scratch, pcb_stream_t stream) {
+    PCB_CHECK(x && loss && scratch && numel > 0, "pcb_l1_mean_forward: bad arguments");
+    PCB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), ST));
+    const int grid = ew_grid(numel, EW_THREADS * 16);
+    if (dtype == PCB_BF16) l1_sum_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), numel, scratch);
+    else l1_sum_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), numel, scratch);
+    PCB_LAUNCH_CHECK();
+    l1_finish_kernel<<<1, 1, 0, ST>>>(scratch, numel, loss);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_l1_mean_backward(const void *x, int dtype, long long numel, float gscale, void *gx, pcb_stream_t stream) {
+    PCB_CHECK(x && gx && numel > 0, "pcb_l1_mean_backward: bad arguments");
+    const int grid = ew_grid(numel, EW_THREADS * 8);
+    if (dtype == PCB_BF16) l1_bwd_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), numel, gscale, static_cast<bf16 *>(gx));
+    else l1_bwd_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), numel, gscale, static_cast<float *>(gx));
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_sgd_step(float *param, const float *grad, float *momentum_buf, long long numel, float lr, float momentum,
+                            float weight_decay, int nesterov, int first_step, pcb_stream_t stream) {
+    PCB_CHECK(param && grad && numel > 0 && (momentum == 0.f || momentum_buf), "pcb_sgd_step: bad arguments");
+    sgd_kernel<<<ew_grid(numel, EW_THREADS * 8), EW_THREADS, 0, ST>>>(param, grad, momentum_buf, numel, lr, momentum, weight_decay, nesterov, first_step);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
