@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- PartialConv U-Net (ImageFillOrigin) 512x512 images/sec, forward + backward (+ SGD update).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).  Workload = BASELINE.json configs[2] ("image_inpainting.py PartialConv UNet
+@512x512 batch=8, 1xB200 fwd+bwd bf16"), the configuration the headline metric is quoted on; weak scaling
+(batch 8 per GPU, gradients all-reduced over NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PartialConv UNet 512x512 images/sec (fwd+bwd)"
+PER_GPU_BATCH = 8
+HW = 512
+FWD_GFLOP_PER_IMAGE = 75.94        # feature convs only, SURVEY 8d (mask convs are a box sum: 0 FLOPs)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-layers", action="store_true", help="print a per-layer CUDA-event table to stderr")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in a side process during the timed region)
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # "under load" = upper half of the samples (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm on the host cores (oracle port of models/image_inpainting.py)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch=1, seed=0):
+    """fwd + bwd + SGD of ImageFillOrigin on CPU through the oracle's functional restatement of the
+    reference (same ATen ops in the same order; pinned bit-exactly by tests/golden).  Returns
+    (images_per_sec, ms_per_step, cores)."""
+    import numpy as np
+    import torch
+
+    from oracle import pconv_torch as O                       # cpu_baseline leg: allowed importer of oracle/
+    from text_segmentation_image_inpainting_b200.models.image_inpainting import ImageFillOrigin
+    from text_segmentation_image_inpainting_b200.synthetic import random_hole_masks
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(seed)
+    skeleton = ImageFillOrigin()                               # parameter names / shapes / default init only
+    sd = O.clone_state_dict(skeleton.state_dict(), requires_grad=True)
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.SGD(params, lr=2e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    x = torch.randn(batch, 3, HW, HW)
+    mask = torch.from_numpy(random_hole_masks(batch, HW, HW, seed=seed))
+    xin = x * mask
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = O.image_fill_origin(sd, xin, mask, training=True)
+        loss = out.abs().mean()
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, 1e3 * total / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                               # other ranks exit 0 without work
+    ips, ms, cores = cpu_reference_steps(args.steps, args.warmup, batch=1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ImageFillOrigin 512x512 fwd+bwd+SGD, CPU (reference algorithm via oracle port)",
+                   "batch_per_step": 1, "note": "each step is a bounded sample (1 image) of the batch-8 workload"},
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 image @512x512 after {args.warmup} warm-up"},
+        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def conv_flops(g):
+    return 2.0 * g.n * g.ho * g.wo * g.cout * (g.cin // g.groups) * g.kh * g.kw
+
+
+def layer_profile(ts, x, mask, peaks, verbose):
+    """One instrumented EAGER step: CUDA events around every conv launch on the launching stream.
+    Returns the roofline dict of the dominant kernel family."""
+    import torch
+    from text_segmentation_image_inpainting_b200 import _lib, ops
+
+    rec = []
+    ops.set_profile(rec)
+    ts._step(x, mask, False)
+    torch.cuda.synchronize()
+    ops.set_profile(None)
+    fam = {}
+    rows = []
+    for kind, g, s, e in rec:
+        ms = s.elapsed_time(e)
+        c = g.struct(None)
+        tc = bool(_lib.load().pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)))
+        key = ("tc_" if tc else "generic_") + kind
+        f = fam.setdefault(key, [0.0, 0.0, 0])
+        f[0] += conv_flops(g); f[1] += ms; f[2] += 1
+        rows.append((key, f"{g.cin}->{g.cout} k{g.kh} s{g.stride} @{g.h}x{g.w}", conv_flops(g) / 1e9, ms))
+    if verbose:
+        for r in rows:
+            print(f"  {r[0]:14s} {r[1]:28s} {r[2]:8.1f} GF {r[3]:8.3f} ms {r[2] / max(r[3], 1e-9):8.1f} TF/s", file=sys.stderr)
+        for k, (fl, ms, n) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+            print(f"  == {k:14s} launches={n:3d} {fl / 1e9:9.1f} GF {ms:8.3f} ms {fl / 1e9 / max(ms, 1e-9):8.1f} TF/s", file=sys.stderr)
+    tcf = {k: v for k, v in fam.items() if k.startswith("tc_")}
+    if not tcf:
+        return None, fam
+    dom = max(tcf.items(), key=lambda kv: kv[1][1])
+    fl, ms, n = dom[1]
+    achieved = fl / (ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    return {"bound": "tensor", "kernel": {"tc_fwd": "pconv_tc_kernel<MODE=0>", "tc_dgrad": "pconv_tc_kernel<MODE=1>",
+                                          "tc_wgrad": "pconv_tc_wgrad_kernel"}[dom[0]],
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",
+            "launches_per_step": n, "flops_per_step": fl, "ms_per_step_in_kernel": ms, "traffic": None}, fam
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from text_segmentation_image_inpainting_b200 import _lib
+    from text_segmentation_image_inpainting_b200.engine import TrainStep
+    from text_segmentation_image_inpainting_b200.models.image_inpainting import ImageFillOrigin
+    from text_segmentation_image_inpainting_b200.synthetic import random_hole_masks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    _lib.load()
+
+    torch.manual_seed(0)                                        # identical initial weights on every rank
+    net = ImageFillOrigin().to(dev)
+    ts = TrainStep(net, compute_dtype=torch.bfloat16, process_group=pg, use_graph=not args.no_graph)
+
+    # synthetic inputs: x ~ N(0,1), free-form line/ellipse holes, one plane per image x3 channels
+    B = PER_GPU_BATCH
+    g = torch.Generator().manual_seed(1234 + rank)
+    NBUF = 2
+    host_x = [torch.randn(B, 3, HW, HW, generator=g).pin_memory() for _ in range(NBUF)]
+    host_m = [torch.from_numpy(random_hole_masks(B, HW, HW, seed=100 * rank + i)).pin_memory() for i in range(NBUF)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_m = [t.to(dev) for t in host_m]
+    h2d_bytes = host_x[0].numel() * 4 + host_m[0].numel() * 4
+
+    ts.warmup_and_capture(dev_x[0], dev_m[0], eager_warmup=2)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing: inputs already in HBM (two 50 MB input sets alternate; the
+    # step's working set (~3 GB of activations) is far larger than L2, so no explicit flush is needed)
+    for i in range(args.warmup):
+        ts.step(dev_x[i % NBUF], dev_m[i % NBUF])
+    clocks = Clocks(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        ts.step(dev_x[i % NBUF], dev_m[i % NBUF])
+    e1.record()
+    barrier()
+    ms_total = maxreduce(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end to end: host (pinned) buffers -> H2D on a copy stream, double buffered against
+    # compute -> step -> D2H of the loss, every step inside the timed region
+    copy_stream = torch.cuda.Stream()
+    stage_x = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    stage_m = [torch.empty_like(dev_m[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def upload(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            stage_x[b].copy_(host_x[i % NBUF], non_blocking=True)
+            stage_m[b].copy_(host_m[i % NBUF], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_run(nsteps):
+        for b in range(2):
+            consumed[b].record()
+        upload(0)
+        for i in range(nsteps):
+            if i + 1 < nsteps:
+                upload(i + 1)
+            b = i % 2
+            torch.cuda.current_stream().wait_event(ready[b])
+            loss = ts.step(stage_x[b], stage_m[b])
+            consumed[b].record()
+            loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_run(max(2, min(args.warmup, 3)))
+    barrier()
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = maxreduce(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    # ---------------- per-kernel roofline (rank 0): eager instrumented step, events on the launching stream
+    roof, fam = (None, {})
+    if rank == 0:
+        roof, fam = layer_profile(ts, dev_x[0], dev_m[0], peaks, args.profile_layers)
+    barrier()
+
+    # ---------------- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores = cpu_reference_steps(steps=3, warmup=1, batch=1)
+        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
+               "sample": "3 steps x 1 image @512x512 (fwd+bwd+SGD) after 1 warm-up, all host threads"}
+
+    if rank == 0:
+        step_flop = (3 * FWD_GFLOP_PER_IMAGE - 1.23) * 1e9 * B          # fwd+bwd, minus the stem dgrad
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ImageFillOrigin (PartialConv U-Net) 512x512, batch 8 per GPU, fwd+bwd+SGD(nesterov), train-mode BN",
+                       "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": ts.graph is not None,
+                       "l2": "inputs+activations per step (~3 GB) exceed the 126 MB L2; no explicit flush",
+                       "loss": "out.abs().mean()", "algorithmic_tflop_per_step_per_gpu": step_flop / 1e12},
+            "step_tflops_per_gpu": step_flop / 1e12 / (ms_total / args.steps * 1e-3),
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": ts.launches_per_step * args.steps,
+            "roofline": roof,
+            "kernel_families_ms": {k: round(v[1], 4) for k, v in fam.items()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

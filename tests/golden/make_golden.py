@@ -168,3 +168,14 @@ if __name__ == "__main__":
                  "decoder.6.0.1.bn_act.0.bias", "encoder.7.0.1.bn_act.0.weight"])
     gen_network("ImageFillOriginV2", 2, 256, ["decoder.7.0.feature_conv.weight"])
     gen_network("ImageFill", 2, 128, ["decoder.3.0.feature_conv.weight"])
+
+
+def gen_state_dict_keys():
+    import json
+    out = {n: [[k, list(v.shape)] for k, v in getattr(rii, n)().state_dict().items()]
+           for n in ("ImageFillOrigin", "ImageFillOriginV2", "ImageFill")}
+    json.dump(out, open(os.path.join(HERE, "state_dict_keys.json"), "w"))
+
+
+if __name__ == "__main__":
+    gen_state_dict_keys()

@@ -1,0 +1,199 @@
+"""Shared GPU parity helpers (used by tests/test_gpu_parity.py and tools/gpu_diag.py).
+
+Every case runs a module of the product package on cuda:0 through the C ABI and compares with the torch-CPU
+oracle evaluated on the SAME dtype-rounded operands (so the bf16 tolerance below measures the kernel, not
+the input quantisation):
+  * fp32 mode  : 1e-4 relative to max|ref|   (north_star bar: 1e-3 relative fp32)
+  * bf16 mode  : 2e-2 relative to max|ref|   (outputs/grads are stored in bf16: 2^-8 relative rounding on
+                 top of fp32 accumulation; weight gradients are fp32 and typically 1e-3)
+  * new masks  : bit-exact always.
+"""
+import os
+
+import numpy as np
+import torch
+
+from oracle import pconv_torch as O
+from oracle.detfill import det_fill_state_dict, det_tensor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def blob(n, c, h, w, seed, per_channel=False):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = np.ones((n, c, h, w), np.float32)
+    for i in range(n):
+        for ch in range(c if per_channel else 1):
+            for _ in range(2):
+                y0, x0 = rng.integers(0, max(1, h - 3)), rng.integers(0, max(1, w - 3))
+                hh, ww = rng.integers(2, max(3, h // 2)), rng.integers(2, max(3, w // 2))
+                if per_channel:
+                    m[i, ch, y0:y0 + hh, x0:x0 + ww] = 0
+                else:
+                    m[i, :, y0:y0 + hh, x0:x0 + ww] = 0
+    return torch.from_numpy(m)
+
+
+def relerr(a, b):
+    a = a.detach().float().cpu(); b = b.detach().float().cpu()
+    fin = torch.isfinite(b)
+    if not torch.equal(torch.isfinite(a), fin):
+        return float("inf")
+    if not fin.any():
+        return 0.0
+    return (a[fin] - b[fin]).abs().max().item() / max(b[fin].abs().max().item(), 1e-20)
+
+
+# name: (cin, cout, k, s, p, d, groups, bias, same_holes, n, h, w, dtype, mask_kind, cls)
+#   mask_kind: "uniform" (one plane over all channels), "perchannel" (<= 8 channels), "two" (two planes split cin/2)
+F32, BF = torch.float32, torch.bfloat16
+CONV_CASES = {
+    # ---- shape-general kernels, exact fp32 mode (mirrors of the committed reference goldens)
+    "g_k3": (4, 6, 3, 1, 1, 1, 1, True, False, 2, 20, 24, F32, "uniform", "pc"),
+    "g_k3_sh": (4, 6, 3, 1, 1, 1, 1, True, True, 2, 20, 24, F32, "uniform", "pc"),
+    "g_k3_perchannel": (4, 6, 3, 1, 1, 1, 1, False, False, 2, 20, 24, F32, "perchannel", "pc"),
+    "g_k5_s2": (8, 8, 5, 2, 2, 1, 1, False, True, 2, 21, 26, F32, "uniform", "pc"),
+    "g_k7_s2_stem": (3, 8, 7, 2, 3, 1, 1, True, True, 2, 32, 32, F32, "uniform", "pc"),
+    "g_d2": (4, 4, 3, 1, 2, 2, 1, False, False, 1, 24, 24, F32, "uniform", "pc"),
+    "g_d4_sh": (4, 4, 3, 1, 4, 4, 1, True, True, 1, 24, 24, F32, "uniform", "pc"),
+    "g_d8": (2, 4, 3, 1, 8, 8, 1, False, False, 1, 28, 28, F32, "perchannel", "pc"),
+    "g_dw_sh": (8, 8, 3, 1, 1, 1, 8, False, True, 2, 16, 16, F32, "uniform", "pc"),
+    "g_dw_s2": (8, 8, 3, 2, 1, 1, 8, False, True, 2, 17, 19, F32, "uniform", "pc"),
+    "g_groups2": (4, 6, 3, 1, 1, 1, 2, True, False, 1, 12, 12, F32, "perchannel", "pc"),
+    "g_nopad": (3, 5, 3, 1, 0, 1, 1, True, False, 1, 10, 12, F32, "uniform", "pc"),
+    "g_1x1": (4, 8, 1, 1, 0, 1, 1, True, False, 2, 12, 12, F32, "uniform", "1x1"),
+    "g_nh_1x1": (6, 4, 1, 1, 0, 1, 1, False, False, 2, 12, 12, F32, "nh", "nh"),
+    "g_nh_k3_nan": (4, 4, 3, 1, 1, 1, 1, True, False, 1, 16, 16, F32, "uniform", "nh"),
+    "g_tail_67_3": (67, 3, 3, 1, 1, 1, 1, True, False, 1, 16, 16, F32, "uniform", "pc"),
+    "g_bf16_k3": (8, 8, 3, 1, 1, 1, 1, True, False, 2, 12, 12, BF, "uniform", "pc"),
+    "g_bf16_dw": (16, 16, 3, 1, 2, 2, 16, False, True, 2, 12, 12, BF, "uniform", "pc"),
+    # ---- tcgen05 path (bf16, channels % 64 == 0)
+    "tc_1x1_k64_n64": (64, 64, 1, 1, 0, 1, 1, False, False, 1, 16, 16, BF, "uniform", "1x1"),
+    "tc_1x1_k128_n128": (128, 128, 1, 1, 0, 1, 1, True, False, 1, 16, 16, BF, "uniform", "1x1"),
+    "tc_1x1_k256_n64_ragged_m": (256, 64, 1, 1, 0, 1, 1, True, False, 2, 12, 13, BF, "uniform", "1x1"),
+    "tc_k3_64_64": (64, 64, 3, 1, 1, 1, 1, True, False, 1, 16, 16, BF, "uniform", "pc"),
+    "tc_k3_64_128_sh": (64, 128, 3, 1, 1, 1, 1, False, True, 2, 20, 24, BF, "uniform", "pc"),
+    "tc_k3_128_64_two": (128, 64, 3, 1, 1, 1, 1, True, False, 2, 20, 24, BF, "two", "pc"),
+    "tc_k5_s2_64_128": (64, 128, 5, 2, 2, 1, 1, False, True, 2, 21, 26, BF, "uniform", "pc"),
+    "tc_k3_s2_128_256": (128, 256, 3, 2, 1, 1, 1, False, True, 2, 18, 18, BF, "uniform", "pc"),
+    "tc_k3_d2_64_64": (64, 64, 3, 1, 2, 2, 1, False, False, 1, 24, 24, BF, "uniform", "pc"),
+    "tc_nh_1x1_128_64_two": (128, 64, 1, 1, 0, 1, 1, False, False, 2, 12, 12, BF, "nh2", "nh"),
+    "tc_k3_192_64_two": (192, 64, 3, 1, 1, 1, 1, False, False, 1, 32, 32, BF, "two", "pc"),
+    "tc_k3_512_512_tiny": (512, 512, 3, 2, 1, 1, 1, False, True, 2, 4, 4, BF, "uniform", "pc"),
+    "tc_k3_320_64_two_odd_split": (320, 64, 3, 1, 1, 1, 1, False, False, 1, 16, 16, BF, "two64", "pc"),
+}
+
+
+def make_mask(kind, n, cin, h, w, seed):
+    """Returns (dense fp32 mask for the oracle, builder(dev) -> mask object for the device module)."""
+    from text_segmentation_image_inpainting_b200.masks import HoleMask
+    if kind in ("uniform",):
+        m = blob(n, cin, h, w, seed)
+        if cin <= 8:
+            return m, lambda dev: m.to(dev)
+        return m, lambda dev: HoleMask.from_plane(m[:, 0].to(dev).to(torch.uint8).contiguous(), cin)
+    if kind == "perchannel":
+        m = blob(n, cin, h, w, seed, per_channel=True)
+        return m, lambda dev: m.to(dev)
+    if kind == "nh":                       # decoder case: every pixel valid in at least one channel
+        m = blob(n, cin, h, w, seed, per_channel=True)
+        m[:, 0] = 1.0
+        return m, lambda dev: m.to(dev)
+    # two planes: channels [0, c0) and [c0, cin)
+    c0 = {"two": cin // 2, "two64": 64, "nh2": cin // 2}[kind]
+    a = blob(n, 1, h, w, seed)[:, 0]
+    b = blob(n, 1, h, w, seed + 977)[:, 0]
+    if kind == "nh2":
+        a = torch.ones_like(a)
+    m = torch.cat([a[:, None].expand(n, c0, h, w), b[:, None].expand(n, cin - c0, h, w)], 1).contiguous()
+    def build(dev):
+        pa = HoleMask.from_plane(a.to(dev).to(torch.uint8).contiguous(), c0)
+        pb = HoleMask.from_plane(b.to(dev).to(torch.uint8).contiguous(), cin - c0)
+        return torch.cat([pa, pb], dim=1)
+    return m, build
+
+
+def conv_case(tag, dev, dump_dir=None):
+    """fwd + bwd of one PartialConv* module on the GPU vs the oracle.  Returns dict of errors + flags."""
+    from text_segmentation_image_inpainting_b200 import _lib, ops
+    from text_segmentation_image_inpainting_b200.models import partial_convolution as PC
+    cin, cout, k, s, p, d, g, bias, same_holes, n, h, w, dtype, mkind, cls = CONV_CASES[tag]
+    if cls == "pc":
+        mod = PC.PartialConv(cin, cout, k, s, p, d, g, bias, same_holes)
+    elif cls == "1x1":
+        mod = PC.PartialConv1x1(cin, cout, k, s, p, d, g, bias)
+    else:
+        mod = PC.PartialConvNoHoles(cin, cout, k, s, p, d, g, bias)
+    sd = det_fill_state_dict(mod.state_dict())
+    mod.load_state_dict(sd)
+    x = det_tensor(tag + ".x", (n, cin, h, w))
+    mask, build_mask = make_mask(mkind, n, cin, h, w, seed=len(tag) * 7 + k)
+    wq = sd["feature_conv.weight"].to(dtype).float()
+    xq = x.to(dtype).float()
+    bq = sd["feature_conv.bias"] if bias else None
+    xo = xq.clone().requires_grad_(True); wo = wq.clone().requires_grad_(True)
+    bo = bq.clone().requires_grad_(True) if bias else None
+    if cls == "pc":
+        yo, mo = O.partial_conv(xo, mask, wo, bo, s, p, d, g, same_holes)
+    elif cls == "1x1":
+        yo, mo = O.partial_conv_1x1(xo, mask, wo, bo, g)
+    else:
+        yo, mo = O.partial_conv_no_holes(xo, mask, wo, bo, s, p, d)
+    gy = det_tensor(tag + ".gy", tuple(yo.shape)).to(dtype).float()
+    (torch.where(torch.isfinite(yo), yo, torch.zeros_like(yo)) * gy).sum().backward()
+    with torch.no_grad():
+        mod.feature_conv.weight.copy_(wq)
+    mod = mod.to(dev)
+    xd = xq.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yd, md = mod((xd, build_mask(dev)))
+    gyd = gy.to(dev).to(dtype)
+    if not torch.isfinite(yo).all():          # NoHoles NaN case: backprop only through the finite outputs
+        gyd = torch.where(torch.isfinite(yd), gyd, torch.zeros_like(gyd))
+        (torch.where(torch.isfinite(yd), yd, torch.zeros_like(yd)) * gyd).sum().backward()
+    else:
+        yd.backward(gyd)
+    torch.cuda.synchronize()
+    res = {"y": relerr(yd, yo), "gx": relerr(xd.grad, xo.grad), "gw": relerr(mod.feature_conv.weight.grad, wo.grad),
+           "gb": relerr(mod.feature_conv.bias.grad, bo.grad) if bias else 0.0,
+           "mask_equal": torch.equal(md.dense().cpu(), mo.contiguous())}
+    c = ops.ConvGeom(xd.shape, cout, k, s, p, d, g, same_holes, cls == "nh", 1 if dtype == BF else 0, [(None, cin, 0)]).struct(xd)
+    res["tc"] = int(_lib.load().pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)))
+    res["tol"] = TOL[dtype]
+    res["ok"] = all(res[k2] <= res["tol"] for k2 in ("y", "gx", "gw", "gb")) and res["mask_equal"]
+    if dump_dir and not res["ok"]:
+        for nm, a in (("y_dev", yd), ("y_ref", yo), ("gw_dev", mod.feature_conv.weight.grad), ("gw_ref", wo.grad),
+                      ("gx_dev", xd.grad), ("gx_ref", xo.grad)):
+            np.save(os.path.join(dump_dir, f"dump_{tag}_{nm}.npy"), a.detach().float().cpu().numpy())
+    return res
+
+
+# well-conditioned quantities only in bf16: the count-2/8 BatchNorm layers at the bottom of ImageFillOrigin make the
+# deep-layer gradients numerically ill-posed (x_hat = +-1), so bf16 compares outputs, loss and decoder-side grads.
+def run_net(cls_name, dev, dtype):
+    from text_segmentation_image_inpainting_b200 import ops
+    from text_segmentation_image_inpainting_b200.models import image_inpainting as PII
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"net_{cls_name}.npz"))
+    n, hw, step = int(g["n"]), int(g["hw"]), int(g["step"])
+    net = getattr(PII, cls_name)()
+    net.load_state_dict(det_fill_state_dict(net.state_dict()))
+    net = net.to(dev).train()
+    plane = np.unpackbits(g["mask_bits"])[: n * hw * hw].reshape(n, 1, hw, hw).astype(np.float32)
+    mask = torch.from_numpy(np.repeat(plane, 3, 1))
+    x = det_tensor(cls_name + ".x", (n, 3, hw, hw))
+    xin = (x * mask).to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    out = net((xin, mask.to(dev)))
+    loss = ops.l1_mean(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    errs = {"out": relerr(out[..., ::step, ::step], torch.from_numpy(g["out_sub"])),
+            "out_row": relerr(out[0, :, hw // 2, :], torch.from_numpy(g["out_row"])),
+            "loss": abs(float(loss) - float(g["loss"])) / abs(float(g["loss"]))}
+    params = dict(net.named_parameters())
+    sdn = net.state_dict()
+    for k in g.files:
+        if k.startswith("g.") and (dtype == F32 or k.startswith("g.decoder")):
+            errs[k] = relerr(params[k[2:]].grad, torch.from_numpy(g[k]))
+        if k.startswith("bn.") and (dtype == F32 or ".encoder.1." in k or ".encoder.0." in k):
+            errs[k] = relerr(sdn[k[3:]], torch.from_numpy(g[k]))
+    return errs

@@ -1,0 +1,134 @@
+"""Training-step engine for the partial-conv U-Nets: flat fp32 parameter / gradient arenas, one fused SGD
+launch, optional data-parallel gradient all-reduce (NCCL over NVLink) and whole-step CUDA-graph capture.
+
+The reference has no train script: its recipe is prose -- SGD + Nesterov momentum, weight decay,
+cyclic LR (checkpoints/ReadME.md:4).  One step here = forward + loss + backward (+ all-reduce) + SGD update,
+the unit BASELINE.json's images/sec is quoted on.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib, ops
+from .masks import HoleMask
+
+CL = torch.channels_last
+
+
+def _flat_view(flat: torch.Tensor, off: int, like: torch.Tensor) -> torch.Tensor:
+    """A view into `flat` with the same logical shape AND physical element order as `like`."""
+    n = like.numel()
+    seg = flat[off:off + n]
+    if like.dim() == 4 and like.is_contiguous(memory_format=CL) and not like.is_contiguous():
+        co, ci, kh, kw = like.shape
+        return seg.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+    return seg.view(like.shape)
+
+
+class FlatParams:
+    """All trainable parameters of a module re-pointed into one fp32 arena (and their grads into another)."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        # pad every tensor to a multiple of 4 elements so all views stay 16-byte aligned
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                v = _flat_view(self.flat_p, o, p.data)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = _flat_view(self.flat_g, o, p.data)
+        self.true_numel = total
+
+
+class TrainStep:
+    def __init__(self, net: torch.nn.Module, compute_dtype=torch.bfloat16, lr=2e-4, momentum=0.9, weight_decay=1e-4,
+                 nesterov=True, process_group=None, use_graph=True, bucket_mb=32):
+        self.net = net.train()
+        self.dtype = compute_dtype
+        self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
+        self.flat = FlatParams(net)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_x = self.static_m = self.static_loss = None
+        self.first = True
+        self.bucket_elems = bucket_mb * (1 << 20) // 4
+        self.launches_per_step = 0
+
+    # -- one eager step ----------------------------------------------------------------------------
+    def _prepare(self, x: torch.Tensor, mask: torch.Tensor):
+        """reference-style inputs (fp32 NCHW image, fp32/uint8 {0,1} NCHW mask) -> (x*mask in compute dtype NHWC, HoleMask)"""
+        xin = (x * mask.to(x.dtype)).to(self.dtype).contiguous(memory_format=CL)       # Dataloader.py:131
+        return xin, HoleMask.from_dense(mask)
+
+    def _allreduce(self):
+        if self.world == 1:
+            return
+        g = self.flat.flat_g
+        g.mul_(1.0 / self.world)
+        for s in range(0, g.numel(), self.bucket_elems):
+            torch.distributed.all_reduce(g[s:s + self.bucket_elems], group=self.pg)
+
+    def _step(self, x, mask, first_step: bool):
+        self.flat.flat_g.zero_()
+        ops.bump_weight_epoch()
+        xin, hm = self._prepare(x, mask)
+        out = self.net((xin, hm))
+        loss = ops.l1_mean(out)
+        loss.backward()
+        self._allreduce()
+        ops.sgd_step(self.flat.flat_p, self.flat.flat_g, self.flat.flat_m, self.lr, self.momentum, self.wd, self.nesterov,
+                     first_step)
+        return loss.detach()
+
+    # -- public -------------------------------------------------------------------------------------
+    def warmup_and_capture(self, x: torch.Tensor, mask: torch.Tensor, eager_warmup=2):
+        """Run eager warm-up steps (also counts this library's launches per step), then capture the step."""
+        for _ in range(eager_warmup):
+            before = _lib.launch_count()
+            self._step(x, mask, self.first)
+            self.first = False
+            self.launches_per_step = _lib.launch_count() - before
+        torch.cuda.synchronize()
+        if not self.use_graph:
+            return
+        self.static_x = x.clone()
+        self.static_m = mask.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step(self.static_x, self.static_m, False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.static_loss = self._step(self.static_x, self.static_m, False)
+        self.graph = graph
+        torch.cuda.synchronize()
+
+    def step(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """x, mask already on the device.  Returns the (device) loss of this step."""
+        if self.graph is not None:
+            if x.data_ptr() != self.static_x.data_ptr():
+                self.static_x.copy_(x, non_blocking=True)
+            if mask.data_ptr() != self.static_m.data_ptr():
+                self.static_m.copy_(mask, non_blocking=True)
+            self.graph.replay()
+            return self.static_loss
+        loss = self._step(x, mask, self.first)
+        self.first = False
+        return loss

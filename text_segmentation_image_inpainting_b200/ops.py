@@ -101,6 +101,33 @@ class ConvGeom:
         return c
 
 
+_PROFILE = None     # optional list: (kind, geom, start_event, end_event) appended per conv kernel call
+
+
+def set_profile(sink):
+    """bench.py: pass a list to record CUDA-event-bracketed conv launches (eager mode only), or None to stop."""
+    global _PROFILE
+    _PROFILE = sink
+
+
+class _Timed:
+    def __init__(self, kind, geom):
+        self.kind, self.geom = kind, geom
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.e.record()
+            _PROFILE.append((self.kind, self.geom, self.s, self.e))
+        return False
+
+
 class PartialConvFn(torch.autograd.Function):
     """y, msum, newmask = pconv(x, W, b | mask)   (models/partial_convolution.py:49-80 / :121-137)."""
 
@@ -115,8 +142,9 @@ class PartialConvFn(torch.autograd.Function):
         ws_bytes = lib.pcb_pconv_workspace(ctypes.byref(c))
         ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=x.device)
         b32 = bias.detach().float().contiguous() if bias is not None else None
-        _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_krsc.data_ptr(), _ptr(b32), y.data_ptr(), msum.data_ptr(),
-                                         newmask.data_ptr(), ws.data_ptr(), _stream()))
+        with _Timed("fwd", geom):
+            _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_krsc.data_ptr(), _ptr(b32), y.data_ptr(), msum.data_ptr(),
+                                             newmask.data_ptr(), ws.data_ptr(), _stream()))
         ctx.geom, ctx.wprep, ctx.has_bias = geom, wprep, bias is not None
         ctx.save_for_backward(x, msum)
         ctx.mark_non_differentiable(msum, newmask)
@@ -141,16 +169,28 @@ class PartialConvFn(torch.autograd.Function):
                              memory_format=CL)
             ws_bytes = lib.pcb_pconv_workspace(ctypes.byref(c))
             ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=x.device)
-            _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dw.data_ptr(), ws.data_ptr(), _stream()))
+            with _Timed("wgrad", geom):
+                _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dw.data_ptr(), ws.data_ptr(), _stream()))
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x, memory_format=CL)
-            _lib.check(lib.pcb_pconv_backward_data(ctypes.byref(c), dc.data_ptr(), w_krsc.data_ptr(), _ptr(w_crsk), dx.data_ptr(), _stream()))
+            with _Timed("dgrad", geom):
+                _lib.check(lib.pcb_pconv_backward_data(ctypes.byref(c), dc.data_ptr(), w_krsc.data_ptr(), _ptr(w_crsk), dx.data_ptr(), _stream()))
         return dx, dw, dbias, None, None
+
+
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch():
+    """Invalidate every cached compute-dtype weight copy (call after updating parameters through raw pointers,
+    e.g. `sgd_step`, which does not bump tensor version counters)."""
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
 
 
 def prepare_weight(weight: torch.Tensor, dtype: torch.dtype, groups: int, cache: dict):
     """fp32 master weight (OIHW logical) -> (KRSC, CRSK) copies in the compute dtype, cached per parameter version."""
-    key = (weight.data_ptr(), weight._version, dtype, str(weight.device))
+    key = (weight.data_ptr(), weight._version, dtype, str(weight.device), _WEIGHT_EPOCH)
     hit = cache.get("key")
     if hit == key:
         return cache["val"]
@@ -392,3 +432,4 @@ def sgd_step(param, grad, buf, lr, momentum=0.0, weight_decay=0.0, nesterov=Fals
         raise _lib.PcbError("sgd_step: param and grad must be dense with identical strides")
     _lib.check(lib.pcb_sgd_step(param.data_ptr(), grad.data_ptr(), _ptr(buf), param.numel(), float(lr), float(momentum),
                                 float(weight_decay), int(nesterov), int(first_step), _stream()))
+    bump_weight_epoch()
