@@ -51,6 +51,7 @@ typedef struct {
     int32_t same_holes;        /* PartialConv(same_holes=True): msum = cin * box(mask of part 0)        */
     int32_t no_guard;          /* PartialConvNoHoles: no zero guard, new mask all ones (may emit NaN)   */
     int32_t plain;             /* ordinary convolution (PartialConv1x1 / nn.Conv2d): renormaliser == 1   */
+    int32_t force_generic;     /* never take the tensor-core path for this problem                      */
     int32_t nparts;
     pcb_part parts[PCB_MAX_PARTS];
 } pcb_conv;
@@ -69,44 +70,46 @@ int pcb_conv_uses_tensor_cores(const pcb_conv *c);
  * bit masks); 0 when the generic path is taken.  Contents are not preserved between calls. */
 size_t pcb_pconv_workspace(const pcb_conv *c);
 
+/* Compute-dtype weight operands.  The tensor-core path wants the K axis padded to its 64-element block
+ * structure (and a transposed copy for the data gradient); the generic path wants a plain KRSC cast.
+ * pcb_conv_weight_layout gives the element counts (of c->dtype) of the two buffers (dgrad_elems may be 0);
+ * pcb_conv_weight_prepare fills them from the fp32 master weight, physically [cout][kh][kw][cin/groups]
+ * (= an OIHW nn.Conv2d weight in torch.channels_last memory format).                              */
+void pcb_conv_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems);
+int pcb_conv_weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream);
+
 /* PartialConv.forward / PartialConvNoHoles.forward (models/partial_convolution.py:49-80, :121-137):
  *   y = where(s==0, 0, conv(x*m; W)/s + b),  s = box-sum of the mask (all-ones mask_conv, :41-47,59-66),
  *   new_mask = (s != 0).
- * w      : [cout][kh][kw][cin/groups]  (KRSC), dtype = c->dtype
+ * w_fwd  : from pcb_conv_weight_prepare
  * bias   : fp32 [cout] or NULL
- * y      : NHWC [n,ho,wo,cout], dtype = c->dtype
+ * y      : NHWC [n,ho,wo,y_cstride], y_cstride >= cout (channels [cout, y_cstride) are written as zeros)
  * msum   : fp32 [mg][n,ho,wo]  mask sums s (0 at holes); mg = 1, or groups when groups>1 && !same_holes
  * newmask: u8   [mg][n,ho,wo]
  * workspace : pcb_pconv_workspace(c) bytes (may be NULL when that is 0)                        */
-int pcb_pconv_forward(const pcb_conv *c, const void *w, const float *bias, void *y, float *msum,
+int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
                       uint8_t *newmask, void *workspace, pcb_stream_t stream);
 
 /* Backward of the renormalisation (autograd of partial_convolution.py:71-72):
- *   dc = dy * [s>0] / s          (same dtype as dy, NHWC [n,ho,wo,cout])
+ *   dc = dy * [s>0] / s          (NHWC [n,ho,wo,dc_cstride]; channels [cout, dc_cstride) zeroed)
  *   dbias[co] = sum dy*[s>0]     (fp32, optional, overwritten)                                 */
-int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, const float *msum, void *dc,
+int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, int dy_cstride, const float *msum, void *dc, int dc_cstride,
                               float *dbias, pcb_stream_t stream);
 
-/* dx = conv_transpose(dc; W) * m   (autograd of partial_convolution.py:51).
- * w_krsc : the forward weight [cout][kh][kw][cin/groups], dtype = c->dtype (always required);
- * w_crsk : [cin][kh][kw][cout] copy (groups == 1), enables the tensor-core path; NULL => generic kernel.
- * dx : NHWC [n,h,w,cin] dense (virtual input resolution), dtype = c->dtype.
+/* dx_p = (conv_transpose(dc; W) * m)[channels of part p]   (autograd of partial_convolution.py:51).
+ * dx[p] : NHWC [n,h,w,dx_cstride[p]] at the conv-input resolution (a 2x-upsampled part still gets a full
+ *         resolution gradient; reduce it with pcb_upsample2x_backward), or NULL when part p needs none.
  * parts[].mask are the INPUT masks (dx is zeroed at input holes); parts[].x is not read.      */
-int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, const void *w_krsc, const void *w_crsk,
-                            void *dx, pcb_stream_t stream);
+int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_fwd, const void *w_dgrad,
+                            void *const *dx, const int32_t *dx_cstride, pcb_stream_t stream);
 
-/* dw[co][r][s][ci] = sum_pixels dc[p][co] * (x*m)[p@tap][ci]   (fp32 KRSC, overwritten).
+/* dw[co][r][s][ci] = sum_pixels dc[p][co] * (x*m)[p@tap][ci]   (fp32 KRSC, logical/unpadded, overwritten).
  * workspace: pcb_pconv_workspace(c) bytes (may be NULL when that is 0).                         */
-int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, float *dw, void *workspace, pcb_stream_t stream);
+int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream);
 
 /* Debug aid: after a device synchronise, returns the (sticky) pipeline-timeout code set by a tensor-core
  * kernel whose mbarrier wait expired (0 = none) and clears it. */
 int pcb_debug_pipeline_status(int *code);
-
-/* fp32 OIHW-logical / KRSC-physical master weight -> compute-dtype copies.
- * w_krsc: [cout][kh][kw][cig]; w_crsk (optional, groups==1 only): [cin][kh][kw][cout].        */
-int pcb_weight_prepare(const float *w_master_krsc, int cout, int kh, int kw, int cig, int dtype,
-                       void *w_krsc, void *w_crsk, pcb_stream_t stream);
 
 /* ---- masks ----------------------------------------------------------------------------- */
 /* dense fp32 NCHW mask (the reference API, partial_convolution.py:50) -> c u8 planes [c][n,h,w]. */

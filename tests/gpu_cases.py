@@ -82,12 +82,23 @@ CONV_CASES = {
     "tc_k3_192_64_two": (192, 64, 3, 1, 1, 1, 1, False, False, 1, 32, 32, BF, "two", "pc"),
     "tc_k3_512_512_tiny": (512, 512, 3, 2, 1, 1, 1, False, True, 2, 4, 4, BF, "uniform", "pc"),
     "tc_k3_320_64_two_odd_split": (320, 64, 3, 1, 1, 1, 1, False, False, 1, 16, 16, BF, "two64", "pc"),
+    # ---- channel padding / small-Cin row-packed mode (x lives in an 8-channel-padded NHWC buffer)
+    "tc_stem_rowpack_k7_s2": (3, 64, 7, 2, 3, 1, 1, True, True, 2, 40, 44, BF, "uniform3", "pc"),
+    "tc_rowpack_k3_cin8": (8, 32, 3, 1, 1, 1, 1, False, False, 1, 20, 20, BF, "uniform", "pc"),
+    "tc_rowpack_k5_d2_cin4": (4, 128, 5, 1, 4, 2, 1, True, False, 1, 24, 24, BF, "uniform", "pc"),
+    "tc_cin72_padded_kblock": (72, 64, 3, 1, 1, 1, 1, True, False, 1, 16, 16, BF, "uniform", "pc"),
+    "tc_cout24_padded_n": (64, 24, 3, 1, 1, 1, 1, True, False, 1, 16, 16, BF, "uniform", "pc"),
+    "tc_cout3_tail_like": (64, 3, 3, 1, 1, 1, 1, True, False, 2, 16, 16, BF, "uniform", "pc"),
 }
+PADDED_X = {"tc_stem_rowpack_k7_s2", "tc_rowpack_k5_d2_cin4"}
 
 
 def make_mask(kind, n, cin, h, w, seed):
     """Returns (dense fp32 mask for the oracle, builder(dev) -> mask object for the device module)."""
     from text_segmentation_image_inpainting_b200.masks import HoleMask
+    if kind == "uniform3":                 # dense 3-channel repeated plane, declared channel-uniform by the caller
+        m = blob(n, cin, h, w, seed)
+        return m, lambda dev: HoleMask.from_dense(m.to(dev), channel_uniform=True)
     if kind in ("uniform",):
         m = blob(n, cin, h, w, seed)
         if cin <= 8:
@@ -145,7 +156,12 @@ def conv_case(tag, dev, dump_dir=None):
     with torch.no_grad():
         mod.feature_conv.weight.copy_(wq)
     mod = mod.to(dev)
-    xd = xq.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    if tag in PADDED_X:
+        buf = torch.zeros((n, 8, h, w), dtype=dtype, device=dev).contiguous(memory_format=torch.channels_last)
+        buf[:, :cin].copy_(xq.to(dev).to(dtype))
+        xd = buf[:, :cin].detach().requires_grad_(True)
+    else:
+        xd = xq.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     yd, md = mod((xd, build_mask(dev)))
     gyd = gy.to(dev).to(dtype)
     if not torch.isfinite(yo).all():          # NoHoles NaN case: backprop only through the finite outputs
@@ -157,7 +173,7 @@ def conv_case(tag, dev, dump_dir=None):
     res = {"y": relerr(yd, yo), "gx": relerr(xd.grad, xo.grad), "gw": relerr(mod.feature_conv.weight.grad, wo.grad),
            "gb": relerr(mod.feature_conv.bias.grad, bo.grad) if bias else 0.0,
            "mask_equal": torch.equal(md.dense().cpu(), mo.contiguous())}
-    c = ops.ConvGeom(xd.shape, cout, k, s, p, d, g, same_holes, cls == "nh", 1 if dtype == BF else 0, [(None, cin, 0)]).struct(xd)
+    c = ops.ConvGeom([xd.detach()], [0], cout, k, s, p, d, g, same_holes, cls == "nh", [(None, cin, 0)]).struct([xd.detach()])
     res["tc"] = int(_lib.load().pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)))
     res["tol"] = TOL[dtype]
     res["ok"] = all(res[k2] <= res["tol"] for k2 in ("y", "gx", "gw", "gb")) and res["mask_equal"]
@@ -165,6 +181,60 @@ def conv_case(tag, dev, dump_dir=None):
         for nm, a in (("y_dev", yd), ("y_ref", yo), ("gw_dev", mod.feature_conv.weight.grad), ("gw_ref", wo.grad),
                       ("gx_dev", xd.grad), ("gx_ref", xo.grad)):
             np.save(os.path.join(dump_dir, f"dump_{tag}_{nm}.npy"), a.detach().float().cpu().numpy())
+    return res
+
+
+# (ca at half resolution -> 2x nearest upsampled, cb at full resolution, cout, bias): the decoder / tail input pattern
+LAZYCAT_CASES = {"lc_128up_64_to_64": (128, 64, 64, False), "lc_256up_64_to_128": (256, 64, 128, False),
+                 "lc_tail_64up_3_to_3": (64, 3, 3, True), "lc_64up_8_to_16": (64, 8, 16, True)}
+
+
+def lazycat_case(tag, dev, dtype=BF):
+    """PartialConv over LazyCat([up2x(a), b]) with HoleMask cat([mask_a.upsampled(), mask_b]) vs the oracle on the
+    materialised cat (image_inpainting.py:183-186)."""
+    import torch.nn.functional as F
+    from text_segmentation_image_inpainting_b200 import _lib, ops
+    from text_segmentation_image_inpainting_b200.masks import HoleMask
+    from text_segmentation_image_inpainting_b200.models import partial_convolution as PC
+    ca, cb, cout, bias = LAZYCAT_CASES[tag]
+    n, h, w = 2, 24, 20
+    mod = PC.PartialConv(ca + cb, cout, 3, 1, 1, 1, 1, bias, False)
+    sd = det_fill_state_dict(mod.state_dict()); mod.load_state_dict(sd)
+    wq = sd["feature_conv.weight"].to(dtype).float()
+    a = det_tensor(tag + ".a", (n, ca, h // 2, w // 2)).to(dtype).float()
+    b = det_tensor(tag + ".b", (n, cb, h, w)).to(dtype).float()
+    pa = blob(n, 1, h // 2, w // 2, 11)[:, 0]; pb = blob(n, 1, h, w, 23)[:, 0]
+    mask = torch.cat([F.interpolate(pa[:, None], scale_factor=2, mode="nearest").expand(n, ca, h, w), pb[:, None].expand(n, cb, h, w)], 1)
+    ao, bo, wo = a.clone().requires_grad_(True), b.clone().requires_grad_(True), wq.clone().requires_grad_(True)
+    bio = sd["feature_conv.bias"].clone().requires_grad_(True) if bias else None
+    yo, mo = O.partial_conv(torch.cat([F.interpolate(ao, scale_factor=2, mode="nearest"), bo], 1), mask.contiguous(), wo, bio, 1, 1, 1, 1, False)
+    gy = det_tensor(tag + ".gy", tuple(yo.shape)).to(dtype).float()
+    (yo * gy).sum().backward()
+    with torch.no_grad():
+        mod.feature_conv.weight.copy_(wq)
+    mod = mod.to(dev)
+    ad = a.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    if cb % 8:
+        buf = torch.zeros((n, 8, h, w), dtype=dtype, device=dev).contiguous(memory_format=torch.channels_last)
+        buf[:, :cb].copy_(b.to(dev).to(dtype)); bd = buf[:, :cb].detach().requires_grad_(True)
+    else:
+        bd = b.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    hm = torch.cat([HoleMask.from_plane(pa.to(dev).to(torch.uint8).contiguous(), ca).upsampled(),
+                    HoleMask.from_plane(pb.to(dev).to(torch.uint8).contiguous(), cb)], dim=1)
+    x = ops.LazyCat([ad, bd], ups=(1, 0))
+    yd, md = mod((x, hm))
+    yd.backward(gy.to(dev).to(dtype))
+    torch.cuda.synchronize()
+    res = {"y": relerr(yd, yo), "ga": relerr(ad.grad, ao.grad), "gb_in": relerr(bd.grad, bo.grad),
+           "gw": relerr(mod.feature_conv.weight.grad, wo.grad), "gbias": relerr(mod.feature_conv.bias.grad, bio.grad) if bias else 0.0,
+           "mask_equal": torch.equal(md.dense().cpu(), mo.contiguous())}
+    # the materialised path must agree too
+    ym, _ = mod((x.materialize(), hm))
+    res["vs_materialized"] = relerr(ym, yd)
+    c = ops.ConvGeom(x.xs, x.ups, cout, 3, 1, 1, 1, 1, False, False, hm.parts).struct(x.xs)
+    res["tc"] = int(_lib.load().pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)))
+    res["tol"] = TOL[dtype]
+    res["ok"] = all(res[k2] <= res["tol"] for k2 in ("y", "ga", "gb_in", "gw", "gbias", "vs_materialized")) and res["mask_equal"]
     return res
 
 

@@ -41,12 +41,30 @@ def test_argument_validation_without_gpu():
     c = _lib.Conv()
     c.n = c.h = c.w = 8; c.cin = 4; c.cout = 4; c.kh = c.kw = 3; c.stride = 1; c.pad_h = c.pad_w = 1; c.dil = 1
     c.groups = 3; c.ho = c.wo = 8; c.nparts = 1; c.parts[0].c = 4; c.parts[0].x_cstride = 4
-    rc = lib.pcb_pconv_forward(_lib.ctypes.byref(c), 1, None, 1, 1, 1, None, None)
+    rc = lib.pcb_pconv_forward(_lib.ctypes.byref(c), 1, None, 1, 4, 1, 1, None, None)
     assert rc != 0 and b"groups" in lib.pcb_last_error()
     c.groups = 1; c.ho = 7
-    assert lib.pcb_pconv_forward(_lib.ctypes.byref(c), 1, None, 1, 1, 1, None, None) != 0
+    assert lib.pcb_pconv_forward(_lib.ctypes.byref(c), 1, None, 1, 4, 1, 1, None, None) != 0
     assert b"output size" in lib.pcb_last_error()
     assert lib.pcb_pconv_workspace(_lib.ctypes.byref(c)) == 0          # fp32 / 4 channels: generic path
+    fe, de = _lib.c_size_t(0), _lib.c_size_t(0)
+    c.ho = 8
+    lib.pcb_conv_weight_layout(_lib.ctypes.byref(c), _lib.ctypes.byref(fe), _lib.ctypes.byref(de))
+    assert (fe.value, de.value) == (4 * 9 * 4, 0)
+    # a bf16 64->128 k3 layer is a tensor-core problem: K padded per tap, transposed copy for the data gradient
+    c.dtype = _lib.PCB_BF16; c.cin = 64; c.cout = 128; c.parts[0].c = 64; c.parts[0].x_cstride = 64
+    assert lib.pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)) == 1
+    lib.pcb_conv_weight_layout(_lib.ctypes.byref(c), _lib.ctypes.byref(fe), _lib.ctypes.byref(de))
+    assert (fe.value, de.value) == (128 * 9 * 64, 128 * 9 * 128)
+    assert lib.pcb_pconv_workspace(_lib.ctypes.byref(c)) == 8 * 8 * 8 * 8
+    # the RGB stem (3 channels in an 8-channel-padded NHWC buffer) runs row-packed: one K block per kernel row
+    c.cin = 3; c.cout = 64; c.kh = c.kw = 7; c.pad_h = c.pad_w = 3; c.stride = 2; c.ho = c.wo = 4
+    c.parts[0].c = 3; c.parts[0].x_cstride = 8
+    assert lib.pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)) == 1
+    lib.pcb_conv_weight_layout(_lib.ctypes.byref(c), _lib.ctypes.byref(fe), _lib.ctypes.byref(de))
+    assert (fe.value, de.value) == (64 * 7 * 64, 0)
+    c.parts[0].x_cstride = 3                                           # dense 3-channel pixels: not 16-byte chunks
+    assert lib.pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)) == 0
 
 
 def test_no_cpu_fallback():

@@ -3,7 +3,7 @@ autograd Functions -> ctypes -> C ABI (include/pconv_b200.h), against the oracle
 import pytest
 import torch
 
-from gpu_cases import BF, CONV_CASES, F32, conv_case, relerr, run_net
+from gpu_cases import BF, CONV_CASES, F32, LAZYCAT_CASES, conv_case, lazycat_case, relerr, run_net
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +31,15 @@ def test_partial_conv_module_fwd_bwd(tag, dev):
     if tag.startswith("tc_"):
         assert res["tc"] == 1, "this case must run on the tcgen05 path"
     for k in ("y", "gx", "gw", "gb"):
+        assert res[k] <= res["tol"], (k, res)
+
+
+@pytest.mark.parametrize("tag", sorted(LAZYCAT_CASES))
+def test_partial_conv_over_lazy_upsample_concat(tag, dev):
+    """The decoder pattern: conv(cat([up2x(a), b])) without materialising the upsample or the concat."""
+    res = lazycat_case(tag, dev)
+    assert _pipeline_clean() and res["mask_equal"] and res["tc"] == 1, res
+    for k in ("y", "ga", "gb_in", "gw", "gbias", "vs_materialized"):
         assert res[k] <= res["tol"], (k, res)
 
 

@@ -23,7 +23,7 @@ class Part(ctypes.Structure):
 class Conv(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in
                 ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad_h", "pad_w", "dil", "groups", "ho", "wo",
-                 "dtype", "same_holes", "no_guard", "plain", "nparts")] + [("parts", Part * MAX_PARTS)]
+                 "dtype", "same_holes", "no_guard", "plain", "force_generic", "nparts")] + [("parts", Part * MAX_PARTS)]
 
 
 _SIGS = {
@@ -32,12 +32,14 @@ _SIGS = {
     "pcb_launch_count": (ctypes.c_ulonglong, []),
     "pcb_conv_uses_tensor_cores": (c_int, [ctypes.POINTER(Conv)]),
     "pcb_pconv_workspace": (c_size_t, [ctypes.POINTER(Conv)]),
-    "pcb_pconv_forward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "pcb_pconv_renorm_backward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "pcb_pconv_backward_data": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "pcb_pconv_backward_weight": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_conv_weight_layout": (None, [ctypes.POINTER(Conv), ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
+    "pcb_conv_weight_prepare": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_pconv_forward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_pconv_renorm_backward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pcb_pconv_backward_data": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p),
+                                        ctypes.POINTER(ctypes.c_int32), c_void_p]),
+    "pcb_pconv_backward_weight": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pcb_debug_pipeline_status": (c_int, [ctypes.POINTER(c_int)]),
-    "pcb_weight_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pcb_mask_planes_from_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pcb_mask_plane_to_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pcb_bn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p]),

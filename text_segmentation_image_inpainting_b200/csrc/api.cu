@@ -47,47 +47,68 @@ static int validate(const pcb_conv *c, bool need_x) {
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_conv_uses_tensor_cores(const pcb_conv *c) { return (c && pcb_tc_forward_eligible(c)) ? 1 : 0; }
+static bool use_tc(const pcb_conv *c) { return !c->force_generic && pcb_tc_eligible(c); }
 
-extern "C" __attribute__((visibility("default"))) size_t pcb_pconv_workspace(const pcb_conv *c) {
-    if (!c || !pcb_tc_forward_eligible(c)) return 0;
-    return pcb_tc_forward_workspace(c);
+#define PCB_API extern "C" __attribute__((visibility("default")))
+
+PCB_API int pcb_conv_uses_tensor_cores(const pcb_conv *c) { return (c && use_tc(c)) ? 1 : 0; }
+
+PCB_API size_t pcb_pconv_workspace(const pcb_conv *c) { return (c && use_tc(c)) ? pcb_tc_workspace(c) : 0; }
+
+PCB_API void pcb_conv_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems) {
+    if (use_tc(c)) { pcb_tc_weight_layout(c, fwd_elems, dgrad_elems); return; }
+    *fwd_elems = static_cast<size_t>(c->cout) * c->kh * c->kw * (c->cin / c->groups);
+    *dgrad_elems = 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_pconv_forward(const pcb_conv *c, const void *w, const float *bias, void *y, float *msum, uint8_t *newmask,
-                                 void *workspace, pcb_stream_t stream) {
+int pcb_cast_weights(const float *src, void *dst, long long n, int dtype, cudaStream_t st);   // elementwise.cu
+
+PCB_API int pcb_conv_weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream) {
+    PCB_CHECK(c && w_master_krsc && w_fwd, "pcb_conv_weight_prepare: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_tc(c)) return pcb_tc_weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, st);
+    return pcb_cast_weights(w_master_krsc, w_fwd, static_cast<long long>(c->cout) * c->kh * c->kw * (c->cin / c->groups), c->dtype, st);
+}
+
+PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                              uint8_t *newmask, void *workspace, pcb_stream_t stream) {
     if (int rc = validate(c, true)) return rc;
-    PCB_CHECK(w && y && msum && newmask, "pcb_pconv_forward: null pointer");
+    PCB_CHECK(w_fwd && y && msum && newmask && y_cstride >= c->cout, "pcb_pconv_forward: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
-    if (pcb_tc_forward_eligible(c)) {
+    if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr, "pcb_pconv_forward: workspace required for the tensor-core path");
-        PCB_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "w / y must be 16-byte aligned");
-        return pcb_tc_forward_ws(c, w, bias, y, msum, static_cast<uint32_t *>(workspace), st);
+        PCB_CHECK((reinterpret_cast<uintptr_t>(w_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "w / y must be 16-byte aligned");
+        return pcb_tc_forward_ws(c, w_fwd, bias, y, y_cstride, msum, static_cast<uint64_t *>(workspace), st);
     }
-    return pcb_generic_forward(c, w, bias, y, msum, newmask, st);
+    return pcb_generic_forward(c, w_fwd, bias, y, y_cstride, msum, st);
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, const void *w_krsc, const void *w_crsk, void *dx,
-                                       pcb_stream_t stream) {
+PCB_API int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_fwd, const void *w_dgrad,
+                                    void *const *dx, const int32_t *dx_cstride, pcb_stream_t stream) {
     if (int rc = validate(c, false)) return rc;
-    PCB_CHECK(dc && w_krsc && dx, "pcb_pconv_backward_data: null pointer");
+    PCB_CHECK(dc && w_fwd && dx && dx_cstride && dc_cstride >= c->cout, "pcb_pconv_backward_data: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (w_crsk && pcb_tc_dgrad_eligible(c) && (reinterpret_cast<uintptr_t>(dc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0)
-        return pcb_tc_dgrad(c, dc, w_crsk, dx, st);
-    return pcb_generic_dgrad(c, dc, w_krsc, dx, st);
+    if (use_tc(c)) {
+        PCB_CHECK(pcb_tc_dgrad_supported(c), "data gradient of a row-packed (cin <= 8) tensor-core layer: set force_generic and pass KRSC weights");
+        PCB_CHECK(w_dgrad != nullptr && (reinterpret_cast<uintptr_t>(dc) & 15) == 0, "pcb_pconv_backward_data: w_dgrad required / dc misaligned");
+        return pcb_tc_dgrad(c, dc, dc_cstride, w_dgrad, dx, dx_cstride, st);
+    }
+    return pcb_generic_dgrad(c, dc, dc_cstride, w_fwd, dx, dx_cstride, st);
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, float *dw, void *workspace, pcb_stream_t stream) {
+PCB_API int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream) {
     if (int rc = validate(c, true)) return rc;
-    PCB_CHECK(dc && dw, "pcb_pconv_backward_weight: null pointer");
+    PCB_CHECK(dc && dw && dc_cstride >= c->cout, "pcb_pconv_backward_weight: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pcb_tc_wgrad_eligible(c) && workspace && (reinterpret_cast<uintptr_t>(dc) & 15) == 0)
-        return pcb_tc_wgrad(c, dc, dw, workspace, st);
-    return pcb_generic_wgrad(c, dc, dw, st);
+    if (use_tc(c)) {
+        PCB_CHECK(workspace != nullptr && (reinterpret_cast<uintptr_t>(dc) & 15) == 0, "pcb_pconv_backward_weight: workspace required / dc misaligned");
+        return pcb_tc_wgrad(c, dc, dc_cstride, dw, workspace, st);
+    }
+    return pcb_generic_wgrad(c, dc, dc_cstride, dw, st);
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_debug_pipeline_status(int *code) {
+PCB_API int pcb_debug_pipeline_status(int *code) {
     PCB_CHECK(code != nullptr, "null code");
     return pcb_tc_read_abort_flag(code);
 }

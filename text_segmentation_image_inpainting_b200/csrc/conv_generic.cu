@@ -3,6 +3,7 @@
 // path does not take (3-channel stem, 3-channel tail, depthwise, per-channel masks) and the exact-fp32 mode.
 // Semantics: models/partial_convolution.py:49-80 (PartialConv), :121-137 (PartialConvNoHoles).
 #include <algorithm>
+#include <string.h>
 
 #include "pcb_common.cuh"
 
@@ -85,7 +86,7 @@ __global__ void mask_sums_kernel(const GParams G, float *msum, uint8_t *newmask)
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CO>
 __global__ void generic_fwd_kernel(const GParams G, const T *__restrict__ w, const float *__restrict__ bias,
-                                   const float *__restrict__ msum, T *__restrict__ y) {
+                                   const float *__restrict__ msum, T *__restrict__ y, int y_cstride) {
     const long long plane = static_cast<long long>(G.ho) * G.wo;
     const long long total = plane * G.n;
     const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -134,14 +135,17 @@ __global__ void generic_fwd_kernel(const GParams G, const T *__restrict__ w, con
 #pragma unroll
     for (int j = 0; j < CO; ++j) {
         const int co = co0 + j;
-        if (co >= G.cout) continue;
+        if (co >= G.cout) {
+            if (co < y_cstride) y[m * y_cstride + co] = from_f32<T>(0.f);      // channel padding stays finite (zero)
+            continue;
+        }
         const int g = (mg == 1) ? 0 : co / cog;
         const float s = msum[g * total + m];
         const float b = bias ? bias[co] : 0.f;
         float v;
         if (G.no_guard) v = acc[j] / s + b;                                    // :134 (NaN/inf on s == 0, as the reference)
         else v = (s == 0.f) ? 0.f : acc[j] / s + b;                            // :71-72
-        y[m * G.cout + co] = from_f32<T>(v);
+        y[m * y_cstride + co] = from_f32<T>(v);
     }
 }
 
@@ -149,8 +153,10 @@ __global__ void generic_fwd_kernel(const GParams G, const T *__restrict__ w, con
 // dgrad: one thread = one input pixel x CI consecutive input channels;  dx = convT(dc, W) * mask
 // w is the forward KRSC weight [cout][kh][kw][cig]
 // ------------------------------------------------------------------------------------------------
+struct DxOut { void *ptr[PCB_MAX_PARTS]; int cstride[PCB_MAX_PARTS]; };
+
 template <typename T, int CI>
-__global__ void generic_dgrad_kernel(const GParams G, const T *__restrict__ dc, const T *__restrict__ w, T *__restrict__ dx) {
+__global__ void generic_dgrad_kernel(const GParams G, const T *__restrict__ dc, int dc_cstride, const T *__restrict__ w, const DxOut O) {
     const long long plane = static_cast<long long>(G.h) * G.w;
     const long long total = plane * G.n;
     const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -170,7 +176,7 @@ __global__ void generic_dgrad_kernel(const GParams G, const T *__restrict__ dc, 
             const int oh = th / G.stride, ow = tw / G.stride;
             if (oh * G.stride != th || ow * G.stride != tw || oh >= G.ho || ow >= G.wo) continue;
             const int tap = tr * G.kw + tc;
-            const T *dp = dc + (static_cast<long long>(nn * G.ho + oh) * G.wo + ow) * G.cout;
+            const T *dp = dc + (static_cast<long long>(nn * G.ho + oh) * G.wo + ow) * dc_cstride;
             if (G.groups == 1) {
                 for (int co = 0; co < G.cout; ++co) {
                     const float dv = to_f32(dp[co]);
@@ -196,8 +202,9 @@ __global__ void generic_dgrad_kernel(const GParams G, const T *__restrict__ dc, 
         if (ci >= G.cin) continue;
         int p = 0;
         while (p + 1 < G.nparts && ci >= G.parts[p].choff + G.parts[p].c) ++p;
+        if (O.ptr[p] == nullptr) continue;
         const float mv = mask_at(G, p, nn, ih, iw) ? 1.f : 0.f;
-        dx[m * G.cin + ci] = from_f32<T>(acc[j] * mv);
+        static_cast<T *>(O.ptr[p])[m * O.cstride[p] + (ci - G.parts[p].choff)] = from_f32<T>(acc[j] * mv);
     }
 }
 
@@ -207,7 +214,7 @@ __global__ void generic_dgrad_kernel(const GParams G, const T *__restrict__ dc, 
 // pixel chunks of PC staged through shared memory; partial sums over pixel slabs via fp32 atomics.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CO_T, int K_T, int PC>
-__global__ void __launch_bounds__(256) generic_wgrad_kernel(const GParams G, const T *__restrict__ dc, float *__restrict__ dw,
+__global__ void __launch_bounds__(256) generic_wgrad_kernel(const GParams G, const T *__restrict__ dc, int dc_cstride, float *__restrict__ dw,
                                                             int g, int pix_per_block) {
     static_assert((CO_T / 4) * (K_T / 4) == 256, "thread tiling");
     __shared__ float s_dc[PC][CO_T];
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(256) generic_wgrad_kernel(const GParams G, con
             const int pp = i / CO_T, cc = i - pp * CO_T;
             const long long m = pc + pp;
             float v = 0.f;
-            if (m < p_end && cob + cc < cog) v = to_f32(dc[m * G.cout + g * cog + cob + cc]);
+            if (m < p_end && cob + cc < cog) v = to_f32(dc[m * dc_cstride + g * cog + cob + cc]);
             s_dc[pp][cc] = v;
         }
         // stage patch[PC][K_T]
@@ -285,29 +292,29 @@ __global__ void __launch_bounds__(256) generic_wgrad_kernel(const GParams G, con
 }
 
 template <typename T>
-int launch_fwd(const GParams &G, const void *w, const float *bias, const float *msum, void *y, cudaStream_t st) {
+int launch_fwd(const GParams &G, const void *w, const float *bias, const float *msum, void *y, int ycs, cudaStream_t st) {
     const long long total = static_cast<long long>(G.n) * G.ho * G.wo;
     const unsigned gx = static_cast<unsigned>((total + 127) / 128);
-    if (G.cout <= 4) {
-        generic_fwd_kernel<T, 4><<<dim3(gx, (G.cout + 3) / 4), 128, 0, st>>>(G, static_cast<const T *>(w), bias, msum, static_cast<T *>(y));
+    if (ycs <= 4) {
+        generic_fwd_kernel<T, 4><<<dim3(gx, (ycs + 3) / 4), 128, 0, st>>>(G, static_cast<const T *>(w), bias, msum, static_cast<T *>(y), ycs);
     } else {
-        generic_fwd_kernel<T, 8><<<dim3(gx, (G.cout + 7) / 8), 128, 0, st>>>(G, static_cast<const T *>(w), bias, msum, static_cast<T *>(y));
+        generic_fwd_kernel<T, 8><<<dim3(gx, (ycs + 7) / 8), 128, 0, st>>>(G, static_cast<const T *>(w), bias, msum, static_cast<T *>(y), ycs);
     }
     PCB_LAUNCH_CHECK();
     return 0;
 }
 
 template <typename T>
-int launch_dgrad(const GParams &G, const void *dc, const void *w, void *dx, cudaStream_t st) {
+int launch_dgrad(const GParams &G, const void *dc, int dcs, const void *w, const DxOut &O, cudaStream_t st) {
     const long long total = static_cast<long long>(G.n) * G.h * G.w;
     const unsigned gx = static_cast<unsigned>((total + 127) / 128);
-    generic_dgrad_kernel<T, 8><<<dim3(gx, (G.cin + 7) / 8), 128, 0, st>>>(G, static_cast<const T *>(dc), static_cast<const T *>(w), static_cast<T *>(dx));
+    generic_dgrad_kernel<T, 8><<<dim3(gx, (G.cin + 7) / 8), 128, 0, st>>>(G, static_cast<const T *>(dc), dcs, static_cast<const T *>(w), O);
     PCB_LAUNCH_CHECK();
     return 0;
 }
 
 template <typename T>
-int launch_wgrad(const GParams &G, const void *dc, float *dw, cudaStream_t st) {
+int launch_wgrad(const GParams &G, const void *dc, int dcs, float *dw, cudaStream_t st) {
     const int cig = G.cin / G.groups, cog = G.cout / G.groups;
     const int kg = G.kh * G.kw * cig;
     const long long total = static_cast<long long>(G.n) * G.ho * G.wo;
@@ -318,14 +325,14 @@ int launch_wgrad(const GParams &G, const void *dc, float *dw, cudaStream_t st) {
             long long slabs = std::max<long long>(1, std::min<long long>((8ll * pcb_num_sms()) / std::max(1, kt * ct), (total + 2047) / 2048));
             const int ppb = static_cast<int>(((total + slabs - 1) / slabs + PC - 1) / PC * PC);
             slabs = (total + ppb - 1) / ppb;
-            generic_wgrad_kernel<T, CO_T, K_T, PC><<<dim3(kt, ct, (unsigned)slabs), 256, 0, st>>>(G, static_cast<const T *>(dc), dw, g, ppb);
+            generic_wgrad_kernel<T, CO_T, K_T, PC><<<dim3(kt, ct, (unsigned)slabs), 256, 0, st>>>(G, static_cast<const T *>(dc), dcs, dw, g, ppb);
         } else {
             constexpr int CO_T = 64, K_T = 64, PC = 16;
             const int kt = (kg + K_T - 1) / K_T, ct = (cog + CO_T - 1) / CO_T;
             long long slabs = std::max<long long>(1, std::min<long long>((8ll * pcb_num_sms()) / std::max(1, kt * ct), (total + 1023) / 1024));
             const int ppb = static_cast<int>(((total + slabs - 1) / slabs + PC - 1) / PC * PC);
             slabs = (total + ppb - 1) / ppb;
-            generic_wgrad_kernel<T, CO_T, K_T, PC><<<dim3(kt, ct, (unsigned)slabs), 256, 0, st>>>(G, static_cast<const T *>(dc), dw, g, ppb);
+            generic_wgrad_kernel<T, CO_T, K_T, PC><<<dim3(kt, ct, (unsigned)slabs), 256, 0, st>>>(G, static_cast<const T *>(dc), dcs, dw, g, ppb);
         }
         PCB_LAUNCH_CHECK();
     }
@@ -343,27 +350,29 @@ int pcb_mask_sums(const pcb_conv *c, float *msum, uint8_t *newmask, cudaStream_t
     return 0;
 }
 
-int pcb_generic_forward(const pcb_conv *c, const void *w, const float *bias, void *y, float *msum, uint8_t *newmask,
-                        cudaStream_t st) {
-    (void)newmask;
+int pcb_generic_forward(const pcb_conv *c, const void *w, const float *bias, void *y, int y_cstride, const float *msum, cudaStream_t st) {
     GParams G;
     fill(G, c);
-    if (c->dtype == PCB_BF16) return launch_fwd<bf16>(G, w, bias, msum, y, st);
-    return launch_fwd<float>(G, w, bias, msum, y, st);
+    if (c->dtype == PCB_BF16) return launch_fwd<bf16>(G, w, bias, msum, y, y_cstride, st);
+    return launch_fwd<float>(G, w, bias, msum, y, y_cstride, st);
 }
 
-int pcb_generic_dgrad(const pcb_conv *c, const void *dc, const void *w_krsc, void *dx, cudaStream_t st) {
+int pcb_generic_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_krsc, void *const *dx, const int *dx_cstride,
+                      cudaStream_t st) {
     GParams G;
     fill(G, c);
-    if (c->dtype == PCB_BF16) return launch_dgrad<bf16>(G, dc, w_krsc, dx, st);
-    return launch_dgrad<float>(G, dc, w_krsc, dx, st);
+    DxOut O;
+    memset(&O, 0, sizeof(O));
+    for (int p = 0; p < c->nparts; ++p) { O.ptr[p] = dx[p]; O.cstride[p] = dx_cstride[p]; }
+    if (c->dtype == PCB_BF16) return launch_dgrad<bf16>(G, dc, dc_cstride, w_krsc, O, st);
+    return launch_dgrad<float>(G, dc, dc_cstride, w_krsc, O, st);
 }
 
-int pcb_generic_wgrad(const pcb_conv *c, const void *dc, float *dw, cudaStream_t st) {
+int pcb_generic_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, cudaStream_t st) {
     GParams G;
     fill(G, c);
     const size_t bytes = sizeof(float) * c->cout * c->kh * c->kw * (c->cin / c->groups);
     PCB_CUDA(cudaMemsetAsync(dw, 0, bytes, st));
-    if (c->dtype == PCB_BF16) return launch_wgrad<bf16>(G, dc, dw, st);
-    return launch_wgrad<float>(G, dc, dw, st);
+    if (c->dtype == PCB_BF16) return launch_wgrad<bf16>(G, dc, dc_cstride, dw, st);
+    return launch_wgrad<float>(G, dc, dc_cstride, dw, st);
 }

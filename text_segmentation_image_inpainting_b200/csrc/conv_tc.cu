@@ -2,25 +2,28 @@
 //
 // Replaces (per layer) the reference's pair of dense convolutions + ~9 elementwise passes
 // (models/partial_convolution.py:49-80): `feature_conv(x*mask)`, the all-ones `mask_conv`, `==0`,
-// `masked_fill_`, `(out-b)/mask_sum+b`, `masked_fill_`, `ones_like`+`masked_fill_`.
+// `masked_fill_`, `(out-b)/mask_sum+b`, `masked_fill_`, `ones_like`+`masked_fill_` -- and, in the U-Net
+// decoders, the `nn.Upsample` + `torch.cat` in front of it (models/image_inpainting.py:183-185).
 //
 // Forward / data-gradient kernel (one kernel, MODE template):
 //   GEMM view   M = output pixels (n*ho*wo) [fwd]  or input pixels (n*h*w) [dgrad]
-//               N = cout [fwd] / cin [dgrad],  K = taps * channels, walked tap-major in 64-channel blocks
+//               N = cout [fwd] / input channels [dgrad],  K walked tap-major in 64-element blocks
 //   A operand   im2col rows gathered by 4 producer warps with 16-byte cp.async (LDGSTS), zero-filled where
-//               the tap falls on padding or on a HOLE (x*mask folded into the load: no masked copy of x
-//               is ever materialised), across up to PCB_MAX_PARTS concatenated / 2x-nearest-upsampled
-//               sources (torch.cat + DoubleUpSample become index math).  Written straight into the
-//               128B-swizzled K-major layout UMMA reads.
-//   B operand   weights [N][K] bf16, TMA 2D tiles (SWIZZLE_128B), one elected thread.
+//               the tap falls on padding or on a HOLE (x*mask folded into the load: no masked copy of x is
+//               ever materialised), across up to 2 concatenated sources, each optionally 2x nearest-upsampled
+//               (torch.cat + DoubleUpSample become index math) and optionally channel-padded.  Written
+//               straight into the 128B-swizzled K-major layout UMMA reads.
+//               Small-Cin "row-packed" mode (cin <= 8, e.g. the RGB stem): one K block = one kernel ROW,
+//               its eight 16-byte chunks are the taps of that row, so a 7x7x3 stem costs 7 K blocks, not 49.
+//   B operand   weights [N][K] bf16 (K padded to the same block structure), TMA 2D tiles (SWIZZLE_128B).
 //   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BLOCK_N x K=16, fp32 accumulators in TMEM,
 //               issued by one thread; smem stages recycled through tcgen05.commit -> mbarrier.
 //   epilogue    TMEM -> registers (tcgen05.ld 32x32b), fwd: y = hole ? 0 : acc / s + bias (s = mask box
-//               sum), dgrad: dx = acc * input-mask; bf16 NHWC stores.
+//               sum), dgrad: dx_part = acc * input-mask of that part; bf16 NHWC stores.
 //
-// Weight-gradient kernel: D[ci][co] (+)= sum_pixels x_gathered[p][ci] * dc[p][co] per tap: both operands
-// are "pixel-row x 128-byte channel chunk" tiles, i.e. MN-major UMMA operands with the same swizzled smem
-// image as above; split-K over pixels with fp32 red.global.add.
+// Weight-gradient kernel: D[k][co] (+)= sum_pixels x_gathered[p][k] * dc[p][co] per tap: both operands are
+// "pixel-row x 128-byte channel chunk" tiles, i.e. MN-major UMMA operands with the same swizzled smem image
+// as above; split-K over pixels with fp32 red.global.add into the (logical, unpadded) KRSC gradient.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,24 +38,29 @@ constexpr int BLOCK_K = 64;                 // bf16 elements = 128 bytes = one s
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 constexpr int NUM_PRODUCER_THREADS = 128;
 constexpr int TC_THREADS = 192;             // 4 producer/epilogue warps + TMA warp + MMA warp
-constexpr int TC_MAX_PARTS = 2;        // U-Net inputs are cat([upsampled, skip]) at most
+constexpr int TC_MAX_PARTS = 2;             // U-Net inputs are cat([upsampled, skip]) at most
+
+inline int rup(int v, int m) { return (v + m - 1) / m * m; }
 
 struct TcPart {
     const bf16 *x;            // first channel of the part (fwd / wgrad gather source)
-    const uint32_t *tapmask;  // [m_total] bit t = tap t is in-bounds and not a hole (fwd / wgrad)
+    const uint64_t *tapmask;  // [m_total] bit t = tap t is in-bounds and not a hole (fwd / wgrad)
     const uint8_t *mask;      // input hole plane (dgrad epilogue), may be null
-    int c, choff, cstride, xup, mup;
+    bf16 *dx;                 // dgrad output of this part [n,h,w,dx_cstride] (null: not needed)
+    int c, c8, kext, koff, choff, cstride, xup, mup, dx_cstride;
 };
 
 struct TcParams {
     int n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil, ho, wo;
     int m_total;              // GEMM M
-    int nparts;
-    int no_guard;
+    int nparts, no_guard, rowpack;
+    int ktap;                 // K extent of one tap (sum of part kext); rowpack: 64 per kernel row
+    int ncols;                // GEMM N extent covered by the grid (multiple of BLOCK_N)
     TcPart parts[TC_MAX_PARTS];
-    const float *bias;        // fwd
-    const float *msum;        // fwd: [m_total]
-    bf16 *out;                // y (fwd) / dx (dgrad)
+    // fwd epilogue
+    const float *bias; const float *msum; bf16 *y; int y_cstride;
+    // dgrad gather source
+    const bf16 *dc; int dc_cstride, dc_c8, dc_kext;
     int *abort_flag;
 };
 
@@ -65,6 +73,14 @@ template <int BLOCK_N, int STAGES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, (BLOCK_N <= 128) ? 2 : 1)
 pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w) {
     constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
+    if (MODE == 1) {      // dgrad: skip N tiles none of whose parts wants a gradient (uniform per CTA)
+        bool any = false;
+        for (int p = 0; p < P.nparts; ++p)
+            if (P.parts[p].dx && n0 < P.parts[p].koff + P.parts[p].kext && n0 + BLOCK_N > P.parts[p].koff) any = true;
+        if (!any) return;
+    }
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
     const uint32_t sA = smem_base;
@@ -78,13 +94,8 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
     uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-    const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
-
     const int taps = P.kh * P.kw;
-    const int kchan = (MODE == 0) ? P.cin : P.cout;             // channels per tap along K
-    const int kb_per_tap = kchan / BLOCK_K;
-    const int num_kb = taps * kb_per_tap;
+    const int num_kb = (MODE == 0) ? (P.rowpack ? P.kh : taps * (P.ktap / BLOCK_K)) : taps * (P.dc_kext / BLOCK_K);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -129,55 +140,81 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
         }
 
         // per-row tap-validity bits (bounds + holes), loaded once per tile: the k-loop issues no mask loads
-        uint32_t tmv[TC_MAX_PARTS][8];
+        uint64_t tmv[TC_MAX_PARTS][8];
         if (MODE == 0) {
 #pragma unroll
             for (int p = 0; p < TC_MAX_PARTS; ++p)
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    tmv[p][i] = (p < P.nparts && prow[i]) ? __ldg(P.parts[p].tapmask + m0 + r0 + 16 * i) : 0u;
+                    tmv[p][i] = (p < P.nparts && prow[i]) ? __ldg(P.parts[p].tapmask + m0 + r0 + 16 * i) : 0ull;
         }
 
         int kb = 0;
         bool dead = false;
-        for (int tap = 0; tap < taps && !dead; ++tap) {
-            const int tr = tap / P.kw, tc = tap - tr * P.kw;
-            const int np = (MODE == 0) ? P.nparts : 1;
+        auto push = [&](const bf16 *const (&src)[8], const bool (&ok)[8]) -> bool {
+            const int s = kb % STAGES;
+            const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
+            if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 101)) return false;
+            const uint32_t dst = sA + s * A_STAGE_BYTES + r0 * 128 + sw;
 #pragma unroll
-            for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                if (p >= np || dead) break;
-                const TcPart &pt = P.parts[p];
+            for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), src[i], ok[i]);
+            ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
+            ptx::mbar_arrive(bar_full_a + 8 * s);
+            ++kb;
+            return true;
+        };
+
+        if (MODE == 0 && P.rowpack) {
+            // ---- small-Cin mode: K block = kernel row `tr`; chunk = tap column; source pixel shifts with the chunk
+            const TcPart &pt = P.parts[0];
+            for (int tr = 0; tr < P.kh && !dead; ++tr) {
                 const bf16 *src[8];
                 bool ok[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    int hi, wi;
-                    bool v = prow[i];
-                    if (MODE == 0) {
-                        hi = ph[i] + tr * P.dil;
-                        wi = pw[i] + tc * P.dil;
-                        v = (tmv[p][i] >> tap) & 1u;      // bounds + hole (0 for rows past m_total)
-                        hi >>= pt.xup; wi >>= pt.xup;
-                        const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
-                        src[i] = pt.x + (static_cast<long long>(pn[i] * hp + (v ? hi : 0)) * wp + (v ? wi : 0)) * pt.cstride + chunk * 8;
-                    } else {
-                        const int th = ph[i] - tr * P.dil, tw = pw[i] - tc * P.dil;
-                        hi = th / P.stride; wi = tw / P.stride;
-                        v = v && th >= 0 && tw >= 0 && (hi * P.stride == th) && (wi * P.stride == tw) && hi < P.ho && wi < P.wo;
-                        src[i] = pt.x + (static_cast<long long>(pn[i] * P.ho + (v ? hi : 0)) * P.wo + (v ? wi : 0)) * pt.cstride + chunk * 8;
-                    }
+                    const bool v = (chunk < P.kw) && ((tmv[0][i] >> (tr * P.kw + chunk)) & 1ull);
+                    const int hi = ph[i] + tr * P.dil, wi = pw[i] + chunk * P.dil;
+                    src[i] = pt.x + (static_cast<long long>(pn[i] * P.h + (v ? hi : 0)) * P.w + (v ? wi : 0)) * pt.cstride;
                     ok[i] = v;
                 }
-                const int nb = ((MODE == 0) ? pt.c : P.cout) / BLOCK_K;
-                for (int cb = 0; cb < nb; ++cb, ++kb) {
-                    const int s = kb % STAGES;
-                    const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
-                    if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 101)) { dead = true; break; }
-                    const uint32_t dst = sA + s * A_STAGE_BYTES + r0 * 128 + sw;
+                if (!push(src, ok)) dead = true;
+            }
+        } else {
+            for (int tap = 0; tap < taps && !dead; ++tap) {
+                const int tr = tap / P.kw, tc = tap - tr * P.kw;
+                const int np = (MODE == 0) ? P.nparts : 1;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), src[i] + cb * BLOCK_K, ok[i]);
-                    ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
-                    ptx::mbar_arrive(bar_full_a + 8 * s);
+                for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                    if (p >= np || dead) break;
+                    const TcPart &pt = P.parts[p];
+                    const bf16 *base[8];
+                    bool rv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        bool v;
+                        if (MODE == 0) {
+                            v = (tmv[p][i] >> tap) & 1ull;                  // bounds + hole (0 for rows past m_total)
+                            const int hi = (ph[i] + tr * P.dil) >> pt.xup, wi = (pw[i] + tc * P.dil) >> pt.xup;
+                            const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
+                            base[i] = pt.x + (static_cast<long long>(pn[i] * hp + (v ? hi : 0)) * wp + (v ? wi : 0)) * pt.cstride + chunk * 8;
+                        } else {
+                            const int th = ph[i] - tr * P.dil, tw = pw[i] - tc * P.dil;
+                            const int hi = th / P.stride, wi = tw / P.stride;
+                            v = prow[i] && th >= 0 && tw >= 0 && (hi * P.stride == th) && (wi * P.stride == tw) && hi < P.ho && wi < P.wo;
+                            base[i] = P.dc + (static_cast<long long>(pn[i] * P.ho + (v ? hi : 0)) * P.wo + (v ? wi : 0)) * P.dc_cstride + chunk * 8;
+                        }
+                        rv[i] = v;
+                    }
+                    const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
+                    const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
+                    for (int cb = 0; cb < nb; ++cb) {
+                        const bool cv = cb * BLOCK_K + chunk * 8 < c8;       // channel padding of the part: zero-fill
+                        const bf16 *src[8];
+                        bool ok[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { src[i] = base[i] + (cv ? cb * BLOCK_K : 0); ok[i] = rv[i] && cv; }
+                        if (!push(src, ok)) { dead = true; break; }
+                    }
                 }
             }
         }
@@ -200,43 +237,51 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
             if (MODE == 1 && rvalid) {
                 en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
             }
-            const int ncols_total = (MODE == 0) ? P.cout : P.cin;
-            bf16 *orow = P.out + static_cast<long long>(rvalid ? m : 0) * ncols_total + n0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
                 ptx::tmem_ld_wait();
+                const int col = n0 + c0;
+                bf16 *orow = nullptr;
+                int nstore = 0;                      // channels to store from this 32-column chunk (multiple of 8)
                 float scale = inv;
-                if (MODE == 1) {
-                    // dx = acc * input mask of the part this channel chunk belongs to
+                if (MODE == 0) {
+                    if (rvalid && col < P.y_cstride) { orow = P.y + static_cast<long long>(m) * P.y_cstride + col; nstore = min(32, P.y_cstride - col); }
+                } else {
                     scale = 1.f;
-                    const int ch = n0 + c0;
                     for (int p = 0; p < P.nparts; ++p) {
                         const TcPart &pt = P.parts[p];
-                        if (ch >= pt.choff && ch < pt.choff + pt.c && pt.mask != nullptr && rvalid)
-                            scale = pt.mask[(static_cast<long long>(en) * (P.h >> pt.mup) + (eh >> pt.mup)) * (P.w >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
+                        const int local = col - pt.koff;
+                        if (local >= 0 && local < pt.kext && pt.dx != nullptr && local < pt.c8 && rvalid) {
+                            orow = pt.dx + static_cast<long long>(m) * pt.dx_cstride + local;
+                            nstore = min(32, pt.c8 - local);
+                            if (pt.mask != nullptr)          // dx = acc * input mask of this part
+                                scale = pt.mask[(static_cast<long long>(en) * (P.h >> pt.mup) + (eh >> pt.mup)) * (P.w >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
+                        }
                     }
                 }
-                if (rvalid && n0 + c0 < ncols_total) {
+                if (nstore > 0) {
                     uint4 o[4];
                     __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(o);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
                         if (MODE == 0) {
-                            const float b0 = P.bias ? P.bias[n0 + c0 + 2 * j] : 0.f;
-                            const float b1 = P.bias ? P.bias[n0 + c0 + 2 * j + 1] : 0.f;
-                            a = hole ? 0.f : a * scale + b0;
-                            b = hole ? 0.f : b * scale + b1;
+                            const int co = col + 2 * j;
+                            const float b0 = (P.bias && co < P.cout) ? P.bias[co] : 0.f;
+                            const float b1 = (P.bias && co + 1 < P.cout) ? P.bias[co + 1] : 0.f;
+                            a = (hole || co >= P.cout) ? 0.f : a * scale + b0;
+                            b = (hole || co + 1 >= P.cout) ? 0.f : b * scale + b1;
                         } else {
                             a *= scale; b *= scale;
                         }
                         ob[j] = __floats2bfloat162_rn(a, b);
                     }
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = o[j];
+                    for (int j = 0; j < 4; ++j)
+                        if (j * 8 < nstore) dst[j] = o[j];
                 }
             }
         }
@@ -288,13 +333,14 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
 struct WgParams {
     int n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil, ho, wo;
     int m_total;              // n*ho*wo : the reduction (K) extent
-    int nparts;
+    int nparts, rowpack;
+    int ktap;                 // gathered-operand extent per tap group (sum of part kext; rowpack: 64)
+    int ntaps;                // tap groups walked: kh*kw, or kh in rowpack mode
     TcPart parts[TC_MAX_PARTS];
-    int taps_per_cta;         // T
     int tap_groups;
-    int ci_tiles;             // ceil(cin / 128)
+    int ci_tiles;             // ceil(ktap / 128)
     int kb_per_split;
-    float *dw;                // [cout][taps][cin] fp32, pre-zeroed
+    float *dw;                // [cout][kh*kw][cin] fp32, pre-zeroed
     int *abort_flag;
 };
 
@@ -302,7 +348,7 @@ template <int BLOCK_N, int T, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant__ CUtensorMap tmap_dc) {
     constexpr int B_STAGE_BYTES = BLOCK_N * 128;            // [64 px][BLOCK_N co] as BLOCK_N/64 blocks of 8 KB
-    constexpr int A_TAP_BYTES = 16384;                      // [64 px][128 ci] as 2 blocks of 8 KB
+    constexpr int A_TAP_BYTES = 16384;                      // [64 px][128 k] as 2 blocks of 8 KB
     constexpr int A_STAGE = T * A_TAP_BYTES;
     constexpr int TMEM_COLS = (T * BLOCK_N <= 64) ? 64 : (T * BLOCK_N <= 128) ? 128 : (T * BLOCK_N <= 256) ? 256 : 512;
     static_assert(T * BLOCK_N <= 512, "TMEM overflow");
@@ -322,9 +368,9 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
     const int ci_tile = bx % P.ci_tiles; bx /= P.ci_tiles;
     const int tap_group = bx % P.tap_groups;
     const int co_tile = bx / P.tap_groups;
-    const int taps = P.kh * P.kw;
+    const int taps_full = P.kh * P.kw;
     const int tap0 = tap_group * T;
-    const int ntap = min(T, taps - tap0);
+    const int ntap = min(T, P.ntaps - tap0);
     const int n0 = co_tile * BLOCK_N;
     const int total_kb = (P.m_total + 63) / 64;
     const int kb_begin = blockIdx.y * P.kb_per_split;
@@ -351,30 +397,38 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_generic;
 
     if (warp < 4) {
-        // ============ A producers: gather x rows (K = pixels) for each tap, 2 x 64-channel blocks ============
+        // ============ A producers: gather x rows (K = pixels) for each tap, 2 x 64-element blocks ============
         const int t = threadIdx.x;
         const int chunk = t & 7, r0 = t >> 3;
         const uint32_t sw = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);
-        // the two 64-channel blocks of this ci tile -> (part, channel offset inside the part)
+        // the two 64-element blocks of this k tile -> (part, channel offset inside the part, chunk readable?)
         int blk_part[2], blk_off[2];
+        bool blk_cv[2];
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
-            const int ch = ci_tile * 128 + hb * 64;
-            blk_part[hb] = -1; blk_off[hb] = 0;
-            for (int p = 0; p < P.nparts; ++p)
-                if (ch >= P.parts[p].choff && ch < P.parts[p].choff + P.parts[p].c) { blk_part[hb] = p; blk_off[hb] = ch - P.parts[p].choff; }
+            const int kpos = ci_tile * 128 + hb * 64;
+            blk_part[hb] = -1; blk_off[hb] = 0; blk_cv[hb] = false;
+            if (P.rowpack) {
+                if (kpos == 0) { blk_part[hb] = 0; blk_cv[hb] = chunk < P.kw; }
+            } else {
+                for (int p = 0; p < P.nparts; ++p)
+                    if (kpos >= P.parts[p].koff && kpos < P.parts[p].koff + P.parts[p].kext) {
+                        blk_part[hb] = p; blk_off[hb] = kpos - P.parts[p].koff;
+                        blk_cv[hb] = blk_off[hb] + chunk * 8 < P.parts[p].c8;
+                    }
+            }
         }
         const int plane = P.ho * P.wo;
         bool dead = false;
         // tap-validity words are prefetched one k-block ahead so their latency hides behind the barrier wait
-        uint32_t tm_next[4][2];
-        auto load_tm = [&](int kb, uint32_t (&dst)[4][2]) {
+        uint64_t tm_next[4][2];
+        auto load_tm = [&](int kb, uint64_t (&dst)[4][2]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = kb * 64 + r0 + 16 * i;
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb)
-                    dst[i][hb] = (m < P.m_total && blk_part[hb] >= 0) ? __ldg(P.parts[blk_part[hb]].tapmask + m) : 0u;
+                    dst[i][hb] = (m < P.m_total && blk_part[hb] >= 0 && blk_cv[hb]) ? __ldg(P.parts[blk_part[hb]].tapmask + m) : 0ull;
             }
         };
         if (num_kb > 0) load_tm(kb_begin, tm_next);
@@ -382,7 +436,7 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
             const int kb = kb_begin + it;
             const int s = it % STAGES;
             const uint32_t parity = ((it / STAGES) & 1) ^ 1;
-            uint32_t tm_cur[4][2];
+            uint64_t tm_cur[4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { tm_cur[i][0] = tm_next[i][0]; tm_cur[i][1] = tm_next[i][1]; }
             if (it + 1 < num_kb) load_tm(kb + 1, tm_next);
@@ -391,22 +445,23 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
             for (int i = 0; i < 4; ++i) {
                 const int r = r0 + 16 * i;
                 const int m = kb * 64 + r;
-                const bool rv = m < P.m_total;
-                const int mm = rv ? m : 0;
+                const int mm = m < P.m_total ? m : 0;
                 const int nn = mm / plane, rem = mm - nn * plane;
                 const int oh = rem / P.wo, ow = rem - oh * P.wo;
-                const uint32_t tm[2] = {tm_cur[i][0], tm_cur[i][1]};
                 for (int tl = 0; tl < ntap; ++tl) {
-                    const int tap = tap0 + tl;
-                    const int tr = tap / P.kw, tc = tap - tr * P.kw;
+                    const int tg = tap0 + tl;                      // tap (or kernel row in rowpack mode)
+                    int tr, tc, bit;
+                    if (P.rowpack) { tr = tg; tc = chunk; bit = tg * P.kw + chunk; }
+                    else { tr = tg / P.kw; tc = tg - tr * P.kw; bit = tg; }
                     const int hi = oh * P.stride - P.pad_h + tr * P.dil, wi = ow * P.stride - P.pad_w + tc * P.dil;
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
-                        const bool v = (tm[hb] >> tap) & 1u;
+                        const bool v = (tm_cur[i][hb] >> bit) & 1ull;   // 0 unless the block/chunk exists
                         const int p = blk_part[hb] >= 0 ? blk_part[hb] : 0;
                         const TcPart &pt = P.parts[p];
                         const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
-                        const bf16 *src = pt.x + (static_cast<long long>(nn * hp + (v ? (hi >> pt.xup) : 0)) * wp + (v ? (wi >> pt.xup) : 0)) * pt.cstride + blk_off[hb] + chunk * 8;
+                        const bf16 *src = pt.x + (static_cast<long long>(nn * hp + (v ? (hi >> pt.xup) : 0)) * wp + (v ? (wi >> pt.xup) : 0)) * pt.cstride +
+                                          (P.rowpack ? 0 : (v ? blk_off[hb] + chunk * 8 : 0));
                         const uint32_t dst = sA + s * A_STAGE + tl * A_TAP_BYTES + hb * 8192 + r * 128 + sw;
                         ptx::cp_async_16(dst, src, v);
                     }
@@ -417,24 +472,34 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
         }
         ptx::cp_async_wait<0>();
 
-        // ============ epilogue: D[ci][co] per tap -> red.global.add into dw[co][tap][ci] ============
+        // ============ epilogue: D[k][co] per tap -> red.global.add into dw[co][tap][ci] ============
         if (!dead && num_kb > 0 && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 202)) {
             ptx::tc_fence_after();
             const int row = warp * 32 + lane;
-            const int ci = ci_tile * 128 + row;
+            const int kpos = ci_tile * 128 + row;
             for (int tl = 0; tl < ntap; ++tl) {
-                const int tap = tap0 + tl;
+                const int tg = tap0 + tl;
+                int ci = -1, tap = tg;
+                if (P.rowpack) {
+                    const int tc = row >> 3, ch = row & 7;
+                    if (row < 64 && ci_tile == 0 && tc < P.kw && ch < P.cin) { ci = ch; tap = tg * P.kw + tc; }
+                } else {
+                    for (int p = 0; p < P.nparts; ++p) {
+                        const int local = kpos - P.parts[p].koff;
+                        if (local >= 0 && local < P.parts[p].c) ci = P.parts[p].choff + local;
+                    }
+                }
 #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + tl * BLOCK_N + c0, r);
                     ptx::tmem_ld_wait();
-                    if (ci < P.cin) {
+                    if (ci >= 0) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int co = n0 + c0 + j;
                             if (co < P.cout)
-                                atomicAdd(P.dw + (static_cast<long long>(co) * taps + tap) * P.cin + ci, __uint_as_float(r[j]));
+                                atomicAdd(P.dw + (static_cast<long long>(co) * taps_full + tap) * P.cin + ci, __uint_as_float(r[j]));
                         }
                     }
                 }
@@ -495,7 +560,7 @@ struct TapMaskParams {
     int n, h, w, kh, kw, stride, pad_h, pad_w, dil, ho, wo, m_total, nparts;
     const uint8_t *mask[TC_MAX_PARTS];
     int mup[TC_MAX_PARTS];
-    uint32_t *out;   // [nparts][m_total]
+    uint64_t *out;   // [nparts][m_total]
 };
 
 __global__ void tapmask_kernel(const TapMaskParams P) {
@@ -503,20 +568,52 @@ __global__ void tapmask_kernel(const TapMaskParams P) {
     if (m >= P.m_total) return;
     const int plane = P.ho * P.wo;
     const int nn = m / plane, rem = m - nn * plane, oh = rem / P.wo, ow = rem - oh * P.wo;
-    for (int p = 0; p < P.nparts; ++p) {
-        uint32_t bits = 0;
+#pragma unroll
+    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+        if (p >= P.nparts) break;
+        const uint8_t *mk = P.mask[p];
+        const int u = P.mup[p];
+        uint64_t bits = 0;
         int tap = 0;
         for (int tr = 0; tr < P.kh; ++tr)
             for (int tc = 0; tc < P.kw; ++tc, ++tap) {
                 const int hi = oh * P.stride - P.pad_h + tr * P.dil, wi = ow * P.stride - P.pad_w + tc * P.dil;
                 bool v = hi >= 0 && hi < P.h && wi >= 0 && wi < P.w;
-                if (v && P.mask[p]) {
-                    const int u = P.mup[p];
-                    v = P.mask[p][(static_cast<long long>(nn) * (P.h >> u) + (hi >> u)) * (P.w >> u) + (wi >> u)] != 0;
-                }
-                bits |= (v ? 1u : 0u) << tap;
+                if (v && mk) v = mk[(static_cast<long long>(nn) * (P.h >> u) + (hi >> u)) * (P.w >> u) + (wi >> u)] != 0;
+                bits |= (v ? 1ull : 0ull) << tap;
             }
         P.out[static_cast<long long>(p) * P.m_total + m] = bits;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight re-layout: fp32 master KRSC [cout][taps][cin] -> padded bf16 operands of the two GEMMs
+//   w_fwd  [rows_f][kf] : row = co ; k = tap*ktap + koff_p + local        (rowpack: tr*64 + tc*8 + ci)
+//   w_dg   [ktap][kd]   : row = koff_p + local ; k = tap*cout64 + co      (not built in rowpack mode)
+// -------------------------------------------------------------------------------------------------
+struct WPrepParams {
+    int cout, taps, cin, kw, rowpack, nparts, ktap, cout64;
+    int choff[TC_MAX_PARTS], c[TC_MAX_PARTS], koff[TC_MAX_PARTS];
+    long long kf, kd;
+};
+
+__global__ void tc_weight_prepare_kernel(const float *__restrict__ wm, const WPrepParams P, bf16 *__restrict__ w_fwd, bf16 *__restrict__ w_dg) {
+    const long long total = static_cast<long long>(P.cout) * P.taps * P.cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % P.cin);
+        const long long t = i / P.cin;
+        const int tap = static_cast<int>(t % P.taps), co = static_cast<int>(t / P.taps);
+        const bf16 v = __float2bfloat16_rn(wm[i]);
+        if (P.rowpack) {
+            const int tr = tap / P.kw, tc = tap - tr * P.kw;
+            w_fwd[static_cast<long long>(co) * P.kf + tr * 64 + tc * 8 + ci] = v;
+        } else {
+            int p = 0;
+            while (p + 1 < P.nparts && ci >= P.choff[p] + P.c[p]) ++p;
+            const int kpos = P.koff[p] + (ci - P.choff[p]);
+            w_fwd[static_cast<long long>(co) * P.kf + static_cast<long long>(tap) * P.ktap + kpos] = v;
+            if (w_dg) w_dg[static_cast<long long>(kpos) * P.kd + static_cast<long long>(tap) * P.cout64 + co] = v;
+        }
     }
 }
 
@@ -539,19 +636,19 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2D bf16 row-major [rows][cols] tensor, box {64 cols (128 bytes), box_rows}, SWIZZLE_128B
-int make_tmap_2d(CUtensorMap *tm, const void *base, long long rows, long long cols, int box_rows) {
+// 2D bf16 row-major [rows][cols] tensor (row pitch `pitch_elems`), box {64 cols (128 bytes), box_rows}, SWIZZLE_128B
+int make_tmap_2d(CUtensorMap *tm, const void *base, long long rows, long long cols, long long pitch_elems, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     PCB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    PCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d base=%p", (int)r, rows,
-              cols, box_rows, base);
+    PCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld pitch=%lld box_rows=%d base=%p", (int)r,
+              rows, cols, pitch_elems, box_rows, base);
     return 0;
 }
 
@@ -564,28 +661,59 @@ int *abort_flag_ptr() {
     return flag;
 }
 
-bool parts_ok_for_tc(const pcb_conv *c) {
+bool is_rowpack(const pcb_conv *c) { return c->nparts == 1 && c->cin <= 8 && c->kw <= 8 && c->parts[0].x_up == 0; }
+
+bool common_ok(const pcb_conv *c) {
+    if (c->dtype != PCB_BF16 || c->groups != 1 || c->kh * c->kw > 64) return false;
     if (c->nparts < 1 || c->nparts > TC_MAX_PARTS) return false;
     for (int p = 0; p < c->nparts; ++p) {
         const pcb_part &pt = c->parts[p];
-        if (pt.c % 64 != 0 || pt.x_cstride % 8 != 0) return false;
+        if (pt.x_cstride % 8 != 0 || pt.x_cstride < rup(pt.c, 8)) return false;     // 16-byte chunks must be readable
         if (pt.x && (reinterpret_cast<uintptr_t>(pt.x) & 15)) return false;
     }
-    return true;
+    if (is_rowpack(c)) return c->cout >= 16;
+    // tensor cores pay off once the reduction is reasonably wide; tiny-channel layers stay on the generic kernels
+    return c->cin >= 32 || c->cout >= 32;
 }
 
-bool common_ok(const pcb_conv *c) {
-    return c->dtype == PCB_BF16 && c->groups == 1 && c->kh * c->kw <= 32 && c->cin % 64 == 0 && c->cout % 64 == 0 &&
-           parts_ok_for_tc(c);
+struct Layout {
+    int rowpack, ktap, cout64, rows_f, bn_f;
+    long long kf, kd;
+    int koff[TC_MAX_PARTS], kext[TC_MAX_PARTS];
+};
+
+Layout layout_of(const pcb_conv *c) {
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    L.rowpack = is_rowpack(c);
+    const int taps = c->kh * c->kw;
+    if (L.rowpack) {
+        L.ktap = 64; L.koff[0] = 0; L.kext[0] = 64;
+        L.kf = static_cast<long long>(c->kh) * 64;
+    } else {
+        int off = 0;
+        for (int p = 0; p < c->nparts; ++p) { L.koff[p] = off; L.kext[p] = rup(c->parts[p].c, 64); off += L.kext[p]; }
+        L.ktap = off;
+        L.kf = static_cast<long long>(taps) * L.ktap;
+    }
+    L.cout64 = rup(c->cout, 64);
+    L.bn_f = (c->cout % 128 == 0) ? 128 : 64;
+    L.rows_f = rup(c->cout, L.bn_f);
+    L.kd = static_cast<long long>(taps) * L.cout64;
+    return L;
 }
 
-void fill_parts(const pcb_conv *c, TcPart *out, const uint32_t *tapmask, long long m_total) {
+void fill_parts(const pcb_conv *c, const Layout &L, TcPart *out, const uint64_t *tapmask, long long m_total) {
     int off = 0;
     for (int p = 0; p < c->nparts; ++p) {
         out[p].x = static_cast<const bf16 *>(c->parts[p].x);
         out[p].tapmask = tapmask ? tapmask + static_cast<long long>(p) * m_total : nullptr;
         out[p].mask = c->parts[p].mask;
+        out[p].dx = nullptr; out[p].dx_cstride = 0;
         out[p].c = c->parts[p].c;
+        out[p].c8 = rup(c->parts[p].c, 8);
+        out[p].kext = L.kext[p];
+        out[p].koff = L.koff[p];
         out[p].choff = off;
         out[p].cstride = c->parts[p].x_cstride;
         out[p].xup = c->parts[p].x_up;
@@ -594,8 +722,9 @@ void fill_parts(const pcb_conv *c, TcPart *out, const uint32_t *tapmask, long lo
     }
 }
 
-int launch_tapmask(const pcb_conv *c, uint32_t *out, cudaStream_t st) {
+int launch_tapmask(const pcb_conv *c, uint64_t *out, cudaStream_t st) {
     TapMaskParams T;
+    memset(&T, 0, sizeof(T));
     T.n = c->n; T.h = c->h; T.w = c->w; T.kh = c->kh; T.kw = c->kw; T.stride = c->stride; T.pad_h = c->pad_h;
     T.pad_w = c->pad_w; T.dil = c->dil; T.ho = c->ho; T.wo = c->wo; T.m_total = c->n * c->ho * c->wo; T.nparts = c->nparts;
     for (int p = 0; p < c->nparts; ++p) { T.mask[p] = c->parts[p].mask; T.mup[p] = c->parts[p].mask_up; }
@@ -605,8 +734,15 @@ int launch_tapmask(const pcb_conv *c, uint32_t *out, cudaStream_t st) {
     return 0;
 }
 
+void base_params(TcParams &P, const pcb_conv *c, const Layout &L) {
+    memset(&P, 0, sizeof(P));
+    P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
+    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo;
+    P.nparts = c->nparts; P.no_guard = c->no_guard; P.rowpack = L.rowpack; P.ktap = L.ktap;
+}
+
 template <int BLOCK_N, int STAGES, int MODE>
-int launch_fwd(const TcParams &P, const CUtensorMap &tm, int ncols, cudaStream_t st) {
+int launch_fwd(const TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     constexpr size_t smem = 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
     auto kern = pconv_tc_kernel<BLOCK_N, STAGES, MODE>;
     static bool attr_done = false;
@@ -614,7 +750,7 @@ int launch_fwd(const TcParams &P, const CUtensorMap &tm, int ncols, cudaStream_t
         PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid(ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
+    dim3 grid(P.ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
     kern<<<grid, TC_THREADS, smem, st>>>(P, tm);
     PCB_LAUNCH_CHECK();
     return 0;
@@ -622,59 +758,89 @@ int launch_fwd(const TcParams &P, const CUtensorMap &tm, int ncols, cudaStream_t
 
 }  // namespace
 
-// ---- eligibility ---------------------------------------------------------------------------------
-bool pcb_tc_forward_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
-bool pcb_tc_dgrad_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
-bool pcb_tc_wgrad_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
+// ---- eligibility / layouts -----------------------------------------------------------------------
+bool pcb_tc_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
 
-size_t pcb_tc_forward_workspace(const pcb_conv *c) {
-    return static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint32_t);
+size_t pcb_tc_workspace(const pcb_conv *c) {
+    return static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint64_t);
 }
 
-int pcb_tc_forward_ws(const pcb_conv *c, const void *w, const float *bias, void *y, const float *msum, uint32_t *tapmask,
-                      cudaStream_t st) {
+void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems) {
+    const Layout L = layout_of(c);
+    *fwd_elems = static_cast<size_t>(L.rows_f) * L.kf;
+    *dgrad_elems = L.rowpack ? 0 : static_cast<size_t>(rup(L.ktap, 128)) * L.kd;
+}
+
+int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, cudaStream_t st) {
+    const Layout L = layout_of(c);
+    size_t fe, de;
+    pcb_tc_weight_layout(c, &fe, &de);
+    PCB_CUDA(cudaMemsetAsync(w_fwd, 0, fe * 2, st));
+    if (w_dgrad && de) PCB_CUDA(cudaMemsetAsync(w_dgrad, 0, de * 2, st));
+    WPrepParams W;
+    memset(&W, 0, sizeof(W));
+    W.cout = c->cout; W.taps = c->kh * c->kw; W.cin = c->cin; W.kw = c->kw; W.rowpack = L.rowpack; W.nparts = c->nparts;
+    W.ktap = L.ktap; W.cout64 = L.cout64; W.kf = L.kf; W.kd = L.kd;
+    int off = 0;
+    for (int p = 0; p < c->nparts; ++p) { W.choff[p] = off; W.c[p] = c->parts[p].c; W.koff[p] = L.koff[p]; off += c->parts[p].c; }
+    const long long total = static_cast<long long>(c->cout) * W.taps * c->cin;
+    const int grid = static_cast<int>(std::min<long long>((total + 1023) / 1024, 8ll * pcb_num_sms()));
+    tc_weight_prepare_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd),
+                                                                   (w_dgrad && de) ? static_cast<bf16 *>(w_dgrad) : nullptr);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
+                      uint64_t *tapmask, cudaStream_t st) {
     int *flag = abort_flag_ptr();
     PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
+    PCB_CHECK(y_cstride % 8 == 0 && y_cstride >= c->cout, "tensor-core forward: y channel stride must be a multiple of 8 and >= cout");
     if (int rc = launch_tapmask(c, tapmask, st)) return rc;
+    const Layout L = layout_of(c);
     TcParams P;
-    memset(&P, 0, sizeof(P));
-    P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
-    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = (int)m_total;
-    P.nparts = c->nparts; P.no_guard = c->no_guard;
-    fill_parts(c, P.parts, tapmask, m_total);
-    P.bias = bias; P.msum = msum; P.out = static_cast<bf16 *>(y); P.abort_flag = flag;
+    base_params(P, c, L);
+    P.m_total = static_cast<int>(m_total);
+    fill_parts(c, L, P.parts, tapmask, m_total);
+    P.bias = bias; P.msum = msum; P.y = static_cast<bf16 *>(y); P.y_cstride = y_cstride; P.abort_flag = flag;
+    P.ncols = L.rows_f;
     CUtensorMap tm;
-    const int bn = (c->cout % 128 == 0) ? 128 : 64;
-    if (int rc = make_tmap_2d(&tm, w, c->cout, static_cast<long long>(c->kh) * c->kw * c->cin, bn)) return rc;
-    if (bn == 128) return launch_fwd<128, 3, 0>(P, tm, c->cout, st);
-    return launch_fwd<64, 4, 0>(P, tm, c->cout, st);
+    if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
+    if (L.bn_f == 128) return launch_fwd<128, 3, 0>(P, tm, st);
+    return launch_fwd<64, 4, 0>(P, tm, st);
 }
 
-int pcb_tc_dgrad(const pcb_conv *c, const void *dc, const void *wt, void *dx, cudaStream_t st) {
+bool pcb_tc_dgrad_supported(const pcb_conv *c) { return pcb_tc_eligible(c) && !is_rowpack(c); }
+
+int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
+                 cudaStream_t st) {
     int *flag = abort_flag_ptr();
     PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
     const long long m_total = static_cast<long long>(c->n) * c->h * c->w;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
+    PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= rup(c->cout, 8), "tensor-core dgrad: dc channel stride must be a multiple of 8");
+    const Layout L = layout_of(c);
     TcParams P;
-    memset(&P, 0, sizeof(P));
-    P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
-    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = (int)m_total;
-    P.nparts = c->nparts;
-    fill_parts(c, P.parts, nullptr, 0);
-    // the gather source of dgrad is dc itself: overwrite part 0's x fields (mask/choff/c of the parts stay for the epilogue)
-    P.parts[0].x = static_cast<const bf16 *>(dc);
-    P.parts[0].cstride = c->cout;
-    P.out = static_cast<bf16 *>(dx); P.abort_flag = flag;
+    base_params(P, c, L);
+    P.m_total = static_cast<int>(m_total);
+    fill_parts(c, L, P.parts, nullptr, 0);
+    for (int p = 0; p < c->nparts; ++p) {
+        P.parts[p].dx = static_cast<bf16 *>(dx[p]);
+        P.parts[p].dx_cstride = dx_cstride[p];
+        PCB_CHECK(!dx[p] || (dx_cstride[p] % 8 == 0 && dx_cstride[p] >= P.parts[p].c8 && (reinterpret_cast<uintptr_t>(dx[p]) & 15) == 0),
+                  "tensor-core dgrad: dx[%d] must be 16-byte aligned with a channel stride that is a multiple of 8", p);
+    }
+    P.dc = static_cast<const bf16 *>(dc); P.dc_cstride = dc_cstride; P.dc_c8 = rup(c->cout, 8); P.dc_kext = L.cout64;
+    P.abort_flag = flag;
+    const int bn = (L.ktap % 128 == 0) ? 128 : 64;
+    P.ncols = L.ktap;
     CUtensorMap tm;
-    const int bn = (c->cin % 128 == 0) ? 128 : 64;
-    if (int rc = make_tmap_2d(&tm, wt, c->cin, static_cast<long long>(c->kh) * c->kw * c->cout, bn)) return rc;
-    if (bn == 128) return launch_fwd<128, 3, 1>(P, tm, c->cin, st);
-    return launch_fwd<64, 4, 1>(P, tm, c->cin, st);
+    if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
+    if (bn == 128) return launch_fwd<128, 3, 1>(P, tm, st);
+    return launch_fwd<64, 4, 1>(P, tm, st);
 }
-
-size_t pcb_tc_wgrad_workspace(const pcb_conv *c) { return pcb_tc_forward_workspace(c); }
 
 template <int BLOCK_N, int T, int STAGES>
 static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream_t st) {
@@ -685,16 +851,14 @@ static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream
         PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    const int taps = P.kh * P.kw;
-    P.taps_per_cta = T;
-    P.tap_groups = (taps + T - 1) / T;
-    P.ci_tiles = (P.cin + 127) / 128;
-    const int co_tiles = cout / BLOCK_N;
+    P.tap_groups = (P.ntaps + T - 1) / T;
+    P.ci_tiles = (P.ktap + 127) / 128;
+    const int co_tiles = (cout + BLOCK_N - 1) / BLOCK_N;
     const int base_ctas = co_tiles * P.tap_groups * P.ci_tiles;
     const int total_kb = (P.m_total + 63) / 64;
     int splits = (4 * pcb_num_sms() + base_ctas - 1) / base_ctas;      // aim at ~4 CTAs per SM worth of work
-    splits = max(1, min(splits, total_kb));
-    splits = min(splits, 65535);
+    splits = std::max(1, std::min(splits, total_kb));
+    splits = std::min(splits, 65535);
     P.kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
     dim3 grid(base_ctas, splits);
@@ -703,25 +867,27 @@ static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream
     return 0;
 }
 
-int pcb_tc_wgrad(const pcb_conv *c, const void *dc, float *dw, void *workspace, cudaStream_t st) {
+int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, cudaStream_t st) {
     int *flag = abort_flag_ptr();
     PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
     PCB_CHECK(workspace != nullptr, "pcb_tc_wgrad: workspace required");
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
-    uint32_t *tapmask = static_cast<uint32_t *>(workspace);
+    PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= c->cout, "tensor-core wgrad: dc channel stride must be a multiple of 8");
+    uint64_t *tapmask = static_cast<uint64_t *>(workspace);
     if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     const size_t dw_bytes = sizeof(float) * c->cout * c->kh * c->kw * c->cin;
     PCB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, st));
+    const Layout L = layout_of(c);
     WgParams P;
     memset(&P, 0, sizeof(P));
     P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
-    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = (int)m_total;
-    P.nparts = c->nparts;
-    fill_parts(c, P.parts, tapmask, m_total);
+    P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo; P.m_total = static_cast<int>(m_total);
+    P.nparts = c->nparts; P.rowpack = L.rowpack; P.ktap = L.ktap; P.ntaps = L.rowpack ? c->kh : c->kh * c->kw;
+    fill_parts(c, L, P.parts, tapmask, m_total);
     P.dw = dw; P.abort_flag = flag;
     CUtensorMap tm;
-    if (int rc = make_tmap_2d(&tm, dc, m_total, c->cout, 64)) return rc;
+    if (int rc = make_tmap_2d(&tm, dc, m_total, c->cout, dc_cstride, 64)) return rc;
     if (c->cout % 256 == 0) return launch_wgrad<256, 2, 3>(P, tm, c->cout, st);
     if (c->cout % 128 == 0) return launch_wgrad<128, 3, 3>(P, tm, c->cout, st);
     return launch_wgrad<64, 3, 3>(P, tm, c->cout, st);

@@ -217,22 +217,23 @@ __global__ void bn_param_grad_kernel(const double *sum_g, const double *sum_gx, 
 }
 
 // dc = dy * [s>0]/s ; dbias += sum dy*[s>0].  msum is [mg][count]; group of channel ch = ch / (c/mg).
+// dy rows have pitch dys, dc rows pitch dcs (>= c); dc channels [c, dcs) are zero-filled.
 template <typename T>
-__global__ void renorm_bwd_kernel(const T *__restrict__ dy, const float *__restrict__ msum, long long count, int c, int mg, int no_guard,
-                                  T *__restrict__ dc, float *dbias) {
-    // scalar-general: thread per element (channels fastest) with a per-block smem bias reduction
+__global__ void renorm_bwd_kernel(const T *__restrict__ dy, int dys, const float *__restrict__ msum, long long count, int c, int mg,
+                                  int no_guard, T *__restrict__ dc, int dcs, float *dbias) {
     extern __shared__ float s_db[];
     for (int i = threadIdx.x; i < c; i += blockDim.x) s_db[i] = 0.f;
     __syncthreads();
     const int cog = c / mg;
-    const long long numel = count * c;
+    const long long numel = count * dcs;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long row = i / c;
-        const int ch = static_cast<int>(i - row * c);
+        const long long row = i / dcs;
+        const int ch = static_cast<int>(i - row * dcs);
+        if (ch >= c) { dc[i] = from_f32<T>(0.f); continue; }
         const float s = msum[(mg == 1 ? 0 : (ch / cog)) * count + row];
-        const float g = to_f32(dy[i]);
+        const float g = to_f32(dy[row * dys + ch]);
         float d, gb;
-        if (no_guard) { d = g / s; gb = g; }
+        if (no_guard) { d = g / s; gb = (d - d) + g; }      // reference: g/s - g/s + g  (NaN where s == 0, like autograd there)
         else { const bool hole = (s == 0.f); d = hole ? 0.f : g / s; gb = hole ? 0.f : g; }
         dc[i] = from_f32<T>(d);
         if (dbias) atomicAdd(&s_db[ch], gb);
@@ -334,18 +335,9 @@ __global__ void mask_to_dense_kernel(const uint8_t *__restrict__ plane, int n, i
 }
 
 template <typename T>
-__global__ void weight_prepare_kernel(const float *__restrict__ wm, int cout, int taps, int cig, T *__restrict__ w_krsc, T *__restrict__ w_crsk) {
-    const long long total = static_cast<long long>(cout) * taps * cig;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float v = wm[i];
-        if (w_krsc) w_krsc[i] = from_f32<T>(v);
-        if (w_crsk) {
-            const int ci = static_cast<int>(i % cig);
-            const long long t = i / cig;
-            const int tap = static_cast<int>(t % taps), co = static_cast<int>(t / taps);
-            w_crsk[(static_cast<long long>(ci) * taps + tap) * cout + co] = from_f32<T>(v);
-        }
-    }
+__global__ void weight_cast_kernel(const float *__restrict__ src, long long n, T *__restrict__ dst) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = from_f32<T>(src[i]);
 }
 
 template <typename T>
@@ -472,15 +464,23 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply(
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, const float *msum, void *dc, float *dbias, pcb_stream_t stream) {
-    PCB_CHECK(c && dy && msum && dc, "pcb_pconv_renorm_backward: bad arguments");
+extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, int dy_cstride, const float *msum, void *dc, int dc_cstride, float *dbias, pcb_stream_t stream) {
+    PCB_CHECK(c && dy && msum && dc && dy_cstride >= c->cout && dc_cstride >= c->cout, "pcb_pconv_renorm_backward: bad arguments");
     const long long count = static_cast<long long>(c->n) * c->ho * c->wo;
     const int mg = (c->groups > 1 && !c->same_holes) ? c->groups : 1;
     if (dbias) PCB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, ST));
-    const int grid = ew_grid(count * c->cout, EW_THREADS * 8);
+    const int grid = ew_grid(count * dc_cstride, EW_THREADS * 8);
     const size_t smem = sizeof(float) * c->cout;
-    if (c->dtype == PCB_BF16) renorm_bwd_kernel<bf16><<<grid, EW_THREADS, smem, ST>>>(static_cast<const bf16 *>(dy), msum, count, c->cout, mg, c->no_guard, static_cast<bf16 *>(dc), dbias);
-    else renorm_bwd_kernel<float><<<grid, EW_THREADS, smem, ST>>>(static_cast<const float *>(dy), msum, count, c->cout, mg, c->no_guard, static_cast<float *>(dc), dbias);
+    if (c->dtype == PCB_BF16) renorm_bwd_kernel<bf16><<<grid, EW_THREADS, smem, ST>>>(static_cast<const bf16 *>(dy), dy_cstride, msum, count, c->cout, mg, c->no_guard, static_cast<bf16 *>(dc), dc_cstride, dbias);
+    else renorm_bwd_kernel<float><<<grid, EW_THREADS, smem, ST>>>(static_cast<const float *>(dy), dy_cstride, msum, count, c->cout, mg, c->no_guard, static_cast<float *>(dc), dc_cstride, dbias);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+int pcb_cast_weights(const float *src, void *dst, long long n, int dtype, cudaStream_t st) {
+    const int grid = ew_grid(n, EW_THREADS * 4);
+    if (dtype == PCB_BF16) weight_cast_kernel<bf16><<<grid, EW_THREADS, 0, st>>>(src, n, static_cast<bf16 *>(dst));
+    else weight_cast_kernel<float><<<grid, EW_THREADS, 0, st>>>(src, n, static_cast<float *>(dst));
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -565,17 +565,6 @@ extern "C" __attribute__((visibility("default"))) int pcb_mask_plane_to_dense(co
     PCB_CHECK(plane && dst_nchw && c0 >= 0 && c0 + c <= ctot, "pcb_mask_plane_to_dense: bad arguments");
     const long long total = static_cast<long long>(n) * c * h * w;
     mask_to_dense_kernel<<<ew_grid(total, EW_THREADS * 4), EW_THREADS, 0, ST>>>(plane, n, h, w, up, dst_nchw, ctot, c0, c);
-    PCB_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" __attribute__((visibility("default"))) int pcb_weight_prepare(const float *w_master_krsc, int cout, int kh, int kw, int cig, int dtype, void *w_krsc, void *w_crsk,
-                                  pcb_stream_t stream) {
-    PCB_CHECK(w_master_krsc && (w_krsc || w_crsk), "pcb_weight_prepare: bad arguments");
-    const long long total = static_cast<long long>(cout) * kh * kw * cig;
-    const int grid = ew_grid(total, EW_THREADS * 4);
-    if (dtype == PCB_BF16) weight_prepare_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(w_master_krsc, cout, kh * kw, cig, static_cast<bf16 *>(w_krsc), static_cast<bf16 *>(w_crsk));
-    else weight_prepare_kernel<float><<<grid, EW_THREADS, 0, ST>>>(w_master_krsc, cout, kh * kw, cig, static_cast<float *>(w_krsc), static_cast<float *>(w_crsk));
     PCB_LAUNCH_CHECK();
     return 0;
 }

@@ -113,19 +113,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // internal cross-file entry points -------------------------------------------------------------
-int pcb_generic_forward(const pcb_conv *c, const void *w, const float *bias, void *y, float *msum, uint8_t *newmask,
-                        cudaStream_t st);
-int pcb_generic_dgrad(const pcb_conv *c, const void *dc, const void *w_krsc, void *dx, cudaStream_t st);
-int pcb_generic_wgrad(const pcb_conv *c, const void *dc, float *dw, cudaStream_t st);
-bool pcb_tc_forward_eligible(const pcb_conv *c);
-bool pcb_tc_dgrad_eligible(const pcb_conv *c);
-bool pcb_tc_wgrad_eligible(const pcb_conv *c);
-size_t pcb_tc_forward_workspace(const pcb_conv *c);
-int pcb_tc_forward_ws(const pcb_conv *c, const void *w, const float *bias, void *y, const float *msum, uint32_t *tapmask,
+int pcb_generic_forward(const pcb_conv *c, const void *w, const float *bias, void *y, int y_cstride, const float *msum, cudaStream_t st);
+int pcb_generic_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_krsc, void *const *dx, const int *dx_cstride,
                       cudaStream_t st);
-int pcb_tc_read_abort_flag(int *value);
+int pcb_generic_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, cudaStream_t st);
 // mask box sums (all paths): msum fp32 [mg][n,ho,wo] (0 at holes), newmask u8 [mg][n,ho,wo]
 int pcb_mask_sums(const pcb_conv *c, float *msum, uint8_t *newmask, cudaStream_t st);
-int pcb_tc_dgrad(const pcb_conv *c, const void *dc, const void *wt, void *dx, cudaStream_t st);
-size_t pcb_tc_wgrad_workspace(const pcb_conv *c);
-int pcb_tc_wgrad(const pcb_conv *c, const void *dc, float *dw, void *workspace, cudaStream_t st);
+bool pcb_tc_eligible(const pcb_conv *c);
+bool pcb_tc_dgrad_supported(const pcb_conv *c);
+size_t pcb_tc_workspace(const pcb_conv *c);
+void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems);
+int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, cudaStream_t st);
+int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
+                      uint64_t *tapmask, cudaStream_t st);
+int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
+                 cudaStream_t st);
+int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, cudaStream_t st);
+int pcb_tc_read_abort_flag(int *value);

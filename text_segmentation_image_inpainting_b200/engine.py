@@ -72,8 +72,14 @@ class TrainStep:
     # -- one eager step ----------------------------------------------------------------------------
     def _prepare(self, x: torch.Tensor, mask: torch.Tensor):
         """reference-style inputs (fp32 NCHW image, fp32/uint8 {0,1} NCHW mask) -> (x*mask in compute dtype NHWC, HoleMask)"""
-        xin = (x * mask.to(x.dtype)).to(self.dtype).contiguous(memory_format=CL)       # Dataloader.py:131
-        return xin, HoleMask.from_dense(mask)
+        n, c, h, w = x.shape
+        # the 3-channel image travels as an 8-channel-padded NHWC buffer: 16-byte pixels feed the row-packed
+        # tensor-core stem and the tail's second gather source directly
+        buf = torch.zeros((n, (c + 7) // 8 * 8, h, w), dtype=self.dtype, device=x.device, memory_format=CL)
+        xin = buf[:, :c]
+        xin.copy_(x * mask.to(x.dtype))                                                # Dataloader.py:131
+        # masks of the reference's data path are one plane repeated over RGB (Dataloader.py:128-129)
+        return xin, HoleMask.from_dense(mask, channel_uniform=True)
 
     def _allreduce(self):
         if self.world == 1:

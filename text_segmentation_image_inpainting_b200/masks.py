@@ -15,7 +15,7 @@ unchanged) whose storage is a list of parts ``(uint8 plane [N, H>>up, W>>up], ch
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -46,17 +46,30 @@ class HoleMask(torch.Tensor):
 
     # ------------------------------------------------------------------ constructors
     @staticmethod
-    def from_dense(mask: torch.Tensor) -> "HoleMask":
-        """dense fp32/any [N,C,H,W] {0,1} mask -> one uint8 plane per channel (C <= 8 without a sync;
-        for wider masks the channels are verified identical -- one device sync -- and collapsed)."""
+    def from_dense(mask: torch.Tensor, channel_uniform: Optional[bool] = None) -> "HoleMask":
+        """dense fp32/any [N,C,H,W] {0,1} mask -> uint8 planes.
+
+        channel_uniform=True : trust the caller that all channels are equal (the reference's data path repeats one
+                               plane over RGB, Dataloader.py:128-129) -> a single plane, no check, no sync;
+        channel_uniform=None : check on the device (one sync; skipped while a CUDA graph is being captured) and
+                               collapse to one plane when possible, else one plane per channel (C <= 8);
+        channel_uniform=False: one plane per channel, no check."""
         if isinstance(mask, HoleMask):
             return mask
         if not mask.is_cuda:
             raise _lib.PcbError("HoleMask.from_dense: the CUDA path needs CUDA tensors (no CPU fallback)")
         n, c, h, w = mask.shape
         m = mask.detach().to(torch.float32).contiguous()
+        if channel_uniform:
+            m = m[:, :1].contiguous()
+            plane = torch.empty((1, n, h, w), dtype=torch.uint8, device=mask.device)
+            _lib.check(_lib.load().pcb_mask_planes_from_dense(m.data_ptr(), n, 1, h, w, plane.data_ptr(), _stream()))
+            return HoleMask([(plane[0], c, 0)], n, h, w)
         planes = torch.empty((c, n, h, w), dtype=torch.uint8, device=mask.device)
         _lib.check(_lib.load().pcb_mask_planes_from_dense(m.data_ptr(), n, c, h, w, planes.data_ptr(), _stream()))
+        if channel_uniform is None and 1 < c <= _lib.MAX_PARTS and not torch.cuda.is_current_stream_capturing():
+            if bool((planes == planes[:1]).all()):              # one sync, eager mode only
+                return HoleMask([(planes[0], c, 0)], n, h, w)
         if c > _lib.MAX_PARTS:
             if not bool((planes == planes[:1]).all()):          # device sync; only for wide user-supplied masks
                 raise NotImplementedError("dense masks with more than 8 channels must be channel-uniform")

@@ -3,9 +3,9 @@
 :110-191, ImageFillOriginV2 :219-290) with identical module tree -> identical state_dict keys, so reference
 checkpoints load.  (ImageFillOriginV3 is excluded: it raises a shape error in the reference itself)
 
-Differences in *how* it runs: skip concatenation + nearest upsampling of the features is one fused kernel
-(``ops.concat_features``), masks are never materialised (``HoleMask``), and every layer is one launch of
-libpconv_b200's implicit-GEMM kernel.
+Differences in *how* it runs: skip concatenation + nearest upsampling is never materialised (``ops.LazyCat``
+for the features, ``HoleMask`` for the masks: the consumer's gather does the index math), and every layer is
+one launch of libpconv_b200's implicit-GEMM kernel.
 """
 import torch
 from torch import nn
@@ -25,7 +25,7 @@ class _PartialUNet(BaseModule):
 
     def forward(self, args):
         x, mask = args                                  # mask: 1 = ground truth, 0 = hole
-        x = ops.as_feature(x)
+        x = ops.as_feature_padded(x)
         mask = as_hole_mask(mask)
         skips = [(x, mask)]
         for layer in self.encoder:
@@ -35,8 +35,9 @@ class _PartialUNet(BaseModule):
         x, mask = self._bottleneck(x, mask)
         for layer in self.decoder:
             sx, sm = skips.pop()
-            # nearest x2 of (x, mask) + channel concat with the skip: one pass for the features, none for the masks
-            xh = ops.concat_features([x, sx], ups=(1, 0))
+            # nearest x2 of (x, mask) + channel concat with the skip: never materialised -- the next partial
+            # convolution gathers straight from both sources (features) / both planes (masks)
+            xh = ops.LazyCat([x, sx], ups=(1, 0))
             mh = torch.cat([mask.upsampled(), sm], dim=1)
             x, mask = layer((xh, mh))
         return x

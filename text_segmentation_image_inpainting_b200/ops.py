@@ -58,46 +58,114 @@ def act_code(act) -> Tuple[int, float]:
 # ------------------------------------------------------------------------------------------------
 # partial convolution
 # ------------------------------------------------------------------------------------------------
-class ConvGeom:
-    """Plain description of one partial-convolution call (everything but the pointers)."""
+def nhwc_layout(x: torch.Tensor):
+    """(channel stride) of a logical-NCHW tensor whose memory is NHWC with an optionally PADDED pixel stride
+    (e.g. ``buf8[:, :3]`` of a channels_last [N,8,H,W] buffer), or None if it is not such a layout."""
+    n, c, h, w = x.shape
+    if x.is_contiguous(memory_format=CL):
+        return c
+    sn, sc, sh, sw = x.stride()
+    cs = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
+    if sc != 1 and c > 1:
+        return None
+    if cs < c or (w > 1 and sw != cs) or (h > 1 and sh != w * cs) or (n > 1 and sn != h * w * cs):
+        return None
+    return cs
 
-    def __init__(self, x_shape, cout, k, stride, padding, dilation, groups, same_holes, no_guard, dtype_code,
-                 mask_parts: Sequence[Tuple[torch.Tensor, int, int]], plain=False):
-        n, cin, h, w = x_shape
+
+def as_feature_padded(x: torch.Tensor) -> torch.Tensor:
+    """Like as_feature but keeps channel-padded NHWC views as they are."""
+    if not x.is_cuda:
+        raise _lib.PcbError("text_segmentation_image_inpainting_b200 ops need CUDA tensors: there is no CPU fallback")
+    if x.dim() != 4:
+        raise _lib.PcbError(f"expected a 4-D NCHW activation, got shape {tuple(x.shape)}")
+    _dtype_code(x)
+    return x if nhwc_layout(x) is not None else x.contiguous(memory_format=CL)
+
+
+def padded_empty(n, c, h, w, dtype, device):
+    """NHWC buffer whose channel stride is rounded up to 8 (zero-filled padding); returns the logical view."""
+    c8 = (c + 7) // 8 * 8
+    if c8 == c:
+        return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=CL)
+    return torch.zeros((n, c8, h, w), dtype=dtype, device=device, memory_format=CL)[:, :c]
+
+
+class LazyCat:
+    """cat([up2x?(x_i)], dim=1) that is never materialised: a partial convolution consumes the parts directly
+    (image_inpainting.py:183-185 folded into the gather of the next layer)."""
+
+    def __init__(self, xs: Sequence[torch.Tensor], ups: Sequence[int]):
+        self.xs = [as_feature_padded(x) for x in xs]
+        self.ups = [int(u) for u in ups]
+        n = self.xs[0].shape[0]
+        h, w = self.xs[0].shape[2] << self.ups[0], self.xs[0].shape[3] << self.ups[0]
+        for x, u in zip(self.xs, self.ups):
+            if (x.shape[0], x.shape[2] << u, x.shape[3] << u) != (n, h, w) or x.dtype != self.xs[0].dtype:
+                raise _lib.PcbError("LazyCat: mismatched batch / spatial size / dtype")
+        self.shape = torch.Size((n, sum(x.shape[1] for x in self.xs), h, w))
+        self.dtype, self.device = self.xs[0].dtype, self.xs[0].device
+
+    def materialize(self) -> torch.Tensor:
+        return concat_features([x if nhwc_layout(x) == x.shape[1] else x.contiguous(memory_format=CL) for x in self.xs], self.ups)
+
+
+class ConvGeom:
+    """One partial-convolution problem: geometry + the channel partition (x source, mask plane) per part."""
+
+    def __init__(self, xs: Sequence[torch.Tensor], ups: Sequence[int], cout, k, stride, padding, dilation, groups, same_holes,
+                 no_guard, mask_parts: Sequence[Tuple[Optional[torch.Tensor], int, int]], plain=False):
+        n = xs[0].shape[0]
+        h, w = xs[0].shape[2] << ups[0], xs[0].shape[3] << ups[0]
+        cin = sum(x.shape[1] for x in xs)
         kh, kw = (k, k) if isinstance(k, int) else k
         ph, pw = (padding, padding) if isinstance(padding, int) else padding
         s = stride if isinstance(stride, int) else stride[0]
         d = dilation if isinstance(dilation, int) else dilation[0]
-        if not isinstance(stride, int) and stride[0] != stride[1] or not isinstance(dilation, int) and dilation[0] != dilation[1]:
+        if (not isinstance(stride, int) and stride[0] != stride[1]) or (not isinstance(dilation, int) and dilation[0] != dilation[1]):
             raise NotImplementedError("anisotropic stride / dilation")
         self.n, self.cin, self.h, self.w = n, cin, h, w
         self.cout, self.kh, self.kw, self.stride, self.ph, self.pw, self.dil, self.groups = cout, kh, kw, s, ph, pw, d, groups
         self.ho = (h + 2 * ph - d * (kh - 1) - 1) // s + 1
         self.wo = (w + 2 * pw - d * (kw - 1) - 1) // s + 1
-        self.same_holes, self.no_guard, self.dtype, self.plain = int(same_holes), int(no_guard), dtype_code, int(plain)
-        self.mask_parts = list(mask_parts)
+        self.same_holes, self.no_guard, self.plain = int(same_holes), int(no_guard), int(plain)
+        self.dtype = _dtype_code(xs[0])
+        self.esz = 2 if self.dtype == PCB_BF16 else 4
         self.mg = groups if (groups > 1 and not same_holes) else 1
         if self.ho <= 0 or self.wo <= 0:
             raise _lib.PcbError(f"convolution output would be empty ({self.ho}x{self.wo})")
+        self.x_channels = [x.shape[1] for x in xs]
+        self.x_cstrides = [nhwc_layout(x) for x in xs]
+        self.x_ups = list(ups)
+        # common refinement of the x partition and the mask partition
+        xb, off = [], 0
+        for i, c in enumerate(self.x_channels):
+            xb.append((off, off + c, i)); off += c
+        mb, off = [], 0
+        for plane, c, up in mask_parts:
+            mb.append((off, off + c, plane, up)); off += c
+        if off != cin:
+            raise _lib.PcbError(f"mask covers {off} channels but the input has {cin}")
+        self.parts = []            # (x index, channel offset inside that x, channels, plane, mask_up)
+        for lo, hi, xi in xb:
+            for mlo, mhi, plane, mup in mb:
+                a, b_ = max(lo, mlo), min(hi, mhi)
+                if a < b_:
+                    self.parts.append((xi, a - lo, b_ - a, plane, mup))
+        if len(self.parts) > _lib.MAX_PARTS:
+            raise NotImplementedError(f"more than {_lib.MAX_PARTS} (source, mask-plane) parts in one convolution")
+        self.signature = (self.dtype, cin, cout, kh, kw, groups, tuple(p[2] for p in self.parts), tuple(self.x_cstrides))
 
-    def struct(self, x: Optional[torch.Tensor]) -> Conv:
+    def struct(self, xs: Optional[Sequence[torch.Tensor]], force_generic=False) -> Conv:
         c = Conv()
         c.n, c.h, c.w, c.cin, c.cout, c.kh, c.kw = self.n, self.h, self.w, self.cin, self.cout, self.kh, self.kw
         c.stride, c.pad_h, c.pad_w, c.dil, c.groups, c.ho, c.wo = self.stride, self.ph, self.pw, self.dil, self.groups, self.ho, self.wo
-        c.dtype, c.same_holes, c.no_guard, c.plain = self.dtype, self.same_holes, self.no_guard, self.plain
-        esz = 2 if self.dtype == PCB_BF16 else 4
-        parts = self.mask_parts
-        if len(parts) > _lib.MAX_PARTS:
-            raise NotImplementedError(f"more than {_lib.MAX_PARTS} mask parts")
-        c.nparts = len(parts)
-        off = 0
-        for i, (plane, ch, up) in enumerate(parts):
-            c.parts[i].x = (x.data_ptr() + off * esz) if x is not None else None
+        c.dtype, c.same_holes, c.no_guard, c.plain, c.force_generic = self.dtype, self.same_holes, self.no_guard, self.plain, int(force_generic)
+        c.nparts = len(self.parts)
+        for i, (xi, choff, ch, plane, mup) in enumerate(self.parts):
+            c.parts[i].x = (xs[xi].data_ptr() + choff * self.esz) if xs is not None else None
             c.parts[i].mask = plane.data_ptr() if plane is not None else None
-            c.parts[i].c, c.parts[i].x_cstride, c.parts[i].x_up, c.parts[i].mask_up = ch, self.cin, 0, up
-            off += ch
-        if off != self.cin:
-            raise _lib.PcbError(f"mask covers {off} channels but the input has {self.cin}")
+            c.parts[i].c, c.parts[i].x_cstride, c.parts[i].x_up, c.parts[i].mask_up = ch, self.x_cstrides[xi], self.x_ups[xi], mup
         return c
 
 
@@ -128,54 +196,94 @@ class _Timed:
         return False
 
 
+def _workspace(lib, c, device):
+    nbytes = lib.pcb_pconv_workspace(ctypes.byref(c))
+    return torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=device)
+
+
 class PartialConvFn(torch.autograd.Function):
-    """y, msum, newmask = pconv(x, W, b | mask)   (models/partial_convolution.py:49-80 / :121-137)."""
+    """y, msum, newmask = pconv(cat(up?(x_i)), W, b | mask)   (models/partial_convolution.py:49-80 / :121-137)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, geom: ConvGeom, wprep):
+    def forward(ctx, geom: ConvGeom, wprep, weight, bias, *xs):
         lib = _lib.load()
-        w_krsc, w_crsk = wprep
-        c = geom.struct(x)
-        y = torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=x.dtype, device=x.device, memory_format=CL)
-        msum = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.float32, device=x.device)
-        newmask = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.uint8, device=x.device)
-        ws_bytes = lib.pcb_pconv_workspace(ctypes.byref(c))
-        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=x.device)
+        w_fwd, w_dg = wprep
+        c = geom.struct(xs)
+        dev = xs[0].device
+        if geom.dtype == PCB_BF16:
+            y = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, xs[0].dtype, dev)
+        else:
+            y = torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=xs[0].dtype, device=dev, memory_format=CL)
+        msum = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.float32, device=dev)
+        newmask = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.uint8, device=dev)
+        ws = _workspace(lib, c, dev)
         b32 = bias.detach().float().contiguous() if bias is not None else None
         with _Timed("fwd", geom):
-            _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_krsc.data_ptr(), _ptr(b32), y.data_ptr(), msum.data_ptr(),
+            _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
                                              newmask.data_ptr(), ws.data_ptr(), _stream()))
-        ctx.geom, ctx.wprep, ctx.has_bias = geom, wprep, bias is not None
-        ctx.save_for_backward(x, msum)
+        ctx.geom, ctx.wprep, ctx.has_bias, ctx.weight_ref = geom, wprep, bias is not None, weight
+        ctx.save_for_backward(msum, *xs)
         ctx.mark_non_differentiable(msum, newmask)
         return y, msum, newmask
 
     @staticmethod
     def backward(ctx, gy, _gmsum, _gnewmask):
         lib = _lib.load()
-        x, msum = ctx.saved_tensors
+        msum, *xs = ctx.saved_tensors
         geom: ConvGeom = ctx.geom
-        w_krsc, w_crsk = ctx.wprep
-        gy = gy.contiguous(memory_format=CL)
-        if gy.dtype != x.dtype:
-            gy = gy.to(x.dtype)
-        c = geom.struct(x)
-        dc = torch.empty_like(gy, memory_format=CL)
-        dbias = torch.empty((geom.cout,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
-        _lib.check(lib.pcb_pconv_renorm_backward(ctypes.byref(c), gy.data_ptr(), msum.data_ptr(), dc.data_ptr(), _ptr(dbias), _stream()))
-        dx = dw = None
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty((geom.cout, geom.cin // geom.groups, geom.kh, geom.kw), dtype=torch.float32, device=x.device,
-                             memory_format=CL)
-            ws_bytes = lib.pcb_pconv_workspace(ctypes.byref(c))
-            ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=x.device)
+        w_fwd, w_dg = ctx.wprep
+        dev, tdtype = xs[0].device, xs[0].dtype
+        gy = as_feature_padded(gy if gy.dtype == tdtype else gy.to(tdtype))
+        c = geom.struct(xs)
+        dc = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, tdtype, dev) if geom.dtype == PCB_BF16 else \
+            torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=tdtype, device=dev, memory_format=CL)
+        dcs = nhwc_layout(dc)
+        dbias = torch.empty((geom.cout,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+        _lib.check(lib.pcb_pconv_renorm_backward(ctypes.byref(c), gy.data_ptr(), nhwc_layout(gy), msum.data_ptr(), dc.data_ptr(), dcs,
+                                                 _ptr(dbias), _stream()))
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty((geom.cout, geom.cin // geom.groups, geom.kh, geom.kw), dtype=torch.float32, device=dev, memory_format=CL)
+            ws = _workspace(lib, c, dev)
             with _Timed("wgrad", geom):
-                _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dw.data_ptr(), ws.data_ptr(), _stream()))
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x, memory_format=CL)
+                _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
+        need = [ctx.needs_input_grad[4 + i] for i in range(len(xs))]
+        gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
+        if any(need):
+            # full-resolution gradient buffer per source tensor; parts write their channel slices
+            full = [padded_empty(geom.n, geom.x_channels[i], geom.h, geom.w, tdtype, dev) if need[i] else None for i in range(len(xs))]
+            nparts = len(geom.parts)
+            ptrs = (ctypes.c_void_p * nparts)()
+            strides = (ctypes.c_int32 * nparts)()
+            for pi, (xi, choff, ch, plane, mup) in enumerate(geom.parts):
+                if full[xi] is not None:
+                    ptrs[pi] = full[xi].data_ptr() + choff * geom.esz
+                    strides[pi] = nhwc_layout(full[xi])
+                else:
+                    ptrs[pi], strides[pi] = None, 0
+            cc, wf, wd = c, w_fwd, w_dg
+            if lib.pcb_conv_uses_tensor_cores(ctypes.byref(c)) and w_dg is None:
+                # row-packed (cin <= 8) tensor-core layer whose input wants a gradient: generic data-gradient kernel
+                cc = geom.struct(xs, force_generic=True)
+                wf = ctx.weight_ref.detach().float().contiguous(memory_format=CL).to(tdtype)
+                wd = None
             with _Timed("dgrad", geom):
-                _lib.check(lib.pcb_pconv_backward_data(ctypes.byref(c), dc.data_ptr(), w_krsc.data_ptr(), _ptr(w_crsk), dx.data_ptr(), _stream()))
-        return dx, dw, dbias, None, None
+                _lib.check(lib.pcb_pconv_backward_data(ctypes.byref(cc), dc.data_ptr(), dcs, wf.data_ptr(), _ptr(wd), ptrs, strides, _stream()))
+            for i in range(len(xs)):
+                if full[i] is None:
+                    continue
+                if geom.x_ups[i]:
+                    g = padded_empty(geom.n, geom.x_channels[i], geom.h >> 1, geom.w >> 1, tdtype, dev)
+                    src = full[i]
+                    cs_src, cs_dst = nhwc_layout(src), nhwc_layout(g)
+                    if cs_src != cs_dst or cs_src != geom.x_channels[i]:
+                        raise NotImplementedError("upsampled conv source with padded channels")
+                    _lib.check(lib.pcb_upsample2x_backward(src.data_ptr(), geom.dtype, geom.n, geom.h >> 1, geom.w >> 1, geom.x_channels[i],
+                                                           g.data_ptr(), _stream()))
+                    gxs[i] = g
+                else:
+                    gxs[i] = full[i]
+        return (None, None, dw, dbias, *gxs)
 
 
 _WEIGHT_EPOCH = 0
@@ -188,42 +296,44 @@ def bump_weight_epoch():
     _WEIGHT_EPOCH += 1
 
 
-def prepare_weight(weight: torch.Tensor, dtype: torch.dtype, groups: int, cache: dict):
-    """fp32 master weight (OIHW logical) -> (KRSC, CRSK) copies in the compute dtype, cached per parameter version."""
-    key = (weight.data_ptr(), weight._version, dtype, str(weight.device), _WEIGHT_EPOCH)
-    hit = cache.get("key")
-    if hit == key:
+def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
+    """fp32 master weight (OIHW logical, KRSC physical) -> the operand buffers the kernels want
+    (pcb_conv_weight_layout / pcb_conv_weight_prepare), cached per parameter version and problem signature."""
+    key = (weight.data_ptr(), weight._version, str(weight.device), _WEIGHT_EPOCH, geom.signature)
+    if cache.get("key") == key:
         return cache["val"]
     lib = _lib.load()
     wm = weight.detach()
     if wm.dtype != torch.float32:
         wm = wm.float()
     wm = wm.contiguous(memory_format=CL)          # physical [cout][kh][kw][cig]
-    cout, cig, kh, kw = wm.shape
-    code = PCB_BF16 if dtype == torch.bfloat16 else PCB_F32
-    if code == PCB_F32:
-        w_krsc = wm
-        w_crsk = None
-    else:
-        w_krsc = torch.empty((cout, kh, kw, cig), dtype=dtype, device=wm.device)
-        w_crsk = torch.empty((cig, kh, kw, cout), dtype=dtype, device=wm.device) if groups == 1 else None
-        _lib.check(lib.pcb_weight_prepare(wm.data_ptr(), cout, kh, kw, cig, code, w_krsc.data_ptr(), _ptr(w_crsk), _stream()))
-    cache["key"], cache["val"] = key, (w_krsc, w_crsk)
+    c = geom.struct(None)
+    fe, de = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    lib.pcb_conv_weight_layout(ctypes.byref(c), ctypes.byref(fe), ctypes.byref(de))
+    tdt = torch.bfloat16 if geom.dtype == PCB_BF16 else torch.float32
+    w_fwd = torch.empty((fe.value,), dtype=tdt, device=wm.device)
+    w_dg = torch.empty((de.value,), dtype=tdt, device=wm.device) if de.value else None
+    _lib.check(lib.pcb_conv_weight_prepare(ctypes.byref(c), wm.data_ptr(), w_fwd.data_ptr(), _ptr(w_dg), _stream()))
+    cache["key"], cache["val"] = key, (w_fwd, w_dg)
     return cache["val"]
 
 
 def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_holes=False, no_guard=False, cache=None,
                  plain=False):
-    """Returns (y, new_mask: HoleMask).  `mask` may be a HoleMask or a dense tensor; with ``plain=True`` the
-    mask is ignored and an ordinary convolution is computed (same kernels, renormaliser 1)."""
-    x = as_feature(x)
-    n, cin, h, w = x.shape
+    """Returns (y, new_mask: HoleMask).  `x` is a tensor or a LazyCat; `mask` a HoleMask or a dense tensor; with
+    ``plain=True`` the mask is ignored and an ordinary convolution is computed (same kernels, renormaliser 1)."""
+    if isinstance(x, LazyCat):
+        xs, ups = x.xs, x.ups
+    else:
+        xs, ups = [as_feature_padded(x)], [0]
+    n, h, w = xs[0].shape[0], xs[0].shape[2] << ups[0], xs[0].shape[3] << ups[0]
+    cin = sum(t.shape[1] for t in xs)
     if plain:
         parts = [(None, cin, 0)]
     else:
         hm = as_hole_mask(mask)
         if tuple(hm.shape[2:]) != (h, w) or hm.shape[0] != n:
-            raise _lib.PcbError(f"mask shape {tuple(hm.shape)} does not match input {tuple(x.shape)}")
+            raise _lib.PcbError(f"mask shape {tuple(hm.shape)} does not match input {(n, cin, h, w)}")
         parts = hm.parts
         if hm.shape[1] != cin:
             if hm.shape[1] == 1:                       # broadcast of a 1-channel mask over x (x * mask, :51)
@@ -231,10 +341,11 @@ def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_
             else:
                 raise _lib.PcbError(f"mask has {hm.shape[1]} channels, input has {cin}")
     cout = weight.shape[0]
-    geom = ConvGeom(x.shape, cout, tuple(weight.shape[2:]), stride, padding, dilation, groups, same_holes, no_guard,
-                    _dtype_code(x), parts, plain=plain)
-    wprep = prepare_weight(weight, x.dtype, groups, cache if cache is not None else {})
-    y, msum, newmask = PartialConvFn.apply(x, weight, bias, geom, wprep)
+    if weight.shape[1] * groups != cin:
+        raise _lib.PcbError(f"weight expects {weight.shape[1] * groups} input channels, got {cin}")
+    geom = ConvGeom(xs, ups, cout, tuple(weight.shape[2:]), stride, padding, dilation, groups, same_holes, no_guard, parts, plain=plain)
+    wprep = prepare_weight(weight, geom, cache if cache is not None else {})
+    y, msum, newmask = PartialConvFn.apply(geom, wprep, weight, bias, *xs)
     if geom.mg == 1:
         new = HoleMask.from_plane(newmask[0], cout, 0)
     else:
