@@ -75,7 +75,7 @@ class TrainStep:
         n, c, h, w = x.shape
         # the 3-channel image travels as an 8-channel-padded NHWC buffer: 16-byte pixels feed the row-packed
         # tensor-core stem and the tail's second gather source directly
-        buf = torch.zeros((n, (c + 7) // 8 * 8, h, w), dtype=self.dtype, device=x.device, memory_format=CL)
+        buf = torch.empty((n, (c + 7) // 8 * 8, h, w), dtype=self.dtype, device=x.device, memory_format=CL).zero_()
         xin = buf[:, :c]
         xin.copy_(x * mask.to(x.dtype))                                                # Dataloader.py:131
         # masks of the reference's data path are one plane repeated over RGB (Dataloader.py:128-129)

@@ -88,7 +88,7 @@ def padded_empty(n, c, h, w, dtype, device):
     c8 = (c + 7) // 8 * 8
     if c8 == c:
         return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=CL)
-    return torch.zeros((n, c8, h, w), dtype=dtype, device=device, memory_format=CL)[:, :c]
+    return torch.empty((n, c8, h, w), dtype=dtype, device=device, memory_format=CL).zero_()[:, :c]
 
 
 class LazyCat:
