@@ -131,13 +131,13 @@ def test_full_size_properties_cfg1_and_hole_semantics(dev):
     nmd = nm.dense().cpu()
     assert torch.equal(nmd, mo) and int((nmd[0, 0] == 0).sum()) == 30 * 30
     assert bool((y.cpu()[nmd == 0] == 0).all())
-    mod2 = PC.PartialConv(3, 64, 3, 1, 1, same_holes=True); mod2.load_state_dict(sd, strict=False); mod2 = mod2.to(dev)
+    mod2 = PC.PartialConv(3, 64, 3, 1, 1, same_holes=True).to(dev)
     with torch.no_grad():
         mod2.feature_conv.weight.copy_(sd["feature_conv.weight"]); mod2.feature_conv.bias.copy_(sd["feature_conv.bias"])
     y2, nm2 = mod2((x.to(dev).contiguous(memory_format=torch.channels_last), mask.to(dev)))
     assert relerr(y2, y) <= 1e-6 and torch.equal(nm2.dense(), nm.dense())
     # linearity of the masked convolution part: f(2x) - b == 2 (f(x) - b)
-    y3, _ = mod((2 * x.to(dev)).contiguous(memory_format=torch.channels_last), mask.to(dev))
+    y3, _ = mod(((2 * x.to(dev)).contiguous(memory_format=torch.channels_last), mask.to(dev)))
     b = sd["feature_conv.bias"].to(dev).view(1, -1, 1, 1) * nm.dense()
     assert relerr(y3 - b, 2 * (y - b)) <= 1e-5
 
