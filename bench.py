@@ -194,7 +194,7 @@ def layer_profile(ts, x, mask, peaks, verbose):
 
     rec = []
     ops.set_profile(rec)
-    ts._step(x, mask, False)
+    ts._fwd_bwd(x, mask)              # forward + backward only: no collective (rank 0 runs this alone)
     torch.cuda.synchronize()
     ops.set_profile(None)
     fam = {}
@@ -249,6 +249,10 @@ def run_b200(args):
         pg = dist.group.WORLD
     _lib.load()
 
+    def note(msg):
+        if world > 1 or os.environ.get("PCB_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     torch.manual_seed(0)                                        # identical initial weights on every rank
     net = ImageFillOrigin().to(dev)
     ts = TrainStep(net, compute_dtype=torch.bfloat16, process_group=pg, use_graph=not args.no_graph)
@@ -263,7 +267,9 @@ def run_b200(args):
     dev_m = [t.to(dev) for t in host_m]
     h2d_bytes = host_x[0].numel() * 4 + host_m[0].numel() * 4
 
+    note("inputs ready; eager warm-up + graph capture")
     ts.warmup_and_capture(dev_x[0], dev_m[0], eager_warmup=2)
+    note("captured; device-resident timing")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -300,6 +306,7 @@ def run_b200(args):
     ms_total = maxreduce(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
+    note(f"device-resident done: {ms_total / args.steps:.2f} ms/step; end-to-end timing")
 
     # ---------------- end to end: host (pinned) buffers -> H2D on a copy stream, double buffered against
     # compute -> step -> D2H of the loss, every step inside the timed region
@@ -340,6 +347,7 @@ def run_b200(args):
     barrier()
     e2e_ms = maxreduce(e0.elapsed_time(e1))
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    note("end-to-end done")
 
     # ---------------- per-kernel roofline (rank 0): eager instrumented step, events on the launching stream
     roof, fam = (None, {})

@@ -68,6 +68,7 @@ class TrainStep:
         self.first = True
         self.bucket_elems = bucket_mb * (1 << 20) // 4
         self.launches_per_step = 0
+        self.graph_update = None
 
     # -- one eager step ----------------------------------------------------------------------------
     def _prepare(self, x: torch.Tensor, mask: torch.Tensor):
@@ -89,17 +90,24 @@ class TrainStep:
         for s in range(0, g.numel(), self.bucket_elems):
             torch.distributed.all_reduce(g[s:s + self.bucket_elems], group=self.pg)
 
-    def _step(self, x, mask, first_step: bool):
+    def _fwd_bwd(self, x, mask):
         self.flat.flat_g.zero_()
         ops.bump_weight_epoch()
         xin, hm = self._prepare(x, mask)
         out = self.net((xin, hm))
         loss = ops.l1_mean(out)
         loss.backward()
-        self._allreduce()
+        return loss.detach()
+
+    def _update(self, first_step: bool):
         ops.sgd_step(self.flat.flat_p, self.flat.flat_g, self.flat.flat_m, self.lr, self.momentum, self.wd, self.nesterov,
                      first_step)
-        return loss.detach()
+
+    def _step(self, x, mask, first_step: bool):
+        loss = self._fwd_bwd(x, mask)
+        self._allreduce()
+        self._update(first_step)
+        return loss
 
     # -- public -------------------------------------------------------------------------------------
     def warmup_and_capture(self, x: torch.Tensor, mask: torch.Tensor, eager_warmup=2):
@@ -121,8 +129,17 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.static_loss = self._step(self.static_x, self.static_m, False)
+        if self.world == 1:
+            with torch.cuda.graph(graph):
+                self.static_loss = self._step(self.static_x, self.static_m, False)
+        else:
+            # data parallel: the NCCL all-reduce stays OUTSIDE the captured graphs (graph A = forward+backward,
+            # eager bucketed all-reduce of the gradient arena, graph B = fused SGD): no collective is ever captured
+            with torch.cuda.graph(graph):
+                self.static_loss = self._fwd_bwd(self.static_x, self.static_m)
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update):
+                self._update(False)
         self.graph = graph
         torch.cuda.synchronize()
 
@@ -134,6 +151,9 @@ class TrainStep:
             if mask.data_ptr() != self.static_m.data_ptr():
                 self.static_m.copy_(mask, non_blocking=True)
             self.graph.replay()
+            if self.world > 1:
+                self._allreduce()
+                self.graph_update.replay()
             return self.static_loss
         loss = self._step(x, mask, self.first)
         self.first = False
