@@ -158,6 +158,24 @@ int pcb_concat_forward(const pcb_part *parts, int nparts, int dtype, int n, int 
 int pcb_concat_backward(const void *gy, const int32_t *c, const int32_t *up, int nparts, int dtype, int n, int h,
                         int w, void *const *gx, pcb_stream_t stream);
 
+/* ---- segmentation-network glue (models/text_segmentation.py, models/common.py) ------------------- */
+/* nn.AvgPool2d(k, stride, pad) with count_include_pad=True on NHWC (text_segmentation.py:33,66-67; ASP, common.py:62-68). */
+int pcb_avgpool_forward(const void *x, void *y, int dtype, int n, int h, int w, int c, int k, int stride, int pad, pcb_stream_t stream);
+int pcb_avgpool_backward(const void *gy, void *gx, int dtype, int n, int h, int w, int c, int k, int stride, int pad, pcb_stream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=False, scale_factor=scale) on NHWC (text_segmentation.py:54,76,109,113);
+ * h, w are the INPUT (low-resolution) sizes. */
+int pcb_bilinear_forward(const void *x, void *y, int dtype, int n, int h, int w, int c, int scale, pcb_stream_t stream);
+int pcb_bilinear_backward(const void *gy, void *gx, int dtype, int n, int h, int w, int c, int scale, pcb_stream_t stream);
+/* nn.AdaptiveAvgPool2d(1) -> fp32 [n][c] (scSE squeeze, common.py:19,35) and its backward (broadcast of g/hw). */
+int pcb_gap_forward(const void *x, int dtype, int n, long long hw, int c, float *out, pcb_stream_t stream);
+int pcb_gap_backward(const float *g, void *dx, int dtype, int n, long long hw, int c, int accumulate, pcb_stream_t stream);
+/* scSE gate (common.py:37-43): sse = sigmoid(<x[p,:], ws>), y = x*cse[n,:] + x*sse; sse_out fp32 [n*hw] is saved for backward.
+ * backward: dx, dcse fp32 [n][c], dws fp32 [c] (both overwritten). */
+int pcb_scse_forward(const void *x, const float *cse, const float *ws, void *y, float *sse_out, int dtype, int n, long long hw, int c,
+                     pcb_stream_t stream);
+int pcb_scse_backward(const void *gy, const void *x, const float *cse, const float *ws, const float *sse, void *dx, float *dcse,
+                      float *dws, int dtype, int n, long long hw, int c, pcb_stream_t stream);
+
 /* ---- loss / optimiser used by the benchmark step (loss = out.abs().mean()) ------ */
 int pcb_l1_mean_forward(const void *x, int dtype, long long numel, float *loss /* device scalar, overwritten */,
                         double *scratch /* device, 1 double */, pcb_stream_t stream);

@@ -267,3 +267,83 @@ def run_net(cls_name, dev, dtype):
         if k.startswith("bn.") and (dtype == F32 or ".encoder.1." in k or ".encoder.0." in k):
             errs[k] = relerr(sdn[k[3:]], torch.from_numpy(g[k]))
     return errs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense segmentation path: modules of the product package on the GPU vs goldens produced by the reference itself
+# ---------------------------------------------------------------------------------------------------------------
+def seg_block_builders():
+    from torch import nn
+    from text_segmentation_image_inpainting_b200.models import BaseModels as MB, MobileNetV2 as MM, common as MC
+    act = lambda: nn.LeakyReLU(0.3)  # noqa: E731
+    return {
+        "dsconv_s2": lambda: MB.DSConvBlock(16, 24, 3, 2, 1, 1, False, True, act(), act()),
+        "dsconv_d4": lambda: MB.DSConvBlock(16, 16, 3, 1, 4, 4, False, True, act(), None),
+        "invres_scse": lambda: MM.InvertedResidual(16, 16, 1, 6, 2, activation=act(), bias=False, add_sece=True),
+        "invres_s2": lambda: MM.InvertedResidual(16, 24, 2, 6, 1, activation=act(), bias=False, add_sece=False),
+        "scse": lambda: MC.SpatialChannelSqueezeExcitation(32, reduction=16, activation=act()),
+        "rfb": lambda: MC.RFB(40, 16, activation=act(), add_sece=True),
+        "asp": lambda: MC.ASP(24, 16, act(), asp_rate=(3, 5, 9)),
+    }
+
+
+def seg_block_case(name, dev, dtype):
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"seg_{name}.npz"))
+    mod = seg_block_builders()[name]()
+    mod.load_state_dict(det_fill_state_dict(mod.state_dict()))
+    mod = mod.to(dev).train()
+    x = torch.from_numpy(g["x"]).to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = mod(x)
+    y.backward(torch.from_numpy(g["gy"]).to(dev).to(dtype))
+    torch.cuda.synchronize()
+    errs = {"y": relerr(y, torch.from_numpy(g["y"])), "gx": relerr(x.grad, torch.from_numpy(g["gx"]))}
+    params = dict(mod.named_parameters())
+    sdn = mod.state_dict()
+    for k in g.files:
+        if k.startswith("g."):
+            errs[k] = relerr(params[k[2:]].grad, torch.from_numpy(g[k]))
+        if k.startswith("bn."):
+            errs[k] = relerr(sdn[k[3:]], torch.from_numpy(g[k]))
+    return errs
+
+
+def pool_bilinear_case(dev, dtype):
+    from text_segmentation_image_inpainting_b200 import ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "seg_pool_bilinear.npz"))
+    errs = {}
+    xp = torch.from_numpy(g["xp"]).to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yp = ops.avg_pool2d(xp, 3, 2, 1)
+    yp.backward(torch.from_numpy(g["gyp"]).to(dev).to(dtype))
+    errs["pool_y"], errs["pool_gx"] = relerr(yp, torch.from_numpy(g["yp"])), relerr(xp.grad, torch.from_numpy(g["gxp"]))
+    for s in (2, 4):
+        xb = torch.from_numpy(g["xb"]).to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        yb = ops.bilinear_upsample(xb, s)
+        yb.backward(torch.from_numpy(g[f"gy{s}"]).to(dev).to(dtype))
+        errs[f"bil{s}_y"], errs[f"bil{s}_gx"] = relerr(yb, torch.from_numpy(g[f"y{s}"])), relerr(xb.grad, torch.from_numpy(g[f"gx{s}"]))
+    return errs
+
+
+def run_segnet(cls_name, dev, dtype):
+    from text_segmentation_image_inpainting_b200 import ops
+    from text_segmentation_image_inpainting_b200.models import text_segmentation as MT
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"segnet_{cls_name}.npz"))
+    n, hw, step = int(g["n"]), int(g["hw"]), int(g["step"])
+    net = getattr(MT, cls_name)()
+    net.load_state_dict(det_fill_state_dict(net.state_dict()))
+    net = net.to(dev).train()
+    x = det_tensor(cls_name + ".x", (n, 3, hw, hw)).to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    out = net(x)
+    loss = ops.l1_mean(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    errs = {"out": relerr(out[..., ::step, ::step], torch.from_numpy(g["out_sub"])),
+            "out_row": relerr(out[0, :, hw // 2, :], torch.from_numpy(g["out_row"])),
+            "loss": abs(float(loss.detach()) - float(g["loss"])) / abs(float(g["loss"]))}
+    params = dict(net.named_parameters())
+    sdn = net.state_dict()
+    for k in g.files:
+        if k.startswith("g."):
+            errs[k] = relerr(params[k[2:]].grad, torch.from_numpy(g[k]))
+        if k.startswith("bn."):
+            errs[k] = relerr(sdn[k[3:]], torch.from_numpy(g[k]))
+    return errs

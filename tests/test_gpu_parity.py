@@ -159,3 +159,39 @@ def test_train_step_engine_graph_matches_eager(dev):
             assert ts.graph is not None
         losses.append([float(ts.step(x, mask)) for _ in range(3)])
     assert losses[0][0] > 0 and all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(*losses)), losses
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense segmentation path (Conv_block / DSConvBlock / InvertedResidual / scSE / RFB / ASP / pooling / bilinear)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dsconv_s2", "dsconv_d4", "invres_scse", "invres_s2", "scse", "rfb", "asp"])
+@pytest.mark.parametrize("dtype", [F32, BF], ids=["f32", "bf16"])
+def test_segmentation_blocks_vs_reference_golden(name, dtype, dev):
+    from gpu_cases import seg_block_case
+    errs = seg_block_case(name, dev, dtype)
+    assert _pipeline_clean()
+    tol = 2e-4 if dtype == F32 else 4e-2         # bf16: input + every intermediate rounded to 8 mantissa bits
+    assert max(errs.values()) <= tol, errs
+
+
+@pytest.mark.parametrize("dtype", [F32, BF], ids=["f32", "bf16"])
+def test_avgpool_and_bilinear_vs_reference_golden(dtype, dev):
+    from gpu_cases import pool_bilinear_case
+    errs = pool_bilinear_case(dev, dtype)
+    assert max(errs.values()) <= (1e-5 if dtype == F32 else 2e-2), errs
+
+
+@pytest.mark.parametrize("cls_name", ["TextSegament", "XceptionTextSegment"])
+def test_segmentation_network_fp32_matches_reference_golden(cls_name, dev):
+    from gpu_cases import run_segnet
+    errs = run_segnet(cls_name, dev, F32)
+    assert errs["out"] <= 1e-3 and errs["out_row"] <= 1e-3 and errs["loss"] <= 1e-4, errs      # north_star bar on the forward
+    assert max(errs.values()) <= 5e-3, errs
+
+
+@pytest.mark.parametrize("cls_name", ["TextSegament", "XceptionTextSegment"])
+def test_segmentation_network_bf16(cls_name, dev):
+    from gpu_cases import run_segnet
+    errs = run_segnet(cls_name, dev, BF)
+    assert _pipeline_clean()
+    assert errs["out"] <= 5e-2 and errs["loss"] <= 2e-2, errs

@@ -47,7 +47,8 @@ static int validate(const pcb_conv *c, bool need_x) {
     return 0;
 }
 
-static bool use_tc(const pcb_conv *c) { return !c->force_generic && pcb_tc_eligible(c); }
+static bool use_dw(const pcb_conv *c) { return pcb_dw_eligible(c); }
+static bool use_tc(const pcb_conv *c) { return !c->force_generic && !use_dw(c) && pcb_tc_eligible(c); }
 
 #define PCB_API extern "C" __attribute__((visibility("default")))
 
@@ -56,6 +57,7 @@ PCB_API int pcb_conv_uses_tensor_cores(const pcb_conv *c) { return (c && use_tc(
 PCB_API size_t pcb_pconv_workspace(const pcb_conv *c) { return (c && use_tc(c)) ? pcb_tc_workspace(c) : 0; }
 
 PCB_API void pcb_conv_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems) {
+    if (use_dw(c)) { *fwd_elems = static_cast<size_t>(c->cin) * c->kh * c->kw; *dgrad_elems = 0; return; }   // [taps][c]
     if (use_tc(c)) { pcb_tc_weight_layout(c, fwd_elems, dgrad_elems); return; }
     *fwd_elems = static_cast<size_t>(c->cout) * c->kh * c->kw * (c->cin / c->groups);
     *dgrad_elems = 0;
@@ -66,6 +68,7 @@ int pcb_cast_weights(const float *src, void *dst, long long n, int dtype, cudaSt
 PCB_API int pcb_conv_weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream) {
     PCB_CHECK(c && w_master_krsc && w_fwd, "pcb_conv_weight_prepare: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_dw(c)) return pcb_dw_weight_prepare(c, w_master_krsc, w_fwd, st);
     if (use_tc(c)) return pcb_tc_weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, st);
     return pcb_cast_weights(w_master_krsc, w_fwd, static_cast<long long>(c->cout) * c->kh * c->kw * (c->cin / c->groups), c->dtype, st);
 }
@@ -76,6 +79,10 @@ PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float 
     PCB_CHECK(w_fwd && y && msum && newmask && y_cstride >= c->cout, "pcb_pconv_forward: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
+    if (use_dw(c)) {
+        PCB_CHECK(y_cstride % 8 == 0, "depthwise forward: y channel stride must be a multiple of 8");
+        return pcb_dw_forward(c, w_fwd, bias, y, y_cstride, msum, st);
+    }
     if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr, "pcb_pconv_forward: workspace required for the tensor-core path");
         PCB_CHECK((reinterpret_cast<uintptr_t>(w_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "w / y must be 16-byte aligned");
@@ -89,6 +96,11 @@ PCB_API int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cs
     if (int rc = validate(c, false)) return rc;
     PCB_CHECK(dc && w_fwd && dx && dx_cstride && dc_cstride >= c->cout, "pcb_pconv_backward_data: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_dw(c)) {
+        if (!dx[0]) return 0;
+        PCB_CHECK(dc_cstride % 8 == 0 && dx_cstride[0] % 8 == 0, "depthwise dgrad: channel strides must be multiples of 8");
+        return pcb_dw_dgrad(c, dc, dc_cstride, w_fwd, dx[0], dx_cstride[0], st);
+    }
     if (use_tc(c)) {
         PCB_CHECK(pcb_tc_dgrad_supported(c), "data gradient of a row-packed (cin <= 8) tensor-core layer: set force_generic and pass KRSC weights");
         PCB_CHECK(w_dgrad != nullptr && (reinterpret_cast<uintptr_t>(dc) & 15) == 0, "pcb_pconv_backward_data: w_dgrad required / dc misaligned");
@@ -101,6 +113,10 @@ PCB_API int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, int dc_
     if (int rc = validate(c, true)) return rc;
     PCB_CHECK(dc && dw && dc_cstride >= c->cout, "pcb_pconv_backward_weight: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_dw(c)) {
+        PCB_CHECK(dc_cstride % 8 == 0, "depthwise wgrad: dc channel stride must be a multiple of 8");
+        return pcb_dw_wgrad(c, dc, dc_cstride, dw, st);
+    }
     if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr && (reinterpret_cast<uintptr_t>(dc) & 15) == 0, "pcb_pconv_backward_weight: workspace required / dc misaligned");
         return pcb_tc_wgrad(c, dc, dc_cstride, dw, workspace, st);

@@ -1,0 +1,362 @@
+// seg_ops.cu -- HBM-bound glue of the segmentation encoder-decoders (models/text_segmentation.py): average pooling
+// (nn.AvgPool2d, count_include_pad=True: :33,66-67; ASP's AvgPool(k,1,(k-1)//2) models/common.py:62-68), bilinear
+// upsampling with align_corners=False (:54,76,109,113), and the scSE gate (models/common.py:13-43):
+//   y = x * cSE[n,c] + x * sSE[n,p],  cSE = sigmoid(MLP(GAP(x))),  sSE = sigmoid(<x[p,:], w_s>).
+// NHWC, 8-channel vectors, fp32 math.
+#include <string.h>
+
+#include <algorithm>
+
+#include "pcb_common.cuh"
+
+namespace {
+
+inline int sg_grid(long long items, int per_block = 256) {
+    long long b = (items + per_block - 1) / per_block;
+    const long long cap = 32ll * pcb_num_sms();
+    return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------------------ avg pool
+template <typename T, bool BWD>
+__global__ void avgpool_kernel(const T *__restrict__ src, T *__restrict__ dst, int n, int h, int w, int c, int k, int stride, int pad, int ho, int wo) {
+    // FWD: dst[n,ho,wo,c] = sum_{window} src[n,hi,wi,c] / k^2   (padding counted: count_include_pad=True)
+    // BWD: dst[n,h,w,c]   = sum_{outputs covering (h,w)} src[n,oh,ow,c] / k^2
+    const int cv = c >> 3;
+    const int H = BWD ? h : ho, W = BWD ? w : wo;
+    const long long nvec = static_cast<long long>(n) * H * W * cv;
+    const float inv = 1.0f / static_cast<float>(k * k);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / cv;
+        const int ch = static_cast<int>(i - m * cv) * 8;
+        const int x0 = static_cast<int>(m % W);
+        const long long t = m / W;
+        const int y0 = static_cast<int>(t % H), nn = static_cast<int>(t / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) {
+                int sy, sx;
+                if (!BWD) {
+                    sy = y0 * stride - pad + a; sx = x0 * stride - pad + b;
+                    if (sy < 0 || sy >= h || sx < 0 || sx >= w) continue;
+                } else {
+                    const int ty = y0 + pad - a, tx = x0 + pad - b;
+                    if (ty < 0 || tx < 0) continue;
+                    sy = ty / stride; sx = tx / stride;
+                    if (sy * stride != ty || sx * stride != tx || sy >= ho || sx >= wo) continue;
+                }
+                float v[8];
+                const int SH = BWD ? ho : h, SW = BWD ? wo : w;
+                Vec8<T>::load(src + (static_cast<long long>(nn * SH + sy) * SW + sx) * c + ch, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        Vec8<T>::store(dst + i * 8, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear
+// align_corners=False, integer scale s: src coordinate = (dst + 0.5)/s - 0.5, clamped at 0 (PyTorch semantics)
+__device__ __forceinline__ void bil_coeffs(int d, int s, int in_size, int &i0, int &i1, float &l1) {
+    float src = (static_cast<float>(d) + 0.5f) / static_cast<float>(s) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = static_cast<int>(src);
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - static_cast<float>(i0);
+}
+
+template <typename T>
+__global__ void bilinear_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int n, int h, int w, int c, int s) {
+    const int cv = c >> 3, H = h * s, W = w * s;
+    const long long nvec = static_cast<long long>(n) * H * W * cv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / cv;
+        const int ch = static_cast<int>(i - m * cv) * 8;
+        const int ox = static_cast<int>(m % W);
+        const long long t = m / W;
+        const int oy = static_cast<int>(t % H), nn = static_cast<int>(t / H);
+        int y0, y1, x0, x1; float ly, lx;
+        bil_coeffs(oy, s, h, y0, y1, ly); bil_coeffs(ox, s, w, x0, x1, lx);
+        float a[8], b[8], cc[8], d[8], o[8];
+        const T *base = x + static_cast<long long>(nn) * h * w * c + ch;
+        Vec8<T>::load(base + (static_cast<long long>(y0) * w + x0) * c, a);
+        Vec8<T>::load(base + (static_cast<long long>(y0) * w + x1) * c, b);
+        Vec8<T>::load(base + (static_cast<long long>(y1) * w + x0) * c, cc);
+        Vec8<T>::load(base + (static_cast<long long>(y1) * w + x1) * c, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * cc[j] + lx * d[j]);
+        Vec8<T>::store(y + i * 8, o);
+    }
+}
+
+// backward by gathering: each input pixel collects from the output pixels whose stencil touches it
+template <typename T>
+__global__ void bilinear_bwd_kernel(const T *__restrict__ gy, T *__restrict__ gx, int n, int h, int w, int c, int s) {
+    const int cv = c >> 3, H = h * s, W = w * s;
+    const long long nvec = static_cast<long long>(n) * h * w * cv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / cv;
+        const int ch = static_cast<int>(i - m * cv) * 8;
+        const int ix = static_cast<int>(m % w);
+        const long long t = m / w;
+        const int iy = static_cast<int>(t % h), nn = static_cast<int>(t / h);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const int oy_lo = max(0, (iy - 1) * s), oy_hi = min(H - 1, (iy + 2) * s);
+        const int ox_lo = max(0, (ix - 1) * s), ox_hi = min(W - 1, (ix + 2) * s);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            int y0, y1; float ly;
+            bil_coeffs(oy, s, h, y0, y1, ly);
+            const float wy = (y0 == iy ? (1.f - ly) : 0.f) + (y1 == iy ? ly : 0.f);
+            if (wy == 0.f) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                int x0, x1; float lx;
+                bil_coeffs(ox, s, w, x0, x1, lx);
+                const float wx = (x0 == ix ? (1.f - lx) : 0.f) + (x1 == ix ? lx : 0.f);
+                if (wx == 0.f) continue;
+                float g[8];
+                Vec8<T>::load(gy + (static_cast<long long>(nn * H + oy) * W + ox) * c + ch, g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += wy * wx * g[j];
+            }
+        }
+        Vec8<T>::store(gx + i * 8, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GAP
+// out[n][c] (fp32) = mean over hw of x[n,:,c]
+template <typename T>
+__global__ void __launch_bounds__(256) gap_kernel(const T *__restrict__ x, long long hw, int c, float *__restrict__ out, int chunks) {
+    __shared__ float s_red[256][8];
+    const int cv = c >> 3, rpb = 256 / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    const int nn = blockIdx.y;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (r < rpb) {
+        const T *base = x + static_cast<long long>(nn) * hw * c;
+        for (long long p = static_cast<long long>(blockIdx.x) * rpb + r; p < hw; p += static_cast<long long>(chunks) * rpb) {
+            float f[8];
+            Vec8<T>::load(base + p * c + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_red[threadIdx.x][j] = acc[j];
+    }
+    __syncthreads();
+    if (r == 0 && v < cv) {
+        const float inv = 1.0f / static_cast<float>(hw);
+        for (int j = 0; j < 8; ++j) {
+            float tot = 0.f;
+            for (int rr = 0; rr < rpb; ++rr) tot += s_red[rr * cv + v][j];
+            atomicAdd(out + static_cast<long long>(nn) * c + v * 8 + j, tot * inv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ scSE gate
+// one warp per pixel: sse = sigmoid(<x[p,:], ws>) ; y = x * (cse[n,:] + sse)
+template <typename T>
+__global__ void __launch_bounds__(256) scse_fwd_kernel(const T *__restrict__ x, const float *__restrict__ cse, const float *__restrict__ ws,
+                                                       T *__restrict__ y, float *__restrict__ sse_out, long long npix, long long hw, int c) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int cv = c >> 3;
+    for (long long p = warp; p < npix; p += nwarps) {
+        const long long nn = p / hw;
+        float dot = 0.f;
+        for (int v = lane; v < cv; v += 32) {
+            float f[8];
+            Vec8<T>::load(x + p * c + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dot += f[j] * ws[v * 8 + j];
+        }
+        dot = warp_sum(dot);
+        const float sse = 1.0f / (1.0f + __expf(-dot));
+        if (lane == 0) sse_out[p] = sse;
+        for (int v = lane; v < cv; v += 32) {
+            float f[8];
+            Vec8<T>::load(x + p * c + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= (cse[nn * c + v * 8 + j] + sse);
+            Vec8<T>::store(y + p * c + v * 8, f);
+        }
+    }
+}
+
+// dx = g*(cse+sse) + ws * [sse(1-sse) * sum_c g x] ; dcse[n,c] += sum_p g x ; dws[c] += sum_p x * sse(1-sse) * sum_c' g x
+template <typename T>
+__global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ x, const float *__restrict__ cse,
+                                                       const float *__restrict__ ws, const float *__restrict__ sse_in, T *__restrict__ dx,
+                                                       float *__restrict__ dcse, float *__restrict__ dws, long long npix, long long hw, int c) {
+    extern __shared__ float s_acc[];            // [2][c] : dcse partial (for this block's batch index run) and dws partial
+    float *s_dcse = s_acc, *s_dws = s_acc + c;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int cv = c >> 3;
+    // each block owns a contiguous pixel range so that its dcse partial belongs to few batch indices
+    const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
+    const long long p_begin = blockIdx.x * per_block, p_end = min(npix, p_begin + per_block);
+    long long cur_n = -1;
+    for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    for (long long p0 = p_begin; p0 < p_end; p0 += wpb) {
+        const long long p = p0 + wib;
+        const long long n_here = (p0 / hw);          // batch index of the first pixel of this round (uniform)
+        if (n_here != cur_n) {                        // flush the per-sample partial when the block crosses a sample boundary
+            __syncthreads();
+            if (cur_n >= 0)
+                for (int i = threadIdx.x; i < c; i += blockDim.x) { atomicAdd(dcse + cur_n * c + i, s_dcse[i]); s_dcse[i] = 0.f; }
+            __syncthreads();
+            cur_n = n_here;
+        }
+        if (p < p_end) {
+            const long long nn = p / hw;
+            const float sse = sse_in[p];
+            float dot = 0.f;
+            for (int v = lane; v < cv; v += 32) {
+                float g[8], f[8];
+                Vec8<T>::load(gy + p * c + v * 8, g);
+                Vec8<T>::load(x + p * c + v * 8, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dot += g[j] * f[j];
+            }
+            dot = warp_sum(dot);
+            const float dpre = dot * sse * (1.f - sse);
+            for (int v = lane; v < cv; v += 32) {
+                float g[8], f[8], o[8];
+                Vec8<T>::load(gy + p * c + v * 8, g);
+                Vec8<T>::load(x + p * c + v * 8, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ch = v * 8 + j;
+                    o[j] = g[j] * (cse[nn * c + ch] + sse) + ws[ch] * dpre;
+                    if (nn == cur_n) atomicAdd(&s_dcse[ch], g[j] * f[j]);
+                    else atomicAdd(dcse + nn * c + ch, g[j] * f[j]);      // rare: round straddles a sample boundary
+                    atomicAdd(&s_dws[ch], f[j] * dpre);
+                }
+                Vec8<T>::store(dx + p * c + v * 8, o);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        if (cur_n >= 0) atomicAdd(dcse + cur_n * c + i, s_dcse[i]);
+        atomicAdd(dws + i, s_dws[i]);
+    }
+}
+
+// broadcast add: dx[n,p,c] += g[n,c] / hw   (backward of the global average pool)
+template <typename T>
+__global__ void gap_bwd_kernel(const float *__restrict__ g, T *__restrict__ dx, long long npix, long long hw, int c, int accumulate) {
+    const int cv = c >> 3;
+    const long long nvec = npix * cv;
+    const float inv = 1.0f / static_cast<float>(hw);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i / cv;
+        const int ch = static_cast<int>(i - p * cv) * 8;
+        const long long nn = p / hw;
+        float o[8];
+        if (accumulate) Vec8<T>::load(dx + i * 8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (accumulate ? o[j] : 0.f) + g[nn * c + ch + j] * inv;
+        Vec8<T>::store(dx + i * 8, o);
+    }
+}
+
+}  // namespace
+
+#define ST static_cast<cudaStream_t>(stream)
+#define PCB_API extern "C" __attribute__((visibility("default")))
+PCB_API int pcb_avgpool_forward(const void *x, void *y, int dtype, int n, int h, int w, int c, int k, int stride, int pad, pcb_stream_t stream) {
+    PCB_CHECK(x && y && c % 8 == 0 && k > 0 && stride > 0, "pcb_avgpool_forward: bad arguments (channels must be a multiple of 8)");
+    const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+    const long long nvec = static_cast<long long>(n) * ho * wo * (c / 8);
+    if (dtype == PCB_BF16) avgpool_kernel<bf16, false><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y), n, h, w, c, k, stride, pad, ho, wo);
+    else avgpool_kernel<float, false><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const float *>(x), static_cast<float *>(y), n, h, w, c, k, stride, pad, ho, wo);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_avgpool_backward(const void *gy, void *gx, int dtype, int n, int h, int w, int c, int k, int stride, int pad, pcb_stream_t stream) {
+    PCB_CHECK(gy && gx && c % 8 == 0 && k > 0 && stride > 0, "pcb_avgpool_backward: bad arguments");
+    const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+    const long long nvec = static_cast<long long>(n) * h * w * (c / 8);
+    if (dtype == PCB_BF16) avgpool_kernel<bf16, true><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<bf16 *>(gx), n, h, w, c, k, stride, pad, ho, wo);
+    else avgpool_kernel<float, true><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const float *>(gy), static_cast<float *>(gx), n, h, w, c, k, stride, pad, ho, wo);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_bilinear_forward(const void *x, void *y, int dtype, int n, int h, int w, int c, int scale, pcb_stream_t stream) {
+    PCB_CHECK(x && y && c % 8 == 0 && scale >= 1, "pcb_bilinear_forward: bad arguments (channels must be a multiple of 8)");
+    const long long nvec = static_cast<long long>(n) * h * scale * w * scale * (c / 8);
+    if (dtype == PCB_BF16) bilinear_fwd_kernel<bf16><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const bf16 *>(x), static_cast<bf16 *>(y), n, h, w, c, scale);
+    else bilinear_fwd_kernel<float><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const float *>(x), static_cast<float *>(y), n, h, w, c, scale);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_bilinear_backward(const void *gy, void *gx, int dtype, int n, int h, int w, int c, int scale, pcb_stream_t stream) {
+    PCB_CHECK(gy && gx && c % 8 == 0 && scale >= 1, "pcb_bilinear_backward: bad arguments");
+    const long long nvec = static_cast<long long>(n) * h * w * (c / 8);
+    if (dtype == PCB_BF16) bilinear_bwd_kernel<bf16><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<bf16 *>(gx), n, h, w, c, scale);
+    else bilinear_bwd_kernel<float><<<sg_grid(nvec), 256, 0, ST>>>(static_cast<const float *>(gy), static_cast<float *>(gx), n, h, w, c, scale);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_gap_forward(const void *x, int dtype, int n, long long hw, int c, float *out, pcb_stream_t stream) {
+    PCB_CHECK(x && out && c % 8 == 0 && c <= 2048 && hw > 0, "pcb_gap_forward: bad arguments (channels % 8 == 0, <= 2048)");
+    PCB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n * c, ST));
+    const int rpb = 256 / (c / 8);
+    int chunks = static_cast<int>(std::min<long long>((hw + rpb * 8 - 1) / (rpb * 8), std::max(1, 4 * pcb_num_sms() / std::max(1, n))));
+    chunks = std::max(1, chunks);
+    if (dtype == PCB_BF16) gap_kernel<bf16><<<dim3(chunks, n), 256, 0, ST>>>(static_cast<const bf16 *>(x), hw, c, out, chunks);
+    else gap_kernel<float><<<dim3(chunks, n), 256, 0, ST>>>(static_cast<const float *>(x), hw, c, out, chunks);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_gap_backward(const float *g, void *dx, int dtype, int n, long long hw, int c, int accumulate, pcb_stream_t stream) {
+    PCB_CHECK(g && dx && c % 8 == 0, "pcb_gap_backward: bad arguments");
+    const long long npix = static_cast<long long>(n) * hw;
+    if (dtype == PCB_BF16) gap_bwd_kernel<bf16><<<sg_grid(npix * (c / 8)), 256, 0, ST>>>(g, static_cast<bf16 *>(dx), npix, hw, c, accumulate);
+    else gap_bwd_kernel<float><<<sg_grid(npix * (c / 8)), 256, 0, ST>>>(g, static_cast<float *>(dx), npix, hw, c, accumulate);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_scse_forward(const void *x, const float *cse, const float *ws, void *y, float *sse_out, int dtype, int n, long long hw, int c,
+                             pcb_stream_t stream) {
+    PCB_CHECK(x && cse && ws && y && sse_out && c % 8 == 0, "pcb_scse_forward: bad arguments (channels must be a multiple of 8)");
+    const long long npix = static_cast<long long>(n) * hw;
+    const int grid = sg_grid(npix * 32);
+    if (dtype == PCB_BF16) scse_fwd_kernel<bf16><<<grid, 256, 0, ST>>>(static_cast<const bf16 *>(x), cse, ws, static_cast<bf16 *>(y), sse_out, npix, hw, c);
+    else scse_fwd_kernel<float><<<grid, 256, 0, ST>>>(static_cast<const float *>(x), cse, ws, static_cast<float *>(y), sse_out, npix, hw, c);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+PCB_API int pcb_scse_backward(const void *gy, const void *x, const float *cse, const float *ws, const float *sse, void *dx, float *dcse,
+                              float *dws, int dtype, int n, long long hw, int c, pcb_stream_t stream) {
+    PCB_CHECK(gy && x && cse && ws && sse && dx && dcse && dws && c % 8 == 0 && c <= 4096, "pcb_scse_backward: bad arguments");
+    const long long npix = static_cast<long long>(n) * hw;
+    PCB_CUDA(cudaMemsetAsync(dcse, 0, sizeof(float) * n * c, ST));
+    PCB_CUDA(cudaMemsetAsync(dws, 0, sizeof(float) * c, ST));
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((npix + 63) / 64, 8ll * pcb_num_sms())));
+    const size_t smem = sizeof(float) * 2 * c;
+    if (dtype == PCB_BF16) scse_bwd_kernel<bf16><<<grid, 256, smem, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), cse, ws, sse, static_cast<bf16 *>(dx), dcse, dws, npix, hw, c);
+    else scse_bwd_kernel<float><<<grid, 256, smem, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), cse, ws, sse, static_cast<float *>(dx), dcse, dws, npix, hw, c);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}

@@ -7,6 +7,7 @@ initialisers keyed on ``isinstance(m, nn.Conv2d / nn.BatchNorm2d)`` (:17-39), ``
 import math
 from contextlib import contextmanager
 
+import torch
 from torch import nn
 
 
@@ -72,3 +73,59 @@ class BaseModule(nn.Module):
 
     def forward(self, *x):
         raise NotImplementedError
+
+
+# +++++++++++++++++++++++++++++++++++++
+#   Convolution wrappers (reference models/BaseModels.py:91-127)
+# -------------------------------------
+class B200Conv2d(nn.Conv2d):
+    """An ``nn.Conv2d`` (isinstance / out_channels / state_dict identical -- SURVEY 8b "attribute conventions")
+    whose forward runs on libpconv_b200: dense and 1x1 convolutions on the tcgen05 implicit-GEMM kernel,
+    depthwise ones on the vectorised HBM-bound kernel, anything else on the shape-general kernel."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.padding_mode != "zeros" or isinstance(self.padding, str):
+            raise NotImplementedError("only explicit zero padding")
+        self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
+        self._wcache = {}
+
+    def forward(self, x):
+        from .. import ops
+        return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups, cache=self._wcache)
+
+
+class B200BNAct(nn.Sequential):
+    """``nn.Sequential(nn.BatchNorm2d(c)[, act])`` (same keys: ``0.weight`` ...) as one statistics pass + one
+    apply pass of libpconv_b200."""
+
+    def forward(self, x, residual=None):
+        from .. import ops
+        act = self[1] if len(self) > 1 else None
+        return ops.bn_act(x, self[0], act, residual=residual)
+
+
+def Conv_block(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True, BN=False,
+               activation=None):
+    """Returns the LIST ``[conv, (BN[, act]) | act]`` exactly like the reference factory (BaseModels.py:91-102)."""
+    m = [B200Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)]
+    if BN:
+        m.append(B200BNAct(nn.BatchNorm2d(out_channels), activation) if activation else B200BNAct(nn.BatchNorm2d(out_channels)))
+    if BN is False and activation is not None:
+        m.append(activation)
+    return m
+
+
+class DSConvBlock(BaseModule):
+    """Depthwise-separable unit: dw kxk (+BN+act) -> pw 1x1 (+BN+act)  (BaseModels.py:105-127)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True, BN=False,
+                 activation_dep=None, activation_point=None):
+        super().__init__()
+        self.depth_wise_conv = nn.Sequential(*Conv_block(in_channels, in_channels, kernel_size, stride, padding, dilation,
+                                                         in_channels, bias, BN=BN, activation=activation_dep))
+        self.point_wise_conv = nn.Sequential(*Conv_block(in_channels, out_channels, kernel_size=1, stride=1, padding=0, dilation=1,
+                                                         bias=bias, BN=BN, activation=activation_point))
+
+    def forward(self, x):
+        return self.point_wise_conv(self.depth_wise_conv(x))

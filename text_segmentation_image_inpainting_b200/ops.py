@@ -544,3 +544,152 @@ def sgd_step(param, grad, buf, lr, momentum=0.0, weight_decay=0.0, nesterov=Fals
     _lib.check(lib.pcb_sgd_step(param.data_ptr(), grad.data_ptr(), _ptr(buf), param.numel(), float(lr), float(momentum),
                                 float(weight_decay), int(nesterov), int(first_step), _stream()))
     bump_weight_epoch()
+
+
+# ------------------------------------------------------------------------------------------------
+# dense (non-partial) building blocks of the segmentation networks
+# ------------------------------------------------------------------------------------------------
+def _dense8(x: torch.Tensor):
+    """x as a dense NHWC tensor whose channel count is a multiple of 8 (zero-padded copy if needed).
+    Returns (tensor with c8 channels, original channel count)."""
+    x = as_feature_padded(x)
+    n, c, h, w = x.shape
+    c8 = (c + 7) // 8 * 8
+    cs = nhwc_layout(x)
+    if c8 == c and cs == c:
+        return x, c
+    if cs == c8:                       # a [:, :c] view of a padded buffer: use the buffer itself
+        base = x.as_strided((n, c8, h, w), (h * w * c8, 1, w * c8, c8))
+        return base, c
+    buf = padded_empty(n, c, h, w, x.dtype, x.device)
+    buf.copy_(x)
+    return buf.as_strided((n, c8, h, w), (h * w * c8, 1, w * c8, c8)), c
+
+
+def conv2d(x, weight, bias, stride, padding, dilation, groups, cache=None):
+    """nn.Conv2d on the same kernels as the partial convolution (`plain`: mask ignored, renormaliser 1)."""
+    x = as_feature_padded(x)
+    if x.dtype == torch.bfloat16 and x.shape[1] < 8 and nhwc_layout(x) % 8 != 0 and groups == 1:
+        buf = padded_empty(*x.shape, x.dtype, x.device)          # 16-byte pixels -> row-packed tensor-core path
+        buf.copy_(x)
+        x = buf
+    y, _ = partial_conv(x, None, weight, bias, stride, padding, dilation, groups, cache=cache, plain=True)
+    return y
+
+
+class _Pool2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        lib = _lib.load()
+        n, c, h, w = x.shape
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        y = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device, memory_format=CL)
+        _lib.check(lib.pcb_avgpool_forward(x.data_ptr(), y.data_ptr(), _dtype_code(x), n, h, w, c, k, stride, pad, _stream()))
+        ctx.meta = (n, c, h, w, k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        n, c, h, w, k, stride, pad = ctx.meta
+        gy = gy.contiguous(memory_format=CL)
+        gx = torch.empty((n, c, h, w), dtype=gy.dtype, device=gy.device, memory_format=CL)
+        _lib.check(lib.pcb_avgpool_backward(gy.data_ptr(), gx.data_ptr(), _dtype_code(gy), n, h, w, c, k, stride, pad, _stream()))
+        return gx, None, None, None
+
+
+def avg_pool2d(x, k, stride, pad):
+    """nn.AvgPool2d(k, stride, pad), count_include_pad=True."""
+    xb, c = _dense8(x)
+    y = _Pool2dFn.apply(xb, int(k), int(stride), int(pad))
+    return y if y.shape[1] == c else y[:, :c]
+
+
+class _BilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        lib = _lib.load()
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, h * scale, w * scale), dtype=x.dtype, device=x.device, memory_format=CL)
+        _lib.check(lib.pcb_bilinear_forward(x.data_ptr(), y.data_ptr(), _dtype_code(x), n, h, w, c, scale, _stream()))
+        ctx.meta = (n, c, h, w, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        n, c, h, w, scale = ctx.meta
+        gy = gy.contiguous(memory_format=CL)
+        gx = torch.empty((n, c, h, w), dtype=gy.dtype, device=gy.device, memory_format=CL)
+        _lib.check(lib.pcb_bilinear_backward(gy.data_ptr(), gx.data_ptr(), _dtype_code(gy), n, h, w, c, scale, _stream()))
+        return gx, None
+
+
+def bilinear_upsample(x, scale):
+    """F.interpolate(x, scale_factor=scale, mode='bilinear', align_corners=False) for integer scale."""
+    if int(scale) != scale or scale < 1:
+        raise NotImplementedError("bilinear upsampling: integer scale factors only")
+    xb, c = _dense8(x)
+    y = _BilinearFn.apply(xb, int(scale))
+    return y if y.shape[1] == c else y[:, :c]
+
+
+class _GapFn(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(1)(x).view(n, c) in fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        n, c, h, w = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        _lib.check(lib.pcb_gap_forward(x.data_ptr(), _dtype_code(x), n, h * w, c, out.data_ptr(), _stream()))
+        ctx.meta = (n, c, h, w, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n, c, h, w, dt = ctx.meta
+        g = g.contiguous().float()
+        dx = torch.empty((n, c, h, w), dtype=dt, device=g.device, memory_format=CL)
+        _lib.check(lib.pcb_gap_backward(g.data_ptr(), dx.data_ptr(), PCB_BF16 if dt == torch.bfloat16 else PCB_F32, n, h * w, c, 0, _stream()))
+        return dx
+
+
+class _ScseFn(torch.autograd.Function):
+    """y = x * cse[n, c] + x * sigmoid(<x[p, :], ws>)   (models/common.py:37-43)."""
+
+    @staticmethod
+    def forward(ctx, x, cse, ws):
+        lib = _lib.load()
+        n, c, h, w = x.shape
+        cse32, ws32 = cse.contiguous().float(), ws.contiguous().float()
+        y = torch.empty_like(x, memory_format=CL)
+        sse = torch.empty((n * h * w,), dtype=torch.float32, device=x.device)
+        _lib.check(lib.pcb_scse_forward(x.data_ptr(), cse32.data_ptr(), ws32.data_ptr(), y.data_ptr(), sse.data_ptr(), _dtype_code(x),
+                                        n, h * w, c, _stream()))
+        ctx.save_for_backward(x, cse32, ws32, sse)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, cse, ws, sse = ctx.saved_tensors
+        n, c, h, w = x.shape
+        gy = gy.contiguous(memory_format=CL)
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
+        dx = torch.empty_like(x, memory_format=CL)
+        dcse = torch.empty_like(cse)
+        dws = torch.empty_like(ws)
+        _lib.check(lib.pcb_scse_backward(gy.data_ptr(), x.data_ptr(), cse.data_ptr(), ws.data_ptr(), sse.data_ptr(), dx.data_ptr(),
+                                         dcse.data_ptr(), dws.data_ptr(), _dtype_code(x), n, h * w, c, _stream()))
+        return dx, dcse, dws
+
+
+def global_avg_pool(x):
+    return _GapFn.apply(as_feature(x))
+
+
+def scse_gate(x, cse, ws):
+    return _ScseFn.apply(as_feature(x), cse, ws)

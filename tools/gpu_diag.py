@@ -71,6 +71,26 @@ for cls_name in ("ImageFillOrigin", "ImageFillOriginV2", "ImageFill"):
             errs["ok"] = max(errs.values()) <= tol
             return errs
         guarded(f"net:{cls_name}:{'f32' if dt == G.F32 else 'bf16'}", run)
+for name in G.seg_block_builders():
+    for dt in (G.F32, G.BF):
+        def runb(name=name, dt=dt):
+            errs = G.seg_block_case(name, dev, dt)
+            errs["ok"] = max(errs.values()) <= (2e-4 if dt == G.F32 else 4e-2)
+            return errs
+        guarded(f"seg:{name}:{'f32' if dt == G.F32 else 'bf16'}", runb)
+for dt in (G.F32, G.BF):
+    def runp(dt=dt):
+        errs = G.pool_bilinear_case(dev, dt)
+        errs["ok"] = max(errs.values()) <= (1e-5 if dt == G.F32 else 2e-2)
+        return errs
+    guarded(f"seg:pool_bilinear:{'f32' if dt == G.F32 else 'bf16'}", runp)
+for cls_name in ("TextSegament", "XceptionTextSegment"):
+    for dt, tol in ((G.F32, 5e-3), (G.BF, 2e-1)):
+        def runs(cls_name=cls_name, dt=dt, tol=tol):
+            errs = G.run_segnet(cls_name, dev, dt)
+            errs["ok"] = max(errs.values()) <= tol
+            return errs
+        guarded(f"segnet:{cls_name}:{'f32' if dt == G.F32 else 'bf16'}", runs)
 json.dump(RESULTS, open(os.path.join(OUT, "diag.json"), "w"), indent=1)
 bad = [k for k, v in RESULTS.items() if not v["ok"]]
 log("FAILED:", bad if bad else "none")
