@@ -100,8 +100,11 @@ def test_constructor_surface_and_state_dict_keys():
 def test_network_key_lists_match_reference_fixture():
     """tests/golden/state_dict_keys.json was written from the reference's own modules."""
     ref = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    from text_segmentation_image_inpainting_b200.models import text_segmentation as PTS
+    assert set(ref) == {"ImageFillOrigin", "ImageFillOriginV2", "ImageFill", "TextSegament", "XceptionTextSegment"}
     for name, keys in ref.items():
-        mine = [[k, list(v.shape)] for k, v in getattr(PII, name)().state_dict().items()]
+        cls = getattr(PII, name, None) or getattr(PTS, name)
+        mine = [[k, list(v.shape)] for k, v in cls().state_dict().items()]
         assert mine == keys, name
 
 

@@ -209,6 +209,53 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__res
     }
 }
 
+// scalar fallbacks (any channel count; small tensors): one block per channel for the reductions
+template <typename T>
+__global__ void bn_bwd_reduce_scalar_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c, const float *scale,
+                                            const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                            double *sum_g, double *sum_gx) {
+    for (int ch = blockIdx.x; ch < c; ch += gridDim.x) {
+        const float sc = scale ? scale[ch] : 1.f, sh = shift ? shift[ch] : 0.f, mu = mean ? mean[ch] : 0.f, is = invstd ? invstd[ch] : 1.f;
+        float a = 0.f, b = 0.f;
+        for (long long row = threadIdx.x; row < count; row += blockDim.x) {
+            const float f = to_f32(x[row * c + ch]);
+            const float gz = to_f32(gy[row * c + ch]) * act_grad(f * sc + sh, act, slope);
+            a += gz; b += gz * (f - mu) * is;
+        }
+        __shared__ float sa[32], sb[32];
+        a = warp_sum(a); b = warp_sum(b);
+        if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ta = 0, tb = 0;
+            for (int i = 0; i < (blockDim.x >> 5); ++i) { ta += sa[i]; tb += sb[i]; }
+            sum_g[ch] = ta; sum_gx[ch] = tb;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_scalar_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long numel, long long count, int c,
+                                           const float *scale, const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                           const double *sum_g, const double *sum_gx, int training, T *__restrict__ dx) {
+    const float inv_count = 1.0f / static_cast<float>(count);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % c);
+        const float f = to_f32(x[i]);
+        const float sc = scale ? scale[ch] : 1.f, sh = shift ? shift[ch] : 0.f;
+        const float gz = to_f32(gy[i]) * act_grad(f * sc + sh, act, slope);
+        float d;
+        if (!scale) d = gz;
+        else if (!training) d = sc * gz;
+        else {
+            const float xhat = (f - mean[ch]) * invstd[ch];
+            d = sc * (gz - static_cast<float>(sum_g[ch]) * inv_count - xhat * static_cast<float>(sum_gx[ch]) * inv_count);
+        }
+        dx[i] = from_f32<T>(d);
+    }
+}
+
 __global__ void bn_param_grad_kernel(const double *sum_g, const double *sum_gx, int c, float *dgamma, float *dbeta) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
@@ -434,7 +481,12 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
                                           const float *shift, const float *mean, const float *invstd, int act, float slope,
                                           double *sum_g, double *sum_gx, pcb_stream_t stream) {
     PCB_CHECK(gy && x && sum_g && sum_gx && count > 0, "pcb_bn_act_backward_reduce: bad arguments");
-    PCB_CHECK(c % 8 == 0 && c <= 2048, "pcb_bn_act_backward_reduce: channels must be a multiple of 8 and <= 2048 (got %d)", c);
+    if (c % 8 != 0 || c > 2048) {
+        if (dtype == PCB_BF16) bn_bwd_reduce_scalar_kernel<bf16><<<min(c, 1024), 256, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
+        else bn_bwd_reduce_scalar_kernel<float><<<min(c, 1024), 256, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     PCB_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(double) * c, ST));
     PCB_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(double) * c, ST));
     const int rpb = EW_THREADS / (c / 8);
@@ -450,11 +502,13 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply(
                                          const double *sum_g, const double *sum_gx, int training, void *dx, float *dgamma, float *dbeta,
                                          pcb_stream_t stream) {
     PCB_CHECK(gy && x && dx && count > 0, "pcb_bn_act_backward_apply: bad arguments");
-    PCB_CHECK(c % 8 == 0, "pcb_bn_act_backward_apply: channels must be a multiple of 8 (got %d)", c);
     PCB_CHECK(!(scale && training) || (mean && invstd && sum_g && sum_gx), "pcb_bn_act_backward_apply: training needs statistics");
     const long long nvec = count * c / 8;
-    const int grid = ew_grid(nvec, EW_THREADS * 4);
-    if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
+    const int grid = ew_grid(c % 8 == 0 ? nvec : count * c, EW_THREADS * 4);
+    if (c % 8 != 0) {
+        if (dtype == PCB_BF16) bn_bwd_apply_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
+        else bn_bwd_apply_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
+    } else if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
     else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
     PCB_LAUNCH_CHECK();
     if ((dgamma || dbeta) && sum_g && sum_gx) {

@@ -428,8 +428,6 @@ def bn_act(x, bn, act, residual=None):
     """`bn`: nn.BatchNorm2d or None; `act`: nn activation module / None."""
     x = as_feature(x)
     code, slope = act_code(act)
-    if x.shape[1] % 8 != 0:
-        raise NotImplementedError("BatchNorm / activation kernels need channels % 8 == 0")
     if residual is not None:
         residual = as_feature(residual)
     if bn is None:
@@ -442,9 +440,6 @@ def bn_act(x, bn, act, residual=None):
 def activation_only(x, act, residual=None):
     x = as_feature(x)
     code, slope = act_code(act)
-    if x.shape[1] % 8 != 0:      # tiny-channel tensors (e.g. the 3-channel tail): let torch do it
-        y = act(x) if act else x
-        return y + residual if residual is not None else y
     return BNActFn.apply(x, None, None, residual, None, None, None, False, 0.0, 0.0, code, slope)
 
 
