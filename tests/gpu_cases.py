@@ -45,12 +45,12 @@ def relerr(a, b):
     return (a[fin] - b[fin]).abs().max().item() / max(b[fin].abs().max().item(), 1e-20)
 
 
-def rel_l2(a, b):
+def rel_l2(a, b, floor=1e-20):
     """||a - b||_2 / ||b||_2 -- the robust metric for bf16 tensors downstream of ReLU/LeakyReLU derivatives: a
     pre-activation within one bf16 ulp of zero flips the derivative of that ELEMENT (an O(1) error at isolated
     elements that max-abs metrics report as failure although the tensor agrees to a few percent in norm)."""
     a = a.detach().float().cpu(); b = b.detach().float().cpu()
-    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+    return float((a - b).norm() / b.norm().clamp_min(floor))
 
 
 # name: (cin, cout, k, s, p, d, groups, bias, same_holes, n, h, w, dtype, mask_kind, cls)
@@ -304,8 +304,12 @@ def seg_block_case(name, dev, dtype):
     y = mod(x)
     y.backward(torch.from_numpy(g["gy"]).to(dev).to(dtype))
     torch.cuda.synchronize()
-    m = relerr if dtype == F32 else rel_l2        # see rel_l2: bf16 gradients pass through activation derivatives
-    errs = {"y": relerr(y, torch.from_numpy(g["y"])), "gx": m(x.grad, torch.from_numpy(g["gx"]))}
+    # bf16 gradients: relative L2 (see rel_l2).  Gradients that are mathematically ~0 in the reference (a conv weight
+    # directly under a BatchNorm is scale-invariant; RFB's dilation-29 depthwise conv sees only its centre tap on a
+    # 12x12 map) are pure rounding noise there: floor the denominator at 1 % of the largest gradient norm.
+    floor = 0.01 * max([float(np.linalg.norm(g[k])) for k in g.files if k.startswith("g.")] + [1e-20])
+    m = relerr if dtype == F32 else (lambda a, b: rel_l2(a, b, floor))
+    errs = {"y": relerr(y, torch.from_numpy(g["y"])), "gx": (relerr if dtype == F32 else rel_l2)(x.grad, torch.from_numpy(g["gx"]))}
     params = dict(mod.named_parameters())
     sdn = mod.state_dict()
     for k in g.files:
