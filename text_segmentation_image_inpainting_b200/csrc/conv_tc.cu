@@ -54,6 +54,7 @@ struct TcParams {
     int n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil, ho, wo;
     int m_total;              // GEMM M
     int nparts, no_guard, rowpack;
+    int hg;                   // row-halo mode: input pixels staged per group of 8 output pixels = 8 + (kw-1)*dil
     int ktap;                 // K extent of one tap (sum of part kext); rowpack: 64 per kernel row
     int ncols;                // GEMM N extent covered by the grid (multiple of BLOCK_N)
     TcPart parts[TC_MAX_PARTS];
@@ -65,6 +66,75 @@ struct TcParams {
 };
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
+
+// -------------------------------------------------------------------------------------------------
+// epilogue shared by the forward / dgrad kernels: TMEM -> registers -> renormalise / mask -> bf16 NHWC
+// -------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int MODE>
+__device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_base, int warp, int lane, int m0, int n0) {
+                ptx::tc_fence_after();
+                const int row = warp * 32 + lane;
+                const int m = m0 + row;
+                const bool rvalid = m < P.m_total;
+                float inv = 0.f;
+                bool hole = false;
+                if (MODE == 0 && rvalid) {
+                    const float s = P.msum[m];
+                    hole = (s == 0.f) && !P.no_guard;
+                    inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
+                }
+                int en = 0, eh = 0, ew = 0;
+                if (MODE == 1 && rvalid) {
+                    en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
+                }
+    #pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+                    ptx::tmem_ld_wait();
+                    const int col = n0 + c0;
+                    bf16 *orow = nullptr;
+                    int nstore = 0;                      // channels to store from this 32-column chunk (multiple of 8)
+                    float scale = inv;
+                    if (MODE == 0) {
+                        if (rvalid && col < P.y_cstride) { orow = P.y + static_cast<long long>(m) * P.y_cstride + col; nstore = min(32, P.y_cstride - col); }
+                    } else {
+                        scale = 1.f;
+                        for (int p = 0; p < P.nparts; ++p) {
+                            const TcPart &pt = P.parts[p];
+                            const int local = col - pt.koff;
+                            if (local >= 0 && local < pt.kext && pt.dx != nullptr && local < pt.c8 && rvalid) {
+                                orow = pt.dx + static_cast<long long>(m) * pt.dx_cstride + local;
+                                nstore = min(32, pt.c8 - local);
+                                if (pt.mask != nullptr)          // dx = acc * input mask of this part
+                                    scale = pt.mask[(static_cast<long long>(en) * (P.h >> pt.mup) + (eh >> pt.mup)) * (P.w >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
+                            }
+                        }
+                    }
+                    if (nstore > 0) {
+                        uint4 o[4];
+                        __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(o);
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+                            if (MODE == 0) {
+                                const int co = col + 2 * j;
+                                const float b0 = (P.bias && co < P.cout) ? P.bias[co] : 0.f;
+                                const float b1 = (P.bias && co + 1 < P.cout) ? P.bias[co + 1] : 0.f;
+                                a = (hole || co >= P.cout) ? 0.f : a * scale + b0;
+                                b = (hole || co + 1 >= P.cout) ? 0.f : b * scale + b1;
+                            } else {
+                                a *= scale; b *= scale;
+                            }
+                            ob[j] = __floats2bfloat162_rn(a, b);
+                        }
+                        uint4 *dst = reinterpret_cast<uint4 *>(orow);
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 8 < nstore) dst[j] = o[j];
+                    }
+                }
+}
 
 // -------------------------------------------------------------------------------------------------
 // forward (MODE 0) / dgrad (MODE 1)
@@ -221,70 +291,7 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
         ptx::cp_async_wait<0>();
 
         // =========================== epilogue ===========================
-        if (!dead && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 102)) {
-            ptx::tc_fence_after();
-            const int row = warp * 32 + lane;
-            const int m = m0 + row;
-            const bool rvalid = m < P.m_total;
-            float inv = 0.f;
-            bool hole = false;
-            if (MODE == 0 && rvalid) {
-                const float s = P.msum[m];
-                hole = (s == 0.f) && !P.no_guard;
-                inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
-            }
-            int en = 0, eh = 0, ew = 0;
-            if (MODE == 1 && rvalid) {
-                en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
-            }
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
-                ptx::tmem_ld_wait();
-                const int col = n0 + c0;
-                bf16 *orow = nullptr;
-                int nstore = 0;                      // channels to store from this 32-column chunk (multiple of 8)
-                float scale = inv;
-                if (MODE == 0) {
-                    if (rvalid && col < P.y_cstride) { orow = P.y + static_cast<long long>(m) * P.y_cstride + col; nstore = min(32, P.y_cstride - col); }
-                } else {
-                    scale = 1.f;
-                    for (int p = 0; p < P.nparts; ++p) {
-                        const TcPart &pt = P.parts[p];
-                        const int local = col - pt.koff;
-                        if (local >= 0 && local < pt.kext && pt.dx != nullptr && local < pt.c8 && rvalid) {
-                            orow = pt.dx + static_cast<long long>(m) * pt.dx_cstride + local;
-                            nstore = min(32, pt.c8 - local);
-                            if (pt.mask != nullptr)          // dx = acc * input mask of this part
-                                scale = pt.mask[(static_cast<long long>(en) * (P.h >> pt.mup) + (eh >> pt.mup)) * (P.w >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
-                        }
-                    }
-                }
-                if (nstore > 0) {
-                    uint4 o[4];
-                    __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(o);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
-                        if (MODE == 0) {
-                            const int co = col + 2 * j;
-                            const float b0 = (P.bias && co < P.cout) ? P.bias[co] : 0.f;
-                            const float b1 = (P.bias && co + 1 < P.cout) ? P.bias[co + 1] : 0.f;
-                            a = (hole || co >= P.cout) ? 0.f : a * scale + b0;
-                            b = (hole || co + 1 >= P.cout) ? 0.f : b * scale + b1;
-                        } else {
-                            a *= scale; b *= scale;
-                        }
-                        ob[j] = __floats2bfloat162_rn(a, b);
-                    }
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j * 8 < nstore) dst[j] = o[j];
-                }
-            }
-        }
+        if (!dead && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 102)) tc_epilogue<BLOCK_N, MODE>(P, tmem_base, warp, lane, m0, n0);
     } else if (warp == 4) {
         // =========================== B producer: TMA weight tiles ===========================
         if (lane == 0) {
@@ -314,6 +321,208 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
                 for (int k = 0; k < BLOCK_K / 16; ++k)       // +32 bytes per K=16 step inside the swizzle row
                     ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                 ptx::umma_commit(bar_empty + 8 * s);
+            }
+            if (!dead) ptx::umma_commit(bar_tmem_full);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<BLOCK_N>(tmem_base);
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// forward / dgrad, ROW-HALO variant for stride-1 convolutions.
+// The per-tap gather above re-reads every input pixel kh*kw times from L2.  Here each group of 8 consecutive output
+// pixels stages its 8 + (kw-1)*dil input pixels of ONE kernel row once ("halo"), in the canonical NO-SWIZZLE
+// K-major layout  addr(slot, chunk) = chunk * LBO + slot * 16  (8 slots x 16 B = one contiguous core matrix),
+// and the kw taps of that row are kw UMMA descriptors whose start address is shifted by tap*dil slots with a
+// uniform stride-byte-offset of HG*16 between the 8-row groups.  kw x fewer gathers and address computations;
+// the weight tiles still arrive per tap by TMA (SWIZZLE_128B) through their own mbarrier ring.
+// -------------------------------------------------------------------------------------------------
+constexpr int HALO_MAX_HG = 12;
+constexpr int HALO_SA = 2;                                               // halo stages
+constexpr int HALO_A_STAGE = 8 * 16 * (16 * HALO_MAX_HG + 1);            // 8 chunks x LBO_max
+
+template <int BLOCK_N, int SB, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w) {
+    constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
+    if (MODE == 1) {
+        bool any = false;
+        for (int p = 0; p < P.nparts; ++p)
+            if (P.parts[p].dx && n0 < P.parts[p].koff + P.parts[p].kext && n0 + BLOCK_N > P.parts[p].koff) any = true;
+        if (!any) return;
+    }
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
+    const uint32_t sB = smem_base;                                        // 1024-aligned swizzled weight tiles
+    const uint32_t sA = sB + SB * B_STAGE_BYTES;                          // halo stages (16-byte alignment suffices)
+    const uint32_t sBar = sA + HALO_SA * HALO_A_STAGE;
+    const uint32_t bar_full_a = sBar, bar_empty_a = sBar + 8 * HALO_SA;
+    const uint32_t bar_full_b = sBar + 16 * HALO_SA, bar_empty_b = bar_full_b + 8 * SB;
+    const uint32_t bar_tmem_full = bar_empty_b + 8 * SB;
+    const uint32_t s_tmem_ptr = bar_tmem_full + 8;
+    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HG = P.hg;
+    const uint32_t LBO = 16u * (16u * HG + 1u);
+    const int np = (MODE == 0) ? P.nparts : 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HALO_SA; ++s) { ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS); ptx::mbar_init(bar_empty_a + 8 * s, 1); }
+        for (int s = 0; s < SB; ++s) { ptx::mbar_init(bar_full_b + 8 * s, 1); ptx::mbar_init(bar_empty_b + 8 * s, 1); }
+        ptx::mbar_init(bar_tmem_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tmap_w);
+    if (warp == 5) {
+        ptx::tmem_alloc<BLOCK_N>(s_tmem_ptr);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    if (warp < 4) {
+        // =========================== halo producers ===========================
+        const int t = threadIdx.x;
+        const int chunk = t & 7, r0 = t >> 3;
+        int pn[HALO_MAX_HG], ph[HALO_MAX_HG], pc[HALO_MAX_HG];
+        uint32_t vb[TC_MAX_PARTS][HALO_MAX_HG];          // fwd: bit tr = slot valid (bounds + hole) for kernel row tr
+        const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
+        const int pwid = (MODE == 0) ? P.wo : P.w;
+#pragma unroll
+        for (int i = 0; i < HALO_MAX_HG; ++i) {
+            pn[i] = 0; ph[i] = 0; pc[i] = -1000000;
+#pragma unroll
+            for (int p = 0; p < TC_MAX_PARTS; ++p) vb[p][i] = 0;
+            if (i >= HG) continue;
+            const int S = r0 + 16 * i;
+            const int g = S / HG, sl = S - g * HG;
+            const int m = m0 + g * 8;                   // first pixel of the group (groups never straddle image rows)
+            const bool ok = m < P.m_total;
+            const int mm = ok ? m : 0;
+            const int nn = mm / plane, rem = mm - nn * plane;
+            const int hh = rem / pwid, ww = rem - hh * pwid;
+            pn[i] = nn;
+            if (MODE == 0) {
+                ph[i] = hh - P.pad_h;
+                pc[i] = ww - P.pad_w + sl;
+                // the (pixel j of the group, tap column tc) pair that looks at this slot: sl == j + tc*dil
+                const int tcs = sl > 7 ? (sl - 7 + P.dil - 1) / P.dil : 0;
+                const int j = sl - tcs * P.dil;
+                if (ok) {
+#pragma unroll
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                        if (p >= P.nparts) break;
+                        const uint64_t word = __ldg(P.parts[p].tapmask + m + j);
+                        uint32_t bits = 0;
+                        for (int tr = 0; tr < P.kh; ++tr) bits |= static_cast<uint32_t>((word >> (tr * P.kw + tcs)) & 1ull) << tr;
+                        vb[p][i] = bits;
+                    }
+                }
+            } else {
+                ph[i] = hh + P.pad_h;
+                pc[i] = ok ? (ww + P.pad_w - (P.kw - 1) * P.dil + sl) : -1000000;
+            }
+        }
+
+        int it = 0;
+        bool dead = false;
+        for (int tr = 0; tr < P.kh && !dead; ++tr) {
+#pragma unroll
+            for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                if (p >= np || dead) break;
+                const TcPart &pt = P.parts[p];
+                const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
+                const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
+                for (int cb = 0; cb < nb; ++cb, ++it) {
+                    const int s = it % HALO_SA;
+                    const uint32_t parity = ((it / HALO_SA) & 1) ^ 1;
+                    if (!ptx::mbar_wait(bar_empty_a + 8 * s, parity, P.abort_flag, 111)) { dead = true; break; }
+                    const bool cv = cb * BLOCK_K + chunk * 8 < c8;
+                    const uint32_t dst0 = sA + s * HALO_A_STAGE + chunk * LBO + r0 * 16;
+#pragma unroll
+                    for (int i = 0; i < HALO_MAX_HG; ++i) {
+                        if (i >= HG) break;
+                        bool v;
+                        const bf16 *src;
+                        if (MODE == 0) {
+                            v = cv && ((vb[p][i] >> tr) & 1u);
+                            const int hi = (ph[i] + tr * P.dil) >> pt.xup, wi = pc[i] >> pt.xup;
+                            const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
+                            src = pt.x + (static_cast<long long>(pn[i] * hp + (v ? hi : 0)) * wp + (v ? wi : 0)) * pt.cstride + (v ? cb * BLOCK_K + chunk * 8 : 0);
+                        } else {
+                            const int hi = ph[i] - tr * P.dil, wi = pc[i];
+                            v = cv && hi >= 0 && hi < P.ho && wi >= 0 && wi < P.wo;
+                            src = P.dc + (static_cast<long long>(pn[i] * P.ho + (v ? hi : 0)) * P.wo + (v ? wi : 0)) * P.dc_cstride + (v ? cb * BLOCK_K + chunk * 8 : 0);
+                        }
+                        ptx::cp_async_16(dst0 + i * 256, src, v);             // slot S = r0 + 16*i  ->  +16*i slots = +256 bytes
+                    }
+                    ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
+                    ptx::mbar_arrive(bar_full_a + 8 * s);
+                }
+            }
+        }
+        ptx::cp_async_wait<0>();
+        if (!dead && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 112)) tc_epilogue<BLOCK_N, MODE>(P, tmem_base, warp, lane, m0, n0);
+    } else if (warp == 4) {
+        // =========================== weight tiles: one per (kernel row, part, channel block, tap column) ===========================
+        if (lane == 0) {
+            int itb = 0;
+            bool dead = false;
+            for (int tr = 0; tr < P.kh && !dead; ++tr)
+                for (int p = 0; p < np && !dead; ++p) {
+                    const int nb = ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
+                    for (int cb = 0; cb < nb && !dead; ++cb)
+                        for (int tc = 0; tc < P.kw; ++tc, ++itb) {
+                            const int s = itb % SB;
+                            const uint32_t parity = ((itb / SB) & 1) ^ 1;
+                            if (!ptx::mbar_wait(bar_empty_b + 8 * s, parity, P.abort_flag, 113)) { dead = true; break; }
+                            const int tap = tr * P.kw + tc;
+                            const int kidx = (MODE == 0) ? tap * P.ktap + P.parts[p].koff + cb * BLOCK_K : tap * P.dc_kext + cb * BLOCK_K;
+                            ptx::mbar_arrive_expect_tx(bar_full_b + 8 * s, B_STAGE_BYTES);
+                            ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &tmap_w, kidx, n0, bar_full_b + 8 * s);
+                        }
+                }
+        }
+    } else {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            int num_a = 0;
+            for (int p = 0; p < np; ++p) num_a += ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
+            num_a *= P.kh;
+            int itb = 0;
+            bool dead = false;
+            for (int ita = 0; ita < num_a && !dead; ++ita) {
+                const int sa = ita % HALO_SA;
+                if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / HALO_SA) & 1, P.abort_flag, 114)) { dead = true; break; }
+                ptx::fence_proxy_async_smem();
+                for (int tc = 0; tc < P.kw; ++tc, ++itb) {
+                    const int sb = itb % SB;
+                    if (!ptx::mbar_wait(bar_full_b + 8 * sb, (itb / SB) & 1, P.abort_flag, 115)) { dead = true; break; }
+                    ptx::tc_fence_after();
+                    const int shift = ((MODE == 0) ? tc : (P.kw - 1 - tc)) * P.dil;        // slots
+                    const uint32_t a0 = sA + sa * HALO_A_STAGE + shift * 16;
+                    const uint64_t db = ptx::make_smem_desc(sB + sb * B_STAGE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {                                // 2 chunks (16 channels) per MMA
+                        const uint64_t da = ptx::make_smem_desc_noswizzle(a0 + k * 2 * LBO, LBO, HG * 16);
+                        ptx::umma_bf16(tmem_base, da, db + 2 * k, idesc, (ita | tc | k) != 0);
+                    }
+                    ptx::umma_commit(bar_empty_b + 8 * sb);
+                }
+                ptx::umma_commit(bar_empty_a + 8 * sa);
             }
             if (!dead) ptx::umma_commit(bar_tmem_full);
         }
@@ -741,6 +950,30 @@ void base_params(TcParams &P, const pcb_conv *c, const Layout &L) {
     P.nparts = c->nparts; P.no_guard = c->no_guard; P.rowpack = L.rowpack; P.ktap = L.ktap;
 }
 
+// row-halo eligibility: stride 1, output rows made of whole groups of 8 pixels, halo small enough
+int halo_hg(const pcb_conv *c, bool rowpack) {
+    if (rowpack || c->stride != 1 || getenv("PCB_DISABLE_HALO")) return 0;
+    const int hg = 8 + (c->kw - 1) * c->dil;
+    if (c->kw < 2 || hg > HALO_MAX_HG || c->kh > 8) return 0;
+    if (c->wo % 8 != 0 || c->w % 8 != 0 || c->wo != c->w) return 0;
+    return hg;
+}
+
+template <int BLOCK_N, int SB, int MODE>
+int launch_halo(const TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
+    constexpr size_t smem = 1024 + SB * BLOCK_N * 128 + HALO_SA * HALO_A_STAGE + 16 * HALO_SA + 16 * SB + 16 + 16;
+    auto kern = pconv_tc_halo_kernel<BLOCK_N, SB, MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(P.ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
+    kern<<<grid, TC_THREADS, smem, st>>>(P, tm);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int BLOCK_N, int STAGES, int MODE>
 int launch_fwd(const TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     constexpr size_t smem = 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
@@ -808,6 +1041,8 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     P.ncols = L.rows_f;
     CUtensorMap tm;
     if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
+    P.hg = halo_hg(c, L.rowpack);
+    if (P.hg) return (L.bn_f == 128) ? launch_halo<128, 3, 0>(P, tm, st) : launch_halo<64, 4, 0>(P, tm, st);
     if (L.bn_f == 128) return launch_fwd<128, 3, 0>(P, tm, st);
     return launch_fwd<64, 4, 0>(P, tm, st);
 }
@@ -838,6 +1073,8 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     P.ncols = L.ktap;
     CUtensorMap tm;
     if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
+    P.hg = halo_hg(c, L.rowpack);
+    if (P.hg) return (bn == 128) ? launch_halo<128, 3, 1>(P, tm, st) : launch_halo<64, 4, 1>(P, tm, st);
     if (bn == 128) return launch_fwd<128, 3, 1>(P, tm, st);
     return launch_fwd<64, 4, 1>(P, tm, st);
 }

@@ -290,6 +290,47 @@ __global__ void renorm_bwd_kernel(const T *__restrict__ dy, int dys, const float
         for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, s_db[i]);
 }
 
+// vector path of the renormalisation backward: 8 channels per thread, rows strided like bn_stats (one msum load per row,
+// bias-gradient partials block-reduced through shared memory).  Requires c % 8 == 0, dense pitch multiple of 8, mg == 1.
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) renorm_bwd_vec_kernel(const T *__restrict__ dy, int dys, const float *__restrict__ msum, long long count,
+                                                                    int c, int no_guard, T *__restrict__ dc, int dcs, float *dbias) {
+    __shared__ float s_red[EW_THREADS][8];
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (r < rpb) {
+        for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
+            const float s = msum[row];
+            float g[8], d[8];
+            Vec8<T>::load(dy + row * dys + v * 8, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (no_guard) { d[j] = g[j] / s; acc[j] += (d[j] - d[j]) + g[j]; }
+                else { const bool hole = (s == 0.f); d[j] = hole ? 0.f : g[j] / s; acc[j] += hole ? 0.f : g[j]; }
+            }
+            Vec8<T>::store(dc + row * dcs + v * 8, d);
+        }
+    }
+    if (dbias) {
+        if (r < rpb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_red[threadIdx.x][j] = acc[j];
+        }
+        __syncthreads();
+        if (r == 0 && v < cv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float tot = 0.f;
+                for (int rr = 0; rr < rpb; ++rr) tot += s_red[rr * cv + v][j];
+                atomicAdd(dbias + v * 8 + j, tot);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // concat (+ nearest 2x upsample) forward / backward
 // ---------------------------------------------------------------------------------------------
@@ -523,6 +564,14 @@ extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(
     const long long count = static_cast<long long>(c->n) * c->ho * c->wo;
     const int mg = (c->groups > 1 && !c->same_holes) ? c->groups : 1;
     if (dbias) PCB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, ST));
+    if (mg == 1 && c->cout % 8 == 0 && c->cout <= 2048 && dc_cstride == c->cout && dy_cstride % 8 == 0) {
+        const int rpb = EW_THREADS / (c->cout / 8);
+        const int vgrid = ew_grid(count, rpb * 8);
+        if (c->dtype == PCB_BF16) renorm_bwd_vec_kernel<bf16><<<vgrid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(dy), dy_cstride, msum, count, c->cout, c->no_guard, static_cast<bf16 *>(dc), dc_cstride, dbias);
+        else renorm_bwd_vec_kernel<float><<<vgrid, EW_THREADS, 0, ST>>>(static_cast<const float *>(dy), dy_cstride, msum, count, c->cout, c->no_guard, static_cast<float *>(dc), dc_cstride, dbias);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     const int grid = ew_grid(count * dc_cstride, EW_THREADS * 8);
     const size_t smem = sizeof(float) * c->cout;
     if (c->dtype == PCB_BF16) renorm_bwd_kernel<bf16><<<grid, EW_THREADS, smem, ST>>>(static_cast<const bf16 *>(dy), dy_cstride, msum, count, c->cout, mg, c->no_guard, static_cast<bf16 *>(dc), dc_cstride, dbias);

@@ -141,6 +141,17 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
     d |= 2ull << 61;     // SWIZZLE_128B
     return d;
 }
+// Same, layout type 0 (no swizzle, "interleave"): core matrices are 8 rows x 16 bytes stored contiguously (128 B).
+//   K-major : LBO = byte distance between the two 8-element K chunks of one MMA, SBO = distance between 8-row groups.
+//   MN-major: SBO = byte distance between 8-element M/N chunks,                 LBO = distance between 8-row K groups.
+__host__ __device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;     // descriptor version (Blackwell)
+    return d;
+}
 // Instruction descriptor (32-bit) for kind::f16: bf16 A/B, fp32 accumulate.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N>>3  [24,29) M>>4
