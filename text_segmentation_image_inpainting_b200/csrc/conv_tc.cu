@@ -55,6 +55,7 @@ struct TcParams {
     int m_total;              // GEMM M
     int nparts, no_guard, rowpack;
     int hg;                   // row-halo mode: input pixels staged per group of 8 output pixels = 8 + (kw-1)*dil
+    int halo_sa;              // row-halo mode: number of halo stages (2 or 3, smem permitting)
     int ktap;                 // K extent of one tap (sum of part kext); rowpack: 64 per kernel row
     int ncols;                // GEMM N extent covered by the grid (multiple of BLOCK_N)
     TcPart parts[TC_MAX_PARTS];
@@ -188,15 +189,20 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
 
     if (warp < 4) {
         // =========================== A producers: im2col gather ===========================
+        // All address arithmetic is 32-bit element offsets (host guarantees every source tensor < 2^31 elements):
+        // per tile each row keeps its image base per part; per (tap, part) a handful of integer ops per row; per
+        // K block one add + one cp.async per row.
         const int t = threadIdx.x;
         const int chunk = t & 7;                    // 16-byte chunk inside the 128-byte row
         const int r0 = t >> 3;                      // rows r0 + 16*i
         const uint32_t sw = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);   // (r & 7) == (r0 & 7) for all i
 
-        int pn[8], ph[8], pw[8];                    // per-row pixel coordinates (pre-scaled)
+        int ph[8], pw[8];                           // per-row pixel coordinates (pre-scaled)
+        int ibase[TC_MAX_PARTS][8];                 // element offset of the row's image inside each source (+ chunk)
         bool prow[8];
         const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
         const int pwid = (MODE == 0) ? P.wo : P.w;
+        const int ls = 31 - __clz(P.stride);        // dgrad: stride is a power of two on this path (host-checked)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = m0 + r0 + 16 * i;
@@ -204,9 +210,15 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
             const int mm = prow[i] ? m : 0;
             const int nn = mm / plane, rem = mm - nn * plane;
             const int hh = rem / pwid, ww = rem - hh * pwid;
-            pn[i] = nn;
-            if (MODE == 0) { ph[i] = hh * P.stride - P.pad_h; pw[i] = ww * P.stride - P.pad_w; }
-            else           { ph[i] = hh + P.pad_h;            pw[i] = ww + P.pad_w; }
+            if (MODE == 0) {
+                ph[i] = hh * P.stride - P.pad_h; pw[i] = ww * P.stride - P.pad_w;
+#pragma unroll
+                for (int p = 0; p < TC_MAX_PARTS; ++p)
+                    ibase[p][i] = (p < P.nparts) ? nn * (P.h >> P.parts[p].xup) * (P.w >> P.parts[p].xup) * P.parts[p].cstride + chunk * 8 : 0;
+            } else {
+                ph[i] = hh + P.pad_h; pw[i] = ww + P.pad_w;
+                ibase[0][i] = nn * P.ho * P.wo * P.dc_cstride + chunk * 8;
+            }
         }
 
         // per-row tap-validity bits (bounds + holes), loaded once per tile: the k-loop issues no mask loads
@@ -221,13 +233,13 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
 
         int kb = 0;
         bool dead = false;
-        auto push = [&](const bf16 *const (&src)[8], const bool (&ok)[8]) -> bool {
+        auto push = [&](const bf16 *base, const int (&off)[8], const bool (&ok)[8]) -> bool {
             const int s = kb % STAGES;
             const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
             if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 101)) return false;
             const uint32_t dst = sA + s * A_STAGE_BYTES + r0 * 128 + sw;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), src[i], ok[i]);
+            for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), base + off[i], ok[i]);
             ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
             ptx::mbar_arrive(bar_full_a + 8 * s);
             ++kb;
@@ -237,17 +249,17 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
         if (MODE == 0 && P.rowpack) {
             // ---- small-Cin mode: K block = kernel row `tr`; chunk = tap column; source pixel shifts with the chunk
             const TcPart &pt = P.parts[0];
+            const int cs = pt.cstride, rowpitch = P.w * cs;
             for (int tr = 0; tr < P.kh && !dead; ++tr) {
-                const bf16 *src[8];
+                int off[8];
                 bool ok[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool v = (chunk < P.kw) && ((tmv[0][i] >> (tr * P.kw + chunk)) & 1ull);
-                    const int hi = ph[i] + tr * P.dil, wi = pw[i] + chunk * P.dil;
-                    src[i] = pt.x + (static_cast<long long>(pn[i] * P.h + (v ? hi : 0)) * P.w + (v ? wi : 0)) * pt.cstride;
+                    off[i] = v ? (ibase[0][i] - chunk * 8) + (ph[i] + tr * P.dil) * rowpitch + (pw[i] + chunk * P.dil) * cs : 0;
                     ok[i] = v;
                 }
-                if (!push(src, ok)) dead = true;
+                if (!push(pt.x, off, ok)) dead = true;
             }
         } else {
             for (int tap = 0; tap < taps && !dead; ++tap) {
@@ -257,33 +269,36 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
                 for (int p = 0; p < TC_MAX_PARTS; ++p) {
                     if (p >= np || dead) break;
                     const TcPart &pt = P.parts[p];
-                    const bf16 *base[8];
+                    const bf16 *src = (MODE == 0) ? pt.x : P.dc;
+                    const int cs = (MODE == 0) ? pt.cstride : P.dc_cstride;
+                    const int xup = (MODE == 0) ? pt.xup : 0;
+                    const int rowpitch = ((MODE == 0) ? (P.w >> xup) : P.wo) * cs;
+                    int base[8];
                     bool rv[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         bool v;
+                        int hi, wi;
                         if (MODE == 0) {
                             v = (tmv[p][i] >> tap) & 1ull;                  // bounds + hole (0 for rows past m_total)
-                            const int hi = (ph[i] + tr * P.dil) >> pt.xup, wi = (pw[i] + tc * P.dil) >> pt.xup;
-                            const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
-                            base[i] = pt.x + (static_cast<long long>(pn[i] * hp + (v ? hi : 0)) * wp + (v ? wi : 0)) * pt.cstride + chunk * 8;
+                            hi = (ph[i] + tr * P.dil) >> xup; wi = (pw[i] + tc * P.dil) >> xup;
                         } else {
                             const int th = ph[i] - tr * P.dil, tw = pw[i] - tc * P.dil;
-                            const int hi = th / P.stride, wi = tw / P.stride;
-                            v = prow[i] && th >= 0 && tw >= 0 && (hi * P.stride == th) && (wi * P.stride == tw) && hi < P.ho && wi < P.wo;
-                            base[i] = P.dc + (static_cast<long long>(pn[i] * P.ho + (v ? hi : 0)) * P.wo + (v ? wi : 0)) * P.dc_cstride + chunk * 8;
+                            hi = th >> ls; wi = tw >> ls;
+                            v = prow[i] && th >= 0 && tw >= 0 && ((th | tw) & (P.stride - 1)) == 0 && hi < P.ho && wi < P.wo;
                         }
+                        base[i] = v ? ibase[(MODE == 0) ? p : 0][i] + hi * rowpitch + wi * cs : 0;
                         rv[i] = v;
                     }
                     const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
                     const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
                     for (int cb = 0; cb < nb; ++cb) {
                         const bool cv = cb * BLOCK_K + chunk * 8 < c8;       // channel padding of the part: zero-fill
-                        const bf16 *src[8];
+                        int off[8];
                         bool ok[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { src[i] = base[i] + (cv ? cb * BLOCK_K : 0); ok[i] = rv[i] && cv; }
-                        if (!push(src, ok)) { dead = true; break; }
+                        for (int i = 0; i < 8; ++i) { ok[i] = rv[i] && cv; off[i] = ok[i] ? base[i] + cb * BLOCK_K : 0; }
+                        if (!push(src, off, ok)) { dead = true; break; }
                     }
                 }
             }
@@ -345,8 +360,7 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
 // the weight tiles still arrive per tap by TMA (SWIZZLE_128B) through their own mbarrier ring.
 // -------------------------------------------------------------------------------------------------
 constexpr int HALO_MAX_HG = 12;
-constexpr int HALO_SA = 2;                                               // halo stages
-constexpr int HALO_A_STAGE = 8 * 16 * (16 * HALO_MAX_HG + 1);            // 8 chunks x LBO_max
+constexpr int HALO_SA_MAX = 3;                                           // halo stages (runtime: 2 or 3)
 
 template <int BLOCK_N, int SB, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -363,21 +377,22 @@ pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
     const uint32_t sB = smem_base;                                        // 1024-aligned swizzled weight tiles
+    const int HG = P.hg;
+    const uint32_t LBO = 16u * (16u * HG + 1u);
+    const uint32_t A_STAGE = 8u * LBO;                                    // 8 chunks
     const uint32_t sA = sB + SB * B_STAGE_BYTES;                          // halo stages (16-byte alignment suffices)
-    const uint32_t sBar = sA + HALO_SA * HALO_A_STAGE;
-    const uint32_t bar_full_a = sBar, bar_empty_a = sBar + 8 * HALO_SA;
-    const uint32_t bar_full_b = sBar + 16 * HALO_SA, bar_empty_b = bar_full_b + 8 * SB;
+    const uint32_t sBar = (sA + HALO_SA_MAX * A_STAGE + 15u) & ~15u;
+    const uint32_t bar_full_a = sBar, bar_empty_a = sBar + 8 * HALO_SA_MAX;
+    const uint32_t bar_full_b = sBar + 16 * HALO_SA_MAX, bar_empty_b = bar_full_b + 8 * SB;
     const uint32_t bar_tmem_full = bar_empty_b + 8 * SB;
     const uint32_t s_tmem_ptr = bar_tmem_full + 8;
     uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int HG = P.hg;
-    const uint32_t LBO = 16u * (16u * HG + 1u);
     const int np = (MODE == 0) ? P.nparts : 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < HALO_SA; ++s) { ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS); ptx::mbar_init(bar_empty_a + 8 * s, 1); }
+        for (int s = 0; s < HALO_SA_MAX; ++s) { ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS); ptx::mbar_init(bar_empty_a + 8 * s, 1); }
         for (int s = 0; s < SB; ++s) { ptx::mbar_init(bar_full_b + 8 * s, 1); ptx::mbar_init(bar_empty_b + 8 * s, 1); }
         ptx::mbar_init(bar_tmem_full, 1);
         ptx::fence_mbar_init();
@@ -394,17 +409,20 @@ pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__
 
     if (warp < 4) {
         // =========================== halo producers ===========================
+        // 32-bit element offsets; per tile each slot keeps (image base + column term) per part, its row coordinate and its
+        // per-kernel-row validity bits; per halo item: one shift/multiply/add + predicate + cp.async per slot.
         const int t = threadIdx.x;
         const int chunk = t & 7, r0 = t >> 3;
-        int pn[HALO_MAX_HG], ph[HALO_MAX_HG], pc[HALO_MAX_HG];
-        uint32_t vb[TC_MAX_PARTS][HALO_MAX_HG];          // fwd: bit tr = slot valid (bounds + hole) for kernel row tr
+        int ph[HALO_MAX_HG];                              // row coordinate of the slot at kernel row 0
+        int cterm[TC_MAX_PARTS][HALO_MAX_HG];             // image base + column * cstride + chunk*8 (element offset)
+        uint32_t vb[TC_MAX_PARTS][HALO_MAX_HG];           // bit tr = slot valid (bounds [+ hole]) for kernel row tr
         const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
         const int pwid = (MODE == 0) ? P.wo : P.w;
 #pragma unroll
         for (int i = 0; i < HALO_MAX_HG; ++i) {
-            pn[i] = 0; ph[i] = 0; pc[i] = -1000000;
+            ph[i] = 0;
 #pragma unroll
-            for (int p = 0; p < TC_MAX_PARTS; ++p) vb[p][i] = 0;
+            for (int p = 0; p < TC_MAX_PARTS; ++p) { vb[p][i] = 0; cterm[p][i] = 0; }
             if (i >= HG) continue;
             const int S = r0 + 16 * i;
             const int g = S / HG, sl = S - g * HG;
@@ -413,26 +431,31 @@ pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__
             const int mm = ok ? m : 0;
             const int nn = mm / plane, rem = mm - nn * plane;
             const int hh = rem / pwid, ww = rem - hh * pwid;
-            pn[i] = nn;
             if (MODE == 0) {
                 ph[i] = hh - P.pad_h;
-                pc[i] = ww - P.pad_w + sl;
+                const int col = ww - P.pad_w + sl;
                 // the (pixel j of the group, tap column tc) pair that looks at this slot: sl == j + tc*dil
                 const int tcs = sl > 7 ? (sl - 7 + P.dil - 1) / P.dil : 0;
                 const int j = sl - tcs * P.dil;
-                if (ok) {
 #pragma unroll
-                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                        if (p >= P.nparts) break;
-                        const uint64_t word = __ldg(P.parts[p].tapmask + m + j);
-                        uint32_t bits = 0;
-                        for (int tr = 0; tr < P.kh; ++tr) bits |= static_cast<uint32_t>((word >> (tr * P.kw + tcs)) & 1ull) << tr;
-                        vb[p][i] = bits;
-                    }
+                for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                    if (p >= P.nparts || !ok) continue;
+                    const TcPart &pt = P.parts[p];
+                    const uint64_t word = __ldg(pt.tapmask + m + j);
+                    uint32_t bits = 0;
+                    for (int tr = 0; tr < P.kh; ++tr) bits |= static_cast<uint32_t>((word >> (tr * P.kw + tcs)) & 1ull) << tr;
+                    vb[p][i] = bits;
+                    const int colc = min(max(col, 0), P.w - 1) >> pt.xup;       // clamped: only dereferenced when valid
+                    cterm[p][i] = (nn * (P.h >> pt.xup) * (P.w >> pt.xup) + colc) * pt.cstride + chunk * 8;
                 }
             } else {
                 ph[i] = hh + P.pad_h;
-                pc[i] = ok ? (ww + P.pad_w - (P.kw - 1) * P.dil + sl) : -1000000;
+                const int col = ww + P.pad_w - (P.kw - 1) * P.dil + sl;
+                const bool cok = ok && col >= 0 && col < P.wo;
+                uint32_t bits = 0;
+                for (int tr = 0; tr < P.kh; ++tr) { const int hi = ph[i] - tr * P.dil; bits |= (cok && hi >= 0 && hi < P.ho ? 1u : 0u) << tr; }
+                vb[0][i] = bits;
+                cterm[0][i] = (nn * P.ho * P.wo + min(max(col, 0), P.wo - 1)) * P.dc_cstride + chunk * 8;
             }
         }
 
@@ -443,30 +466,29 @@ pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__
             for (int p = 0; p < TC_MAX_PARTS; ++p) {
                 if (p >= np || dead) break;
                 const TcPart &pt = P.parts[p];
+                const bf16 *src = (MODE == 0) ? pt.x : P.dc;
+                const int xup = (MODE == 0) ? pt.xup : 0;
+                const int hmax = ((MODE == 0) ? (P.h >> xup) : P.ho) - 1;
+                const int rowpitch = (MODE == 0) ? (P.w >> xup) * pt.cstride : P.wo * P.dc_cstride;
                 const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
                 const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
+                int rterm[HALO_MAX_HG];
+#pragma unroll
+                for (int i = 0; i < HALO_MAX_HG; ++i) {
+                    const int hi = (MODE == 0) ? ((ph[i] + tr * P.dil) >> xup) : (ph[i] - tr * P.dil);
+                    rterm[i] = cterm[p][i] + min(max(hi, 0), hmax) * rowpitch;
+                }
                 for (int cb = 0; cb < nb; ++cb, ++it) {
-                    const int s = it % HALO_SA;
-                    const uint32_t parity = ((it / HALO_SA) & 1) ^ 1;
+                    const int s = it % P.halo_sa;
+                    const uint32_t parity = ((it / P.halo_sa) & 1) ^ 1;
                     if (!ptx::mbar_wait(bar_empty_a + 8 * s, parity, P.abort_flag, 111)) { dead = true; break; }
                     const bool cv = cb * BLOCK_K + chunk * 8 < c8;
-                    const uint32_t dst0 = sA + s * HALO_A_STAGE + chunk * LBO + r0 * 16;
+                    const uint32_t dst0 = sA + s * A_STAGE + chunk * LBO + r0 * 16;
+                    const bf16 *srcb = src + cb * BLOCK_K;
 #pragma unroll
                     for (int i = 0; i < HALO_MAX_HG; ++i) {
                         if (i >= HG) break;
-                        bool v;
-                        const bf16 *src;
-                        if (MODE == 0) {
-                            v = cv && ((vb[p][i] >> tr) & 1u);
-                            const int hi = (ph[i] + tr * P.dil) >> pt.xup, wi = pc[i] >> pt.xup;
-                            const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
-                            src = pt.x + (static_cast<long long>(pn[i] * hp + (v ? hi : 0)) * wp + (v ? wi : 0)) * pt.cstride + (v ? cb * BLOCK_K + chunk * 8 : 0);
-                        } else {
-                            const int hi = ph[i] - tr * P.dil, wi = pc[i];
-                            v = cv && hi >= 0 && hi < P.ho && wi >= 0 && wi < P.wo;
-                            src = P.dc + (static_cast<long long>(pn[i] * P.ho + (v ? hi : 0)) * P.wo + (v ? wi : 0)) * P.dc_cstride + (v ? cb * BLOCK_K + chunk * 8 : 0);
-                        }
-                        ptx::cp_async_16(dst0 + i * 256, src, v);             // slot S = r0 + 16*i  ->  +16*i slots = +256 bytes
+                        ptx::cp_async_16(dst0 + i * 256, srcb + rterm[i], cv && ((vb[p][i] >> tr) & 1u));   // slot r0 + 16*i
                     }
                     ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
                     ptx::mbar_arrive(bar_full_a + 8 * s);
@@ -505,15 +527,15 @@ pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__
             int itb = 0;
             bool dead = false;
             for (int ita = 0; ita < num_a && !dead; ++ita) {
-                const int sa = ita % HALO_SA;
-                if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / HALO_SA) & 1, P.abort_flag, 114)) { dead = true; break; }
+                const int sa = ita % P.halo_sa;
+                if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / P.halo_sa) & 1, P.abort_flag, 114)) { dead = true; break; }
                 ptx::fence_proxy_async_smem();
                 for (int tc = 0; tc < P.kw; ++tc, ++itb) {
                     const int sb = itb % SB;
                     if (!ptx::mbar_wait(bar_full_b + 8 * sb, (itb / SB) & 1, P.abort_flag, 115)) { dead = true; break; }
                     ptx::tc_fence_after();
                     const int shift = ((MODE == 0) ? tc : (P.kw - 1 - tc)) * P.dil;        // slots
-                    const uint32_t a0 = sA + sa * HALO_A_STAGE + shift * 16;
+                    const uint32_t a0 = sA + sa * A_STAGE + shift * 16;
                     const uint64_t db = ptx::make_smem_desc(sB + sb * B_STAGE_BYTES, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {                                // 2 chunks (16 channels) per MMA
@@ -629,6 +651,25 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
         }
         const int plane = P.ho * P.wo;
         bool dead = false;
+        // per-CTA constants of the gather (32-bit element offsets): tap displacements and per-block source geometry
+        int dtr[T], dtc[T], tbit[T];
+#pragma unroll
+        for (int tl = 0; tl < T; ++tl) {
+            const int tg = tap0 + tl;
+            if (P.rowpack) { dtr[tl] = tg * P.dil; dtc[tl] = chunk * P.dil; tbit[tl] = tg * P.kw + chunk; }
+            else { const int tr = tg / P.kw, tc = tg - tr * P.kw; dtr[tl] = tr * P.dil; dtc[tl] = tc * P.dil; tbit[tl] = tg; }
+        }
+        const bf16 *bsrc[2];
+        int bcs[2], brow[2], bimg[2], bxup[2], boff[2];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            const TcPart &pt = P.parts[blk_part[hb] >= 0 ? blk_part[hb] : 0];
+            bsrc[hb] = pt.x; bcs[hb] = pt.cstride; bxup[hb] = pt.xup;
+            brow[hb] = (P.w >> pt.xup) * pt.cstride;
+            bimg[hb] = (P.h >> pt.xup) * brow[hb];
+            boff[hb] = P.rowpack ? 0 : blk_off[hb] + chunk * 8;
+        }
+        const bool fastrow = P.wo >= 64;
         // tap-validity words are prefetched one k-block ahead so their latency hides behind the barrier wait
         uint64_t tm_next[4][2];
         auto load_tm = [&](int kb, uint64_t (&dst)[4][2]) {
@@ -649,30 +690,32 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i) { tm_cur[i][0] = tm_next[i][0]; tm_cur[i][1] = tm_next[i][1]; }
             if (it + 1 < num_kb) load_tm(kb + 1, tm_next);
+            // coordinates of the k-block's first pixel (two divisions per k-block, not per row)
+            const int mf = kb * 64;
+            const int nf = mf / plane, remf = mf - nf * plane;
+            const int ohf = remf / P.wo, owf = remf - ohf * P.wo;
             if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 201)) { dead = true; break; }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = r0 + 16 * i;
-                const int m = kb * 64 + r;
-                const int mm = m < P.m_total ? m : 0;
-                const int nn = mm / plane, rem = mm - nn * plane;
-                const int oh = rem / P.wo, ow = rem - oh * P.wo;
-                for (int tl = 0; tl < ntap; ++tl) {
-                    const int tg = tap0 + tl;                      // tap (or kernel row in rowpack mode)
-                    int tr, tc, bit;
-                    if (P.rowpack) { tr = tg; tc = chunk; bit = tg * P.kw + chunk; }
-                    else { tr = tg / P.kw; tc = tg - tr * P.kw; bit = tg; }
-                    const int hi = oh * P.stride - P.pad_h + tr * P.dil, wi = ow * P.stride - P.pad_w + tc * P.dil;
+                int nn = nf, oh = ohf, ow = owf + r;
+                if (fastrow) {
+                    if (ow >= P.wo) { ow -= P.wo; if (++oh >= P.ho) { oh = 0; ++nn; } }
+                } else {
+                    const int mm = min(mf + r, P.m_total - 1);
+                    nn = mm / plane; const int rem = mm - nn * plane; oh = rem / P.wo; ow = rem - oh * P.wo;
+                }
+                const int hb0 = oh * P.stride - P.pad_h, wb0 = ow * P.stride - P.pad_w;
+#pragma unroll
+                for (int tl = 0; tl < T; ++tl) {
+                    if (tl >= ntap) break;
+                    const int hi = hb0 + dtr[tl], wi = wb0 + dtc[tl];
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
-                        const bool v = (tm_cur[i][hb] >> bit) & 1ull;   // 0 unless the block/chunk exists
-                        const int p = blk_part[hb] >= 0 ? blk_part[hb] : 0;
-                        const TcPart &pt = P.parts[p];
-                        const int hp = P.h >> pt.xup, wp = P.w >> pt.xup;
-                        const bf16 *src = pt.x + (static_cast<long long>(nn * hp + (v ? (hi >> pt.xup) : 0)) * wp + (v ? (wi >> pt.xup) : 0)) * pt.cstride +
-                                          (P.rowpack ? 0 : (v ? blk_off[hb] + chunk * 8 : 0));
+                        const bool v = (tm_cur[i][hb] >> tbit[tl]) & 1ull;     // 0 unless the block / chunk exists and the tap is valid
+                        const int off = v ? nn * bimg[hb] + (hi >> bxup[hb]) * brow[hb] + (wi >> bxup[hb]) * bcs[hb] + boff[hb] : 0;
                         const uint32_t dst = sA + s * A_STAGE + tl * A_TAP_BYTES + hb * 8192 + r * 128 + sw;
-                        ptx::cp_async_16(dst, src, v);
+                        ptx::cp_async_16(dst, bsrc[hb] + off, v);
                     }
                 }
             }
@@ -874,10 +917,15 @@ bool is_rowpack(const pcb_conv *c) { return c->nparts == 1 && c->cin <= 8 && c->
 
 bool common_ok(const pcb_conv *c) {
     if (c->dtype != PCB_BF16 || c->groups != 1 || c->kh * c->kw > 64) return false;
+    if (c->stride & (c->stride - 1)) return false;                               // shifts instead of divisions in the gather
+    // the gathers use 32-bit element offsets
+    const long long lim = (1ll << 31) - 1;
+    if (static_cast<long long>(c->n) * c->ho * c->wo * rup(c->cout, 64) > lim) return false;
     if (c->nparts < 1 || c->nparts > TC_MAX_PARTS) return false;
     for (int p = 0; p < c->nparts; ++p) {
         const pcb_part &pt = c->parts[p];
         if (pt.x_cstride % 8 != 0 || pt.x_cstride < rup(pt.c, 8)) return false;     // 16-byte chunks must be readable
+        if (static_cast<long long>(c->n) * (c->h >> pt.x_up) * (c->w >> pt.x_up) * pt.x_cstride > lim) return false;
         if (pt.x && (reinterpret_cast<uintptr_t>(pt.x) & 15)) return false;
     }
     if (is_rowpack(c)) return c->cout >= 16;
@@ -960,12 +1008,16 @@ int halo_hg(const pcb_conv *c, bool rowpack) {
 }
 
 template <int BLOCK_N, int SB, int MODE>
-int launch_halo(const TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
-    constexpr size_t smem = 1024 + SB * BLOCK_N * 128 + HALO_SA * HALO_A_STAGE + 16 * HALO_SA + 16 * SB + 16 + 16;
+int launch_halo(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
+    const size_t a_stage = 8 * 16 * (16 * P.hg + 1);
+    const size_t fixed = 1024 + SB * BLOCK_N * 128 + 16 * HALO_SA_MAX + 16 * SB + 64;
+    P.halo_sa = (fixed + 3 * a_stage <= 113 * 1024) ? 3 : 2;             // keep two CTAs per SM
+    const size_t smem = fixed + HALO_SA_MAX * a_stage;
+    constexpr size_t smem_max = 1024 + SB * BLOCK_N * 128 + 16 * HALO_SA_MAX + 16 * SB + 64 + HALO_SA_MAX * 8 * 16 * (16 * HALO_MAX_HG + 1);
     auto kern = pconv_tc_halo_kernel<BLOCK_N, SB, MODE>;
     static bool attr_done = false;
     if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         attr_done = true;
     }
     dim3 grid(P.ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
