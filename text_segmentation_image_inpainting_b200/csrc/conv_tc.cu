@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "pcb_common.cuh"
 #include "pcb_ptx.cuh"
 
@@ -55,7 +57,7 @@ struct TcParams {
     int m_total;              // GEMM M
     int nparts, no_guard, rowpack;
     int hg;                   // row-halo mode: input pixels staged per group of 8 output pixels = 8 + (kw-1)*dil
-    int halo_sa;              // row-halo mode: number of halo stages (2 or 3, smem permitting)
+    int ring_a, ring_b;       // smem ring depths (A items / weight tiles)
     int ktap;                 // K extent of one tap (sum of part kext); rowpack: 64 per kernel row
     int ncols;                // GEMM N extent covered by the grid (multiple of BLOCK_N)
     TcPart parts[TC_MAX_PARTS];
@@ -138,48 +140,73 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
 }
 
 // -------------------------------------------------------------------------------------------------
-// forward (MODE 0) / dgrad (MODE 1)
+// forward (MODE 0) / data gradient (MODE 1): PERSISTENT, warp-specialised implicit GEMM.
+//
+// One CTA per SM loops over output tiles (128 pixels x BLOCK_N channels).  Roles:
+//   warps 0-3  A producers  : im2col gather with zero-filling cp.async (padding AND holes), 32-bit offsets
+//   warp  4    B producer   : weight tiles by TMA (SWIZZLE_128B)
+//   warp  5    MMA issuer   : tcgen05.mma into one of TWO TMEM accumulator stages
+//   warps 6-9  epilogue     : tcgen05.ld -> renormalise / mask -> bf16 NHWC stores
+// so the fixed per-tile latencies (mask-word loads, pipeline fill, accumulator drain, stores) of tile i overlap the
+// main loop of tile i+1 -- with one CTA per tile these latencies (~10 us) dominated every layer with a short K loop.
+//
+// Two A-operand layouts:
+//   HALO = false : per tap, a [128 pixel x 64 channel] tile in the 128B-swizzled K-major layout (any stride / dilation;
+//                  also the row-packed small-Cin mode: K block = kernel row, chunk = tap column).
+//   HALO = true  : stride-1 layers.  Per kernel ROW, each group of 8 consecutive output pixels stages its
+//                  8 + (kw-1)*dil input pixels once in the canonical NO-SWIZZLE K-major layout
+//                  addr(slot, chunk) = chunk*LBO + slot*16; the kw taps of the row are kw UMMA descriptors whose start
+//                  address is shifted by tap*dil slots (SBO = HG*16 between 8-row groups): kw x fewer gathers.
 // -------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, (BLOCK_N <= 128) ? 2 : 1)
-pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w) {
+constexpr int HALO_MAX_HG = 12;
+constexpr int PERSIST_THREADS = 320;
+constexpr int MAX_RING = 8;
+
+template <int BLOCK_N, int MODE, bool HALO>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w) {
     constexpr int B_STAGE_BYTES = BLOCK_N * 128;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-    const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
-    if (MODE == 1) {      // dgrad: skip N tiles none of whose parts wants a gradient (uniform per CTA)
-        bool any = false;
-        for (int p = 0; p < P.nparts; ++p)
-            if (P.parts[p].dx && n0 < P.parts[p].koff + P.parts[p].kext && n0 + BLOCK_N > P.parts[p].koff) any = true;
-        if (!any) return;
-    }
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
-    const uint32_t sA = smem_base;
-    const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
-    const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;          // 8-byte barriers
-    const uint32_t bar_full_a = sBar;                           // [STAGES]
-    const uint32_t bar_full_b = sBar + 8 * STAGES;              // [STAGES]
-    const uint32_t bar_empty = sBar + 16 * STAGES;              // [STAGES]
-    const uint32_t bar_tmem_full = sBar + 24 * STAGES;          // [1]
-    const uint32_t s_tmem_ptr = bar_tmem_full + 8;              // u32
+    const int SA = P.ring_a, SB = P.ring_b;
+    const int HG = P.hg;
+    const uint32_t LBO = 16u * (16u * HG + 1u);                       // halo: byte distance between 8-channel chunks
+    const uint32_t A_STAGE = HALO ? ((8u * LBO + 127u) & ~127u) : static_cast<uint32_t>(A_STAGE_BYTES);
+    const uint32_t sB = smem_base;
+    const uint32_t sA = sB + SB * B_STAGE_BYTES;                      // stays 1024-aligned (B stages are multiples of 1024)
+    const uint32_t sBar = (sA + SA * A_STAGE + 15u) & ~15u;
+    const uint32_t bar_full_a = sBar, bar_empty_a = sBar + 8 * MAX_RING;
+    const uint32_t bar_full_b = sBar + 16 * MAX_RING, bar_empty_b = sBar + 24 * MAX_RING;
+    const uint32_t bar_tmem_full = sBar + 32 * MAX_RING, bar_tmem_empty = bar_tmem_full + 16;
+    const uint32_t s_tmem_ptr = bar_tmem_empty + 16;
     uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = P.kh * P.kw;
-    const int num_kb = (MODE == 0) ? (P.rowpack ? P.kh : taps * (P.ktap / BLOCK_K)) : taps * (P.dc_kext / BLOCK_K);
+    const int np = (MODE == 0) ? P.nparts : 1;
+    const int n_tiles = P.ncols / BLOCK_N;
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles;
+    const int nB = HALO ? P.kw : 1;                                   // weight tiles consumed per A item
+
+    // dgrad: N tiles none of whose parts wants a gradient are skipped (same decision in every role)
+    auto tile_active = [&](int n0) -> bool {
+        if (MODE == 0) return true;
+        for (int p = 0; p < P.nparts; ++p)
+            if (P.parts[p].dx && n0 < P.parts[p].koff + P.parts[p].kext && n0 + BLOCK_N > P.parts[p].koff) return true;
+        return false;
+    };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS);
-            ptx::mbar_init(bar_full_b + 8 * s, 1);
-            ptx::mbar_init(bar_empty + 8 * s, 1);
+        for (int s = 0; s < MAX_RING; ++s) {
+            ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS); ptx::mbar_init(bar_empty_a + 8 * s, 1);
+            ptx::mbar_init(bar_full_b + 8 * s, 1); ptx::mbar_init(bar_empty_b + 8 * s, 1);
         }
-        ptx::mbar_init(bar_tmem_full, 1);
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_tmem_full + 8 * s, 1); ptx::mbar_init(bar_tmem_empty + 8 * s, 128); }
         ptx::fence_mbar_init();
     }
     if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tmap_w);
     if (warp == 5) {
-        ptx::tmem_alloc<BLOCK_N>(s_tmem_ptr);
+        ptx::tmem_alloc<2 * BLOCK_N>(s_tmem_ptr);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -188,365 +215,293 @@ pconv_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUte
     const uint32_t tmem_base = *tmem_ptr_generic;
 
     if (warp < 4) {
-        // =========================== A producers: im2col gather ===========================
-        // All address arithmetic is 32-bit element offsets (host guarantees every source tensor < 2^31 elements):
-        // per tile each row keeps its image base per part; per (tap, part) a handful of integer ops per row; per
-        // K block one add + one cp.async per row.
+        // ================================ A producers ================================
         const int t = threadIdx.x;
-        const int chunk = t & 7;                    // 16-byte chunk inside the 128-byte row
-        const int r0 = t >> 3;                      // rows r0 + 16*i
-        const uint32_t sw = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);   // (r & 7) == (r0 & 7) for all i
-
-        int ph[8], pw[8];                           // per-row pixel coordinates (pre-scaled)
-        int ibase[TC_MAX_PARTS][8];                 // element offset of the row's image inside each source (+ chunk)
-        bool prow[8];
+        const int chunk = t & 7, r0 = t >> 3;
         const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
         const int pwid = (MODE == 0) ? P.wo : P.w;
-        const int ls = 31 - __clz(P.stride);        // dgrad: stride is a power of two on this path (host-checked)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + r0 + 16 * i;
-            prow[i] = m < P.m_total;
-            const int mm = prow[i] ? m : 0;
-            const int nn = mm / plane, rem = mm - nn * plane;
-            const int hh = rem / pwid, ww = rem - hh * pwid;
-            if (MODE == 0) {
-                ph[i] = hh * P.stride - P.pad_h; pw[i] = ww * P.stride - P.pad_w;
-#pragma unroll
-                for (int p = 0; p < TC_MAX_PARTS; ++p)
-                    ibase[p][i] = (p < P.nparts) ? nn * (P.h >> P.parts[p].xup) * (P.w >> P.parts[p].xup) * P.parts[p].cstride + chunk * 8 : 0;
-            } else {
-                ph[i] = hh + P.pad_h; pw[i] = ww + P.pad_w;
-                ibase[0][i] = nn * P.ho * P.wo * P.dc_cstride + chunk * 8;
-            }
-        }
-
-        // per-row tap-validity bits (bounds + holes), loaded once per tile: the k-loop issues no mask loads
-        uint64_t tmv[TC_MAX_PARTS][8];
-        if (MODE == 0) {
-#pragma unroll
-            for (int p = 0; p < TC_MAX_PARTS; ++p)
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    tmv[p][i] = (p < P.nparts && prow[i]) ? __ldg(P.parts[p].tapmask + m0 + r0 + 16 * i) : 0ull;
-        }
-
-        int kb = 0;
+        int it = 0;
         bool dead = false;
-        auto push = [&](const bf16 *base, const int (&off)[8], const bool (&ok)[8]) -> bool {
-            const int s = kb % STAGES;
-            const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
-            if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 101)) return false;
-            const uint32_t dst = sA + s * A_STAGE_BYTES + r0 * 128 + sw;
+        for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            if (!tile_active(n0)) continue;
+            if (HALO) {
+                int ph[HALO_MAX_HG];                              // row coordinate of the slot at kernel row 0
+                int cterm[TC_MAX_PARTS][HALO_MAX_HG];             // image base + column*cstride + chunk*8 (element offset)
+                uint32_t vb[TC_MAX_PARTS][HALO_MAX_HG];           // bit tr = slot valid (bounds [+ hole]) for kernel row tr
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), base + off[i], ok[i]);
-            ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
-            ptx::mbar_arrive(bar_full_a + 8 * s);
-            ++kb;
-            return true;
-        };
-
-        if (MODE == 0 && P.rowpack) {
-            // ---- small-Cin mode: K block = kernel row `tr`; chunk = tap column; source pixel shifts with the chunk
-            const TcPart &pt = P.parts[0];
-            const int cs = pt.cstride, rowpitch = P.w * cs;
-            for (int tr = 0; tr < P.kh && !dead; ++tr) {
-                int off[8];
-                bool ok[8];
+                for (int i = 0; i < HALO_MAX_HG; ++i) {
+                    ph[i] = 0;
+#pragma unroll
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) { vb[p][i] = 0; cterm[p][i] = 0; }
+                    if (i >= HG) continue;
+                    const int S = r0 + 16 * i;
+                    const int g = S / HG, sl = S - g * HG;
+                    const int m = m0 + g * 8;               // first pixel of the group (groups never straddle image rows)
+                    const bool ok = m < P.m_total;
+                    const int mm = ok ? m : 0;
+                    const int nn = mm / plane, rem = mm - nn * plane;
+                    const int hh = rem / pwid, ww = rem - hh * pwid;
+                    if (MODE == 0) {
+                        ph[i] = hh - P.pad_h;
+                        const int col = ww - P.pad_w + sl;
+                        // the (pixel j of the group, tap column tc) pair that looks at this slot: sl == j + tc*dil
+                        const int tcs = sl > 7 ? (sl - 7 + P.dil - 1) / P.dil : 0;
+                        const int j = sl - tcs * P.dil;
+#pragma unroll
+                        for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                            if (p >= P.nparts || !ok) continue;
+                            const TcPart &pt = P.parts[p];
+                            const uint64_t word = __ldg(pt.tapmask + m + j);
+                            uint32_t bits = 0;
+                            for (int tr = 0; tr < P.kh; ++tr) bits |= static_cast<uint32_t>((word >> (tr * P.kw + tcs)) & 1ull) << tr;
+                            vb[p][i] = bits;
+                            const int colc = min(max(col, 0), P.w - 1) >> pt.xup;   // clamped: only dereferenced when valid
+                            cterm[p][i] = (nn * (P.h >> pt.xup) * (P.w >> pt.xup) + colc) * pt.cstride + chunk * 8;
+                        }
+                    } else {
+                        ph[i] = hh + P.pad_h;
+                        const int col = ww + P.pad_w - (P.kw - 1) * P.dil + sl;
+                        const bool cok = ok && col >= 0 && col < P.wo;
+                        uint32_t bits = 0;
+                        for (int tr = 0; tr < P.kh; ++tr) { const int hi = ph[i] - tr * P.dil; bits |= (cok && hi >= 0 && hi < P.ho ? 1u : 0u) << tr; }
+                        vb[0][i] = bits;
+                        cterm[0][i] = (nn * P.ho * P.wo + min(max(col, 0), P.wo - 1)) * P.dc_cstride + chunk * 8;
+                    }
+                }
+                for (int tr = 0; tr < P.kh && !dead; ++tr) {
+#pragma unroll
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                        if (p >= np || dead) break;
+                        const TcPart &pt = P.parts[p];
+                        const bf16 *src = (MODE == 0) ? pt.x : P.dc;
+                        const int xup = (MODE == 0) ? pt.xup : 0;
+                        const int hmax = ((MODE == 0) ? (P.h >> xup) : P.ho) - 1;
+                        const int rowpitch = (MODE == 0) ? (P.w >> xup) * pt.cstride : P.wo * P.dc_cstride;
+                        const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
+                        const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
+                        int rterm[HALO_MAX_HG];
+#pragma unroll
+                        for (int i = 0; i < HALO_MAX_HG; ++i) {
+                            const int hi = (MODE == 0) ? ((ph[i] + tr * P.dil) >> xup) : (ph[i] - tr * P.dil);
+                            rterm[i] = cterm[p][i] + min(max(hi, 0), hmax) * rowpitch;
+                        }
+                        for (int cb = 0; cb < nb; ++cb, ++it) {
+                            const int s = it % SA;
+                            if (!ptx::mbar_wait(bar_empty_a + 8 * s, ((it / SA) & 1) ^ 1, P.abort_flag, 111)) { dead = true; break; }
+                            const bool cv = cb * BLOCK_K + chunk * 8 < c8;
+                            const uint32_t dst0 = sA + s * A_STAGE + chunk * LBO + r0 * 16;
+                            const bf16 *srcb = src + cb * BLOCK_K;
+#pragma unroll
+                            for (int i = 0; i < HALO_MAX_HG; ++i) {
+                                if (i >= HG) break;
+                                ptx::cp_async_16(dst0 + i * 256, srcb + rterm[i], cv && ((vb[p][i] >> tr) & 1u));   // slot r0 + 16*i
+                            }
+                            ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
+                            ptx::mbar_arrive(bar_full_a + 8 * s);
+                        }
+                    }
+                }
+            } else {
+                const uint32_t sw = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);   // (r & 7) == (r0 & 7) for all rows of a thread
+                int ph[8], pw[8];
+                int ibase[TC_MAX_PARTS][8];                 // element offset of the row's image inside each source (+ chunk)
+                bool prow[8];
+                const int ls = 31 - __clz(P.stride);        // dgrad: stride is a power of two on this path (host-checked)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const bool v = (chunk < P.kw) && ((tmv[0][i] >> (tr * P.kw + chunk)) & 1ull);
-                    off[i] = v ? (ibase[0][i] - chunk * 8) + (ph[i] + tr * P.dil) * rowpitch + (pw[i] + chunk * P.dil) * cs : 0;
-                    ok[i] = v;
-                }
-                if (!push(pt.x, off, ok)) dead = true;
-            }
-        } else {
-            for (int tap = 0; tap < taps && !dead; ++tap) {
-                const int tr = tap / P.kw, tc = tap - tr * P.kw;
-                const int np = (MODE == 0) ? P.nparts : 1;
+                    const int m = m0 + r0 + 16 * i;
+                    prow[i] = m < P.m_total;
+                    const int mm = prow[i] ? m : 0;
+                    const int nn = mm / plane, rem = mm - nn * plane;
+                    const int hh = rem / pwid, ww = rem - hh * pwid;
+                    if (MODE == 0) {
+                        ph[i] = hh * P.stride - P.pad_h; pw[i] = ww * P.stride - P.pad_w;
 #pragma unroll
-                for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                    if (p >= np || dead) break;
-                    const TcPart &pt = P.parts[p];
-                    const bf16 *src = (MODE == 0) ? pt.x : P.dc;
-                    const int cs = (MODE == 0) ? pt.cstride : P.dc_cstride;
-                    const int xup = (MODE == 0) ? pt.xup : 0;
-                    const int rowpitch = ((MODE == 0) ? (P.w >> xup) : P.wo) * cs;
-                    int base[8];
-                    bool rv[8];
+                        for (int p = 0; p < TC_MAX_PARTS; ++p)
+                            ibase[p][i] = (p < P.nparts) ? nn * (P.h >> P.parts[p].xup) * (P.w >> P.parts[p].xup) * P.parts[p].cstride + chunk * 8 : 0;
+                    } else {
+                        ph[i] = hh + P.pad_h; pw[i] = ww + P.pad_w;
+                        ibase[0][i] = nn * P.ho * P.wo * P.dc_cstride + chunk * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        bool v;
-                        int hi, wi;
-                        if (MODE == 0) {
-                            v = (tmv[p][i] >> tap) & 1ull;                  // bounds + hole (0 for rows past m_total)
-                            hi = (ph[i] + tr * P.dil) >> xup; wi = (pw[i] + tc * P.dil) >> xup;
-                        } else {
-                            const int th = ph[i] - tr * P.dil, tw = pw[i] - tc * P.dil;
-                            hi = th >> ls; wi = tw >> ls;
-                            v = prow[i] && th >= 0 && tw >= 0 && ((th | tw) & (P.stride - 1)) == 0 && hi < P.ho && wi < P.wo;
-                        }
-                        base[i] = v ? ibase[(MODE == 0) ? p : 0][i] + hi * rowpitch + wi * cs : 0;
-                        rv[i] = v;
+                        for (int p = 1; p < TC_MAX_PARTS; ++p) ibase[p][i] = 0;
                     }
-                    const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
-                    const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
-                    for (int cb = 0; cb < nb; ++cb) {
-                        const bool cv = cb * BLOCK_K + chunk * 8 < c8;       // channel padding of the part: zero-fill
+                }
+                uint64_t tmv[TC_MAX_PARTS][8];              // per-row tap-validity bits (bounds + holes), once per tile
+#pragma unroll
+                for (int p = 0; p < TC_MAX_PARTS; ++p)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        tmv[p][i] = (MODE == 0 && p < P.nparts && prow[i]) ? __ldg(P.parts[p].tapmask + m0 + r0 + 16 * i) : 0ull;
+
+                auto push = [&](const bf16 *base, const int (&off)[8], const bool (&ok)[8]) -> bool {
+                    const int s = it % SA;
+                    if (!ptx::mbar_wait(bar_empty_a + 8 * s, ((it / SA) & 1) ^ 1, P.abort_flag, 101)) return false;
+                    const uint32_t dst = sA + s * A_STAGE + r0 * 128 + sw;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst + i * (16 * 128), base + off[i], ok[i]);
+                    ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
+                    ptx::mbar_arrive(bar_full_a + 8 * s);
+                    ++it;
+                    return true;
+                };
+                if (MODE == 0 && P.rowpack) {
+                    // small-Cin mode: K block = kernel row `tr`; chunk = tap column; the source pixel shifts with the chunk
+                    const TcPart &pt = P.parts[0];
+                    const int cs = pt.cstride, rowpitch = P.w * cs;
+                    for (int tr = 0; tr < P.kh && !dead; ++tr) {
                         int off[8];
                         bool ok[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { ok[i] = rv[i] && cv; off[i] = ok[i] ? base[i] + cb * BLOCK_K : 0; }
-                        if (!push(src, off, ok)) { dead = true; break; }
+                        for (int i = 0; i < 8; ++i) {
+                            const bool v = (chunk < P.kw) && ((tmv[0][i] >> (tr * P.kw + chunk)) & 1ull);
+                            off[i] = v ? (ibase[0][i] - chunk * 8) + (ph[i] + tr * P.dil) * rowpitch + (pw[i] + chunk * P.dil) * cs : 0;
+                            ok[i] = v;
+                        }
+                        if (!push(pt.x, off, ok)) dead = true;
+                    }
+                } else {
+                    for (int tap = 0; tap < taps && !dead; ++tap) {
+                        const int tr = tap / P.kw, tc = tap - tr * P.kw;
+#pragma unroll
+                        for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                            if (p >= np || dead) break;
+                            const TcPart &pt = P.parts[p];
+                            const bf16 *src = (MODE == 0) ? pt.x : P.dc;
+                            const int cs = (MODE == 0) ? pt.cstride : P.dc_cstride;
+                            const int xup = (MODE == 0) ? pt.xup : 0;
+                            const int rowpitch = ((MODE == 0) ? (P.w >> xup) : P.wo) * cs;
+                            int base[8];
+                            bool rv[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                bool v;
+                                int hi, wi;
+                                if (MODE == 0) {
+                                    v = (tmv[p][i] >> tap) & 1ull;                  // bounds + hole (0 for rows past m_total)
+                                    hi = (ph[i] + tr * P.dil) >> xup; wi = (pw[i] + tc * P.dil) >> xup;
+                                } else {
+                                    const int th = ph[i] - tr * P.dil, tw = pw[i] - tc * P.dil;
+                                    hi = th >> ls; wi = tw >> ls;
+                                    v = prow[i] && th >= 0 && tw >= 0 && ((th | tw) & (P.stride - 1)) == 0 && hi < P.ho && wi < P.wo;
+                                }
+                                base[i] = v ? ibase[p][i] + hi * rowpitch + wi * cs : 0;
+                                rv[i] = v;
+                            }
+                            const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
+                            const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
+                            for (int cb = 0; cb < nb; ++cb) {
+                                const bool cv = cb * BLOCK_K + chunk * 8 < c8;       // channel padding of the part: zero-fill
+                                int off[8];
+                                bool ok[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) { ok[i] = rv[i] && cv; off[i] = ok[i] ? base[i] + cb * BLOCK_K : 0; }
+                                if (!push(src, off, ok)) { dead = true; break; }
+                            }
+                        }
                     }
                 }
             }
         }
         ptx::cp_async_wait<0>();
-
-        // =========================== epilogue ===========================
-        if (!dead && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 102)) tc_epilogue<BLOCK_N, MODE>(P, tmem_base, warp, lane, m0, n0);
     } else if (warp == 4) {
-        // =========================== B producer: TMA weight tiles ===========================
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
-                if (!ptx::mbar_wait(bar_empty + 8 * s, parity, P.abort_flag, 103)) break;
-                ptx::mbar_arrive_expect_tx(bar_full_b + 8 * s, B_STAGE_BYTES);
-                ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &tmap_w, kb * BLOCK_K, n0, bar_full_b + 8 * s);
-            }
-        }
-    } else {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-            bool dead = false;
-            for (int kb = 0; kb < num_kb && !dead; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t parity = (kb / STAGES) & 1;
-                if (!ptx::mbar_wait(bar_full_a + 8 * s, parity, P.abort_flag, 104) ||
-                    !ptx::mbar_wait(bar_full_b + 8 * s, parity, P.abort_flag, 105)) { dead = true; break; }
-                ptx::fence_proxy_async_smem();
-                ptx::tc_fence_after();
-                const uint64_t da = ptx::make_smem_desc(sA + s * A_STAGE_BYTES, 16, 1024);
-                const uint64_t db = ptx::make_smem_desc(sB + s * B_STAGE_BYTES, 16, 1024);
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k)       // +32 bytes per K=16 step inside the swizzle row
-                    ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                ptx::umma_commit(bar_empty + 8 * s);
-            }
-            if (!dead) ptx::umma_commit(bar_tmem_full);
-        }
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc<BLOCK_N>(tmem_base);
-    }
-}
-
-
-// -------------------------------------------------------------------------------------------------
-// forward / dgrad, ROW-HALO variant for stride-1 convolutions.
-// The per-tap gather above re-reads every input pixel kh*kw times from L2.  Here each group of 8 consecutive output
-// pixels stages its 8 + (kw-1)*dil input pixels of ONE kernel row once ("halo"), in the canonical NO-SWIZZLE
-// K-major layout  addr(slot, chunk) = chunk * LBO + slot * 16  (8 slots x 16 B = one contiguous core matrix),
-// and the kw taps of that row are kw UMMA descriptors whose start address is shifted by tap*dil slots with a
-// uniform stride-byte-offset of HG*16 between the 8-row groups.  kw x fewer gathers and address computations;
-// the weight tiles still arrive per tap by TMA (SWIZZLE_128B) through their own mbarrier ring.
-// -------------------------------------------------------------------------------------------------
-constexpr int HALO_MAX_HG = 12;
-constexpr int HALO_SA_MAX = 3;                                           // halo stages (runtime: 2 or 3)
-
-template <int BLOCK_N, int SB, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w) {
-    constexpr int B_STAGE_BYTES = BLOCK_N * 128;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-    const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
-    if (MODE == 1) {
-        bool any = false;
-        for (int p = 0; p < P.nparts; ++p)
-            if (P.parts[p].dx && n0 < P.parts[p].koff + P.parts[p].kext && n0 + BLOCK_N > P.parts[p].koff) any = true;
-        if (!any) return;
-    }
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
-    const uint32_t sB = smem_base;                                        // 1024-aligned swizzled weight tiles
-    const int HG = P.hg;
-    const uint32_t LBO = 16u * (16u * HG + 1u);
-    const uint32_t A_STAGE = 8u * LBO;                                    // 8 chunks
-    const uint32_t sA = sB + SB * B_STAGE_BYTES;                          // halo stages (16-byte alignment suffices)
-    const uint32_t sBar = (sA + HALO_SA_MAX * A_STAGE + 15u) & ~15u;
-    const uint32_t bar_full_a = sBar, bar_empty_a = sBar + 8 * HALO_SA_MAX;
-    const uint32_t bar_full_b = sBar + 16 * HALO_SA_MAX, bar_empty_b = bar_full_b + 8 * SB;
-    const uint32_t bar_tmem_full = bar_empty_b + 8 * SB;
-    const uint32_t s_tmem_ptr = bar_tmem_full + 8;
-    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_raw + (s_tmem_ptr - ptx::smem_u32(smem_raw)));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int np = (MODE == 0) ? P.nparts : 1;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < HALO_SA_MAX; ++s) { ptx::mbar_init(bar_full_a + 8 * s, NUM_PRODUCER_THREADS); ptx::mbar_init(bar_empty_a + 8 * s, 1); }
-        for (int s = 0; s < SB; ++s) { ptx::mbar_init(bar_full_b + 8 * s, 1); ptx::mbar_init(bar_empty_b + 8 * s, 1); }
-        ptx::mbar_init(bar_tmem_full, 1);
-        ptx::fence_mbar_init();
-    }
-    if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tmap_w);
-    if (warp == 5) {
-        ptx::tmem_alloc<BLOCK_N>(s_tmem_ptr);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_generic;
-
-    if (warp < 4) {
-        // =========================== halo producers ===========================
-        // 32-bit element offsets; per tile each slot keeps (image base + column term) per part, its row coordinate and its
-        // per-kernel-row validity bits; per halo item: one shift/multiply/add + predicate + cp.async per slot.
-        const int t = threadIdx.x;
-        const int chunk = t & 7, r0 = t >> 3;
-        int ph[HALO_MAX_HG];                              // row coordinate of the slot at kernel row 0
-        int cterm[TC_MAX_PARTS][HALO_MAX_HG];             // image base + column * cstride + chunk*8 (element offset)
-        uint32_t vb[TC_MAX_PARTS][HALO_MAX_HG];           // bit tr = slot valid (bounds [+ hole]) for kernel row tr
-        const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
-        const int pwid = (MODE == 0) ? P.wo : P.w;
-#pragma unroll
-        for (int i = 0; i < HALO_MAX_HG; ++i) {
-            ph[i] = 0;
-#pragma unroll
-            for (int p = 0; p < TC_MAX_PARTS; ++p) { vb[p][i] = 0; cterm[p][i] = 0; }
-            if (i >= HG) continue;
-            const int S = r0 + 16 * i;
-            const int g = S / HG, sl = S - g * HG;
-            const int m = m0 + g * 8;                   // first pixel of the group (groups never straddle image rows)
-            const bool ok = m < P.m_total;
-            const int mm = ok ? m : 0;
-            const int nn = mm / plane, rem = mm - nn * plane;
-            const int hh = rem / pwid, ww = rem - hh * pwid;
-            if (MODE == 0) {
-                ph[i] = hh - P.pad_h;
-                const int col = ww - P.pad_w + sl;
-                // the (pixel j of the group, tap column tc) pair that looks at this slot: sl == j + tc*dil
-                const int tcs = sl > 7 ? (sl - 7 + P.dil - 1) / P.dil : 0;
-                const int j = sl - tcs * P.dil;
-#pragma unroll
-                for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                    if (p >= P.nparts || !ok) continue;
-                    const TcPart &pt = P.parts[p];
-                    const uint64_t word = __ldg(pt.tapmask + m + j);
-                    uint32_t bits = 0;
-                    for (int tr = 0; tr < P.kh; ++tr) bits |= static_cast<uint32_t>((word >> (tr * P.kw + tcs)) & 1ull) << tr;
-                    vb[p][i] = bits;
-                    const int colc = min(max(col, 0), P.w - 1) >> pt.xup;       // clamped: only dereferenced when valid
-                    cterm[p][i] = (nn * (P.h >> pt.xup) * (P.w >> pt.xup) + colc) * pt.cstride + chunk * 8;
-                }
-            } else {
-                ph[i] = hh + P.pad_h;
-                const int col = ww + P.pad_w - (P.kw - 1) * P.dil + sl;
-                const bool cok = ok && col >= 0 && col < P.wo;
-                uint32_t bits = 0;
-                for (int tr = 0; tr < P.kh; ++tr) { const int hi = ph[i] - tr * P.dil; bits |= (cok && hi >= 0 && hi < P.ho ? 1u : 0u) << tr; }
-                vb[0][i] = bits;
-                cterm[0][i] = (nn * P.ho * P.wo + min(max(col, 0), P.wo - 1)) * P.dc_cstride + chunk * 8;
-            }
-        }
-
-        int it = 0;
-        bool dead = false;
-        for (int tr = 0; tr < P.kh && !dead; ++tr) {
-#pragma unroll
-            for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                if (p >= np || dead) break;
-                const TcPart &pt = P.parts[p];
-                const bf16 *src = (MODE == 0) ? pt.x : P.dc;
-                const int xup = (MODE == 0) ? pt.xup : 0;
-                const int hmax = ((MODE == 0) ? (P.h >> xup) : P.ho) - 1;
-                const int rowpitch = (MODE == 0) ? (P.w >> xup) * pt.cstride : P.wo * P.dc_cstride;
-                const int nb = ((MODE == 0) ? pt.kext : P.dc_kext) / BLOCK_K;
-                const int c8 = (MODE == 0) ? pt.c8 : P.dc_c8;
-                int rterm[HALO_MAX_HG];
-#pragma unroll
-                for (int i = 0; i < HALO_MAX_HG; ++i) {
-                    const int hi = (MODE == 0) ? ((ph[i] + tr * P.dil) >> xup) : (ph[i] - tr * P.dil);
-                    rterm[i] = cterm[p][i] + min(max(hi, 0), hmax) * rowpitch;
-                }
-                for (int cb = 0; cb < nb; ++cb, ++it) {
-                    const int s = it % P.halo_sa;
-                    const uint32_t parity = ((it / P.halo_sa) & 1) ^ 1;
-                    if (!ptx::mbar_wait(bar_empty_a + 8 * s, parity, P.abort_flag, 111)) { dead = true; break; }
-                    const bool cv = cb * BLOCK_K + chunk * 8 < c8;
-                    const uint32_t dst0 = sA + s * A_STAGE + chunk * LBO + r0 * 16;
-                    const bf16 *srcb = src + cb * BLOCK_K;
-#pragma unroll
-                    for (int i = 0; i < HALO_MAX_HG; ++i) {
-                        if (i >= HG) break;
-                        ptx::cp_async_16(dst0 + i * 256, srcb + rterm[i], cv && ((vb[p][i] >> tr) & 1u));   // slot r0 + 16*i
-                    }
-                    ptx::cp_async_mbar_arrive(bar_full_a + 8 * s);
-                    ptx::mbar_arrive(bar_full_a + 8 * s);
-                }
-            }
-        }
-        ptx::cp_async_wait<0>();
-        if (!dead && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 112)) tc_epilogue<BLOCK_N, MODE>(P, tmem_base, warp, lane, m0, n0);
-    } else if (warp == 4) {
-        // =========================== weight tiles: one per (kernel row, part, channel block, tap column) ===========================
+        // ================================ B producer: weight tiles by TMA ================================
         if (lane == 0) {
             int itb = 0;
             bool dead = false;
-            for (int tr = 0; tr < P.kh && !dead; ++tr)
-                for (int p = 0; p < np && !dead; ++p) {
-                    const int nb = ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
-                    for (int cb = 0; cb < nb && !dead; ++cb)
-                        for (int tc = 0; tc < P.kw; ++tc, ++itb) {
-                            const int s = itb % SB;
-                            const uint32_t parity = ((itb / SB) & 1) ^ 1;
-                            if (!ptx::mbar_wait(bar_empty_b + 8 * s, parity, P.abort_flag, 113)) { dead = true; break; }
-                            const int tap = tr * P.kw + tc;
-                            const int kidx = (MODE == 0) ? tap * P.ktap + P.parts[p].koff + cb * BLOCK_K : tap * P.dc_kext + cb * BLOCK_K;
-                            ptx::mbar_arrive_expect_tx(bar_full_b + 8 * s, B_STAGE_BYTES);
-                            ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &tmap_w, kidx, n0, bar_full_b + 8 * s);
+            auto load = [&](int kidx, int n0) -> bool {
+                const int s = itb % SB;
+                if (!ptx::mbar_wait(bar_empty_b + 8 * s, ((itb / SB) & 1) ^ 1, P.abort_flag, 103)) return false;
+                ptx::mbar_arrive_expect_tx(bar_full_b + 8 * s, B_STAGE_BYTES);
+                ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &tmap_w, kidx, n0, bar_full_b + 8 * s);
+                ++itb;
+                return true;
+            };
+            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BLOCK_N;
+                if (!tile_active(n0)) continue;
+                if (HALO) {
+                    for (int tr = 0; tr < P.kh && !dead; ++tr)
+                        for (int p = 0; p < np && !dead; ++p) {
+                            const int nb = ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
+                            for (int cb = 0; cb < nb && !dead; ++cb)
+                                for (int tc = 0; tc < P.kw; ++tc) {
+                                    const int tap = tr * P.kw + tc;
+                                    const int kidx = (MODE == 0) ? tap * P.ktap + P.parts[p].koff + cb * BLOCK_K : tap * P.dc_kext + cb * BLOCK_K;
+                                    if (!load(kidx, n0)) { dead = true; break; }
+                                }
                         }
+                } else {
+                    const int num_kb = (MODE == 0) ? (P.rowpack ? P.kh : taps * (P.ktap / BLOCK_K)) : taps * (P.dc_kext / BLOCK_K);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        if (!load(kb * BLOCK_K, n0)) { dead = true; break; }
                 }
+            }
         }
-    } else {
-        // =========================== MMA issuer ===========================
+    } else if (warp == 5) {
+        // ================================ MMA issuer ================================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
             int num_a = 0;
-            for (int p = 0; p < np; ++p) num_a += ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
-            num_a *= P.kh;
-            int itb = 0;
-            bool dead = false;
-            for (int ita = 0; ita < num_a && !dead; ++ita) {
-                const int sa = ita % P.halo_sa;
-                if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / P.halo_sa) & 1, P.abort_flag, 114)) { dead = true; break; }
-                ptx::fence_proxy_async_smem();
-                for (int tc = 0; tc < P.kw; ++tc, ++itb) {
-                    const int sb = itb % SB;
-                    if (!ptx::mbar_wait(bar_full_b + 8 * sb, (itb / SB) & 1, P.abort_flag, 115)) { dead = true; break; }
-                    ptx::tc_fence_after();
-                    const int shift = ((MODE == 0) ? tc : (P.kw - 1 - tc)) * P.dil;        // slots
-                    const uint32_t a0 = sA + sa * A_STAGE + shift * 16;
-                    const uint64_t db = ptx::make_smem_desc(sB + sb * B_STAGE_BYTES, 16, 1024);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {                                // 2 chunks (16 channels) per MMA
-                        const uint64_t da = ptx::make_smem_desc_noswizzle(a0 + k * 2 * LBO, LBO, HG * 16);
-                        ptx::umma_bf16(tmem_base, da, db + 2 * k, idesc, (ita | tc | k) != 0);
-                    }
-                    ptx::umma_commit(bar_empty_b + 8 * sb);
-                }
-                ptx::umma_commit(bar_empty_a + 8 * sa);
+            if (HALO) {
+                for (int p = 0; p < np; ++p) num_a += ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
+                num_a *= P.kh;
+            } else {
+                num_a = (MODE == 0) ? (P.rowpack ? P.kh : taps * (P.ktap / BLOCK_K)) : taps * (P.dc_kext / BLOCK_K);
             }
-            if (!dead) ptx::umma_commit(bar_tmem_full);
+            int ita = 0, itb = 0, tile_iter = 0;
+            bool dead = false;
+            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BLOCK_N;
+                if (!tile_active(n0)) continue;
+                const int acc = tile_iter & 1;
+                // the epilogue must have drained this accumulator stage (two tiles ago)
+                if (!ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 106)) { dead = true; break; }
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int a = 0; a < num_a && !dead; ++a, ++ita) {
+                    const int sa = ita % SA;
+                    if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / SA) & 1, P.abort_flag, 104)) { dead = true; break; }
+                    ptx::fence_proxy_async_smem();
+                    for (int tc = 0; tc < nB; ++tc, ++itb) {
+                        const int sb = itb % SB;
+                        if (!ptx::mbar_wait(bar_full_b + 8 * sb, (itb / SB) & 1, P.abort_flag, 105)) { dead = true; break; }
+                        ptx::tc_fence_after();
+                        const uint64_t db = ptx::make_smem_desc(sB + sb * B_STAGE_BYTES, 16, 1024);
+                        if (HALO) {
+                            const int shift = ((MODE == 0) ? tc : (P.kw - 1 - tc)) * P.dil;    // slots
+                            const uint32_t a0 = sA + sa * A_STAGE + shift * 16;
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {                            // 2 chunks (16 channels) per MMA
+                                const uint64_t da = ptx::make_smem_desc_noswizzle(a0 + k * 2 * LBO, LBO, HG * 16);
+                                ptx::umma_bf16(d_tmem, da, db + 2 * k, idesc, (a | tc | k) != 0);
+                            }
+                        } else {
+                            const uint64_t da = ptx::make_smem_desc(sA + sa * A_STAGE, 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)                              // +32 bytes per K=16 step inside the swizzle row
+                                ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (a | k) != 0);
+                        }
+                        ptx::umma_commit(bar_empty_b + 8 * sb);
+                    }
+                    ptx::umma_commit(bar_empty_a + 8 * sa);
+                }
+                if (!dead) ptx::umma_commit(bar_tmem_full + 8 * acc);
+                ++tile_iter;
+            }
+        }
+    } else {
+        // ================================ epilogue warps (6-9) ================================
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            if (!tile_active(n0)) continue;
+            const int acc = tile_iter & 1;
+            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 102)) break;
+            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
+            ++tile_iter;
         }
     }
 
@@ -554,7 +509,7 @@ pconv_tc_halo_kernel(const __grid_constant__ TcParams P, const __grid_constant__
     __syncthreads();
     if (warp == 5) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<BLOCK_N>(tmem_base);
+        ptx::tmem_dealloc<2 * BLOCK_N>(tmem_base);
     }
 }
 
@@ -1007,38 +962,33 @@ int halo_hg(const pcb_conv *c, bool rowpack) {
     return hg;
 }
 
-template <int BLOCK_N, int SB, int MODE>
-int launch_halo(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
-    const size_t a_stage = 8 * 16 * (16 * P.hg + 1);
-    const size_t fixed = 1024 + SB * BLOCK_N * 128 + 16 * HALO_SA_MAX + 16 * SB + 64;
-    P.halo_sa = (fixed + 3 * a_stage <= 113 * 1024) ? 3 : 2;             // keep two CTAs per SM
-    const size_t smem = fixed + HALO_SA_MAX * a_stage;
-    constexpr size_t smem_max = 1024 + SB * BLOCK_N * 128 + 16 * HALO_SA_MAX + 16 * SB + 64 + HALO_SA_MAX * 8 * 16 * (16 * HALO_MAX_HG + 1);
-    auto kern = pconv_tc_halo_kernel<BLOCK_N, SB, MODE>;
+template <int BLOCK_N, int MODE, bool HALO>
+int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
+    const size_t a_stage = HALO ? ((8 * 16 * (16 * P.hg + 1) + 127) / 128 * 128) : A_STAGE_BYTES;
+    const size_t b_stage = BLOCK_N * 128;
+    const size_t budget = 200 * 1024;
+    P.ring_b = 6;
+    P.ring_a = HALO ? 3 : 6;
+    while (P.ring_a * a_stage + P.ring_b * b_stage > budget && P.ring_b > 3) --P.ring_b;
+    while (P.ring_a * a_stage + P.ring_b * b_stage > budget && P.ring_a > 2) --P.ring_a;
+    const size_t smem = 1024 + P.ring_a * a_stage + P.ring_b * b_stage + 40 * MAX_RING + 64;
+    auto kern = pconv_tc_persistent_kernel<BLOCK_N, MODE, HALO>;
     static bool attr_done = false;
     if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
-    dim3 grid(P.ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
-    kern<<<grid, TC_THREADS, smem, st>>>(P, tm);
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
+    const int grid = std::min(num_tiles, pcb_num_sms());
+    kern<<<grid, PERSIST_THREADS, smem, st>>>(P, tm);
     PCB_LAUNCH_CHECK();
     return 0;
 }
 
-template <int BLOCK_N, int STAGES, int MODE>
-int launch_fwd(const TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
-    constexpr size_t smem = 1024 + STAGES * (A_STAGE_BYTES + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
-    auto kern = pconv_tc_kernel<BLOCK_N, STAGES, MODE>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    dim3 grid(P.ncols / BLOCK_N, (P.m_total + BLOCK_M - 1) / BLOCK_M);
-    kern<<<grid, TC_THREADS, smem, st>>>(P, tm);
-    PCB_LAUNCH_CHECK();
-    return 0;
+template <int MODE>
+int launch_tc(TcParams &P, const CUtensorMap &tm, int bn, cudaStream_t st) {
+    if (P.hg) return (bn == 128) ? launch_persistent<128, MODE, true>(P, tm, st) : launch_persistent<64, MODE, true>(P, tm, st);
+    return (bn == 128) ? launch_persistent<128, MODE, false>(P, tm, st) : launch_persistent<64, MODE, false>(P, tm, st);
 }
 
 }  // namespace
@@ -1094,9 +1044,7 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     CUtensorMap tm;
     if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
     P.hg = halo_hg(c, L.rowpack);
-    if (P.hg) return (L.bn_f == 128) ? launch_halo<128, 3, 0>(P, tm, st) : launch_halo<64, 4, 0>(P, tm, st);
-    if (L.bn_f == 128) return launch_fwd<128, 3, 0>(P, tm, st);
-    return launch_fwd<64, 4, 0>(P, tm, st);
+    return launch_tc<0>(P, tm, L.bn_f, st);
 }
 
 bool pcb_tc_dgrad_supported(const pcb_conv *c) { return pcb_tc_eligible(c) && !is_rowpack(c); }
@@ -1126,9 +1074,7 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     CUtensorMap tm;
     if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
     P.hg = halo_hg(c, L.rowpack);
-    if (P.hg) return (bn == 128) ? launch_halo<128, 3, 1>(P, tm, st) : launch_halo<64, 4, 1>(P, tm, st);
-    if (bn == 128) return launch_fwd<128, 3, 1>(P, tm, st);
-    return launch_fwd<64, 4, 1>(P, tm, st);
+    return launch_tc<1>(P, tm, bn, st);
 }
 
 template <int BLOCK_N, int T, int STAGES>
