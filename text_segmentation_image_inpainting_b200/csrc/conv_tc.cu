@@ -222,8 +222,45 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
         const int pwid = (MODE == 0) ? P.wo : P.w;
         int it = 0;
         bool dead = false;
+        // Tap-validity words of the NEXT tile are loaded while the current tile's items stream (software pipelining across
+        // tiles): their ~1 us global-load latency would otherwise stall all gathers at the start of every tile.
+        constexpr int NW = HALO ? HALO_MAX_HG : 8;
+        uint64_t wnext[TC_MAX_PARTS][NW];
+        auto issue_mask_loads = [&](int tl) {
+#pragma unroll
+            for (int p = 0; p < TC_MAX_PARTS; ++p)
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wnext[p][i] = 0ull;
+            if (MODE != 0 || tl >= num_tiles) return;
+            const int tm0 = (tl / n_tiles) * BLOCK_M;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                int idx;
+                if (HALO) {
+                    if (i >= HG) continue;
+                    const int S = r0 + 16 * i;
+                    const int g = S / HG, sl = S - g * HG;
+                    const int tcs = sl > 7 ? (sl - 7 + P.dil - 1) / P.dil : 0;
+                    idx = tm0 + g * 8 + (sl - tcs * P.dil);
+                    if (tm0 + g * 8 >= P.m_total) continue;
+                } else {
+                    idx = tm0 + r0 + 16 * i;
+                    if (idx >= P.m_total) continue;
+                }
+#pragma unroll
+                for (int p = 0; p < TC_MAX_PARTS; ++p)
+                    if (p < P.nparts) wnext[p][i] = __ldg(P.parts[p].tapmask + idx);
+            }
+        };
+        issue_mask_loads(blockIdx.x);
         for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            uint64_t wcur[TC_MAX_PARTS][NW];
+#pragma unroll
+            for (int p = 0; p < TC_MAX_PARTS; ++p)
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wcur[p][i] = wnext[p][i];
+            issue_mask_loads(tile + gridDim.x);
             if (!tile_active(n0)) continue;
             if (HALO) {
                 int ph[HALO_MAX_HG];                              // row coordinate of the slot at kernel row 0
@@ -247,12 +284,11 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
                         const int col = ww - P.pad_w + sl;
                         // the (pixel j of the group, tap column tc) pair that looks at this slot: sl == j + tc*dil
                         const int tcs = sl > 7 ? (sl - 7 + P.dil - 1) / P.dil : 0;
-                        const int j = sl - tcs * P.dil;
 #pragma unroll
                         for (int p = 0; p < TC_MAX_PARTS; ++p) {
                             if (p >= P.nparts || !ok) continue;
                             const TcPart &pt = P.parts[p];
-                            const uint64_t word = __ldg(pt.tapmask + m + j);
+                            const uint64_t word = wcur[p][i];
                             uint32_t bits = 0;
                             for (int tr = 0; tr < P.kh; ++tr) bits |= static_cast<uint32_t>((word >> (tr * P.kw + tcs)) & 1ull) << tr;
                             vb[p][i] = bits;
@@ -327,12 +363,11 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
                         for (int p = 1; p < TC_MAX_PARTS; ++p) ibase[p][i] = 0;
                     }
                 }
-                uint64_t tmv[TC_MAX_PARTS][8];              // per-row tap-validity bits (bounds + holes), once per tile
+                uint64_t tmv[TC_MAX_PARTS][8];              // per-row tap-validity bits (bounds + holes), prefetched one tile ahead
 #pragma unroll
                 for (int p = 0; p < TC_MAX_PARTS; ++p)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        tmv[p][i] = (MODE == 0 && p < P.nparts && prow[i]) ? __ldg(P.parts[p].tapmask + m0 + r0 + 16 * i) : 0ull;
+                    for (int i = 0; i < 8; ++i) tmv[p][i] = wcur[p][i];
 
                 auto push = [&](const bf16 *base, const int (&off)[8], const bool (&ok)[8]) -> bool {
                     const int s = it % SA;
