@@ -41,6 +41,10 @@ constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 constexpr int NUM_PRODUCER_THREADS = 128;
 constexpr int TC_THREADS = 192;             // 4 producer/epilogue warps + TMA warp + MMA warp
 constexpr int TC_MAX_PARTS = 2;             // U-Net inputs are cat([upsampled, skip]) at most
+// cp.async data is published to the MMA thread through the mbarrier the copies arrive on (cp.async.mbarrier.arrive +
+// mbarrier wait = release/acquire), exactly like CUTLASS's sm100 cp.async mainloop; an extra generic->async proxy fence in
+// the single MMA-issuing thread serialised every K block behind it (~1 us each) and is not needed.
+constexpr bool kProxyFence = false;
 
 inline int rup(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -497,7 +501,7 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
                 for (int a = 0; a < num_a && !dead; ++a, ++ita) {
                     const int sa = ita % SA;
                     if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / SA) & 1, P.abort_flag, 104)) { dead = true; break; }
-                    ptx::fence_proxy_async_smem();
+                    if (kProxyFence) ptx::fence_proxy_async_smem();
                     for (int tc = 0; tc < nB; ++tc, ++itb) {
                         const int sb = itb % SB;
                         if (!ptx::mbar_wait(bar_full_b + 8 * sb, (itb / SB) & 1, P.abort_flag, 105)) { dead = true; break; }
@@ -771,7 +775,7 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
                 const uint32_t parity = (it / STAGES) & 1;
                 if (!ptx::mbar_wait(bar_full_a + 8 * s, parity, P.abort_flag, 204) ||
                     !ptx::mbar_wait(bar_full_b + 8 * s, parity, P.abort_flag, 205)) { dead = true; break; }
-                ptx::fence_proxy_async_smem();
+                if (kProxyFence) ptx::fence_proxy_async_smem();
                 ptx::tc_fence_after();
                 for (int tl = 0; tl < ntap; ++tl) {
 #pragma unroll
