@@ -70,6 +70,7 @@ struct TcParams {
     // dgrad gather source
     const bf16 *dc; int dc_cstride, dc_c8, dc_kext;
     int *abort_flag;
+    long long *dbg;           // optional [grid][8] cycle counters written by the MMA thread (PCB_TC_DEBUG_TIMING)
 };
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
@@ -490,21 +491,30 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
             }
             int ita = 0, itb = 0, tile_iter = 0;
             bool dead = false;
+            long long t_acc = 0, t_a = 0, t_b = 0, t_issue = 0;
+            const long long t_begin = clock64();
             for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
                 const int n0 = (tile % n_tiles) * BLOCK_N;
                 if (!tile_active(n0)) continue;
                 const int acc = tile_iter & 1;
+                long long tq = clock64();
                 // the epilogue must have drained this accumulator stage (two tiles ago)
                 if (!ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 106)) { dead = true; break; }
+                t_acc += clock64() - tq;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int a = 0; a < num_a && !dead; ++a, ++ita) {
                     const int sa = ita % SA;
+                    tq = clock64();
                     if (!ptx::mbar_wait(bar_full_a + 8 * sa, (ita / SA) & 1, P.abort_flag, 104)) { dead = true; break; }
+                    t_a += clock64() - tq;
                     if (kProxyFence) ptx::fence_proxy_async_smem();
                     for (int tc = 0; tc < nB; ++tc, ++itb) {
                         const int sb = itb % SB;
+                        tq = clock64();
                         if (!ptx::mbar_wait(bar_full_b + 8 * sb, (itb / SB) & 1, P.abort_flag, 105)) { dead = true; break; }
+                        const long long tw = clock64();
+                        t_b += tw - tq;
                         ptx::tc_fence_after();
                         const uint64_t db = ptx::make_smem_desc(sB + sb * B_STAGE_BYTES, 16, 1024);
                         if (HALO) {
@@ -522,11 +532,16 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
                                 ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (a | k) != 0);
                         }
                         ptx::umma_commit(bar_empty_b + 8 * sb);
+                        t_issue += clock64() - tw;
                     }
                     ptx::umma_commit(bar_empty_a + 8 * sa);
                 }
                 if (!dead) ptx::umma_commit(bar_tmem_full + 8 * acc);
                 ++tile_iter;
+            }
+            if (P.dbg) {
+                long long *d = P.dbg + 8 * blockIdx.x;
+                d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_a; d[3] = t_b; d[4] = t_issue; d[5] = tile_iter; d[6] = ita; d[7] = itb;
             }
         }
     } else {
@@ -1001,6 +1016,13 @@ int halo_hg(const pcb_conv *c, bool rowpack) {
     return hg;
 }
 
+// PCB_TC_DEBUG_TIMING=1: every forward/dgrad launch synchronises and prints where its MMA threads spent their cycles
+long long *debug_buffer() {
+    static long long *buf = nullptr;
+    if (!buf && getenv("PCB_TC_DEBUG_TIMING")) cudaMalloc(&buf, sizeof(long long) * 8 * 1024);
+    return buf;
+}
+
 template <int BLOCK_N, int MODE, bool HALO>
 int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     const size_t a_stage = HALO ? ((8 * 16 * (16 * P.hg + 1) + 127) / 128 * 128) : A_STAGE_BYTES;
@@ -1019,8 +1041,19 @@ int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     }
     const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
     const int grid = std::min(num_tiles, pcb_num_sms());
+    P.dbg = debug_buffer();
     kern<<<grid, PERSIST_THREADS, smem, st>>>(P, tm);
     PCB_LAUNCH_CHECK();
+    if (P.dbg) {
+        static long long h[8 * 1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, P.dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        double tot = 0, acc = 0, a = 0, b = 0, iss = 0, tiles = 0, ia = 0, ib = 0;
+        for (int i = 0; i < grid; ++i) { tot += h[8*i]; acc += h[8*i+1]; a += h[8*i+2]; b += h[8*i+3]; iss += h[8*i+4]; tiles += h[8*i+5]; ia += h[8*i+6]; ib += h[8*i+7]; }
+        fprintf(stderr, "[tc-timing] mode=%d halo=%d N=%d cin=%d cout=%d %dx%d grid=%d tiles/cta=%.1f items/tile=%.1f | per-CTA cycles: total=%.0f wait_acc=%.0f wait_A=%.0f wait_B=%.0f issue=%.0f | per A item: %.0f cyc (wait_A %.0f, wait_B %.0f)\n",
+                MODE, (int)HALO, BLOCK_N, P.cin, P.cout, P.h, P.w, grid, tiles / grid, ia / std::max(1.0, tiles), tot / grid, acc / grid, a / grid, b / grid, iss / grid,
+                tot / std::max(1.0, ia), a / std::max(1.0, ia), b / std::max(1.0, ia));
+    }
     return 0;
 }
 
