@@ -71,6 +71,8 @@ struct TcParams {
     const bf16 *dc; int dc_cstride, dc_c8, dc_kext;
     int *abort_flag;
     long long *dbg;           // optional [grid][8] cycle counters written by the MMA thread (PCB_TC_DEBUG_TIMING)
+    // TMA-fed kernel: the 128 pixels of an M tile form the box {box_w, box_h, box_n} of the (x, y, image) pixel grid
+    int box_w, box_h, box_n, stages, use_fix;
 };
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
@@ -567,6 +569,246 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// forward (MODE 0) / stride-1 data gradient (MODE 1), TMA-FED: the im2col rows are not gathered by threads at all.
+//
+// An M tile of 128 consecutive output pixels is a box {box_w, box_h, box_n} of the (x, y, image) grid (all extents powers
+// of two here), so the A operand of tap (tr, tc) / channel block cb is ONE 4-D TMA tile {64 ch, box_w, box_h, box_n} of
+// the NHWC source at coordinates shifted by the tap -- negative / past-the-edge coordinates are zero-filled by the TMA
+// unit (the convolution padding), stride-2 layers use the tensor map's traversal stride, channel padding is the map's
+// channel extent.  TMA writes exactly the 128B-swizzled K-major image UMMA reads.  What TMA cannot know are the HOLES
+// (x*mask, models/partial_convolution.py:51): four "fixer" warps (one thread per tile row) test the row's tap-validity
+// bit and overwrite hole rows of the landed tile with zeros before handing the stage to the MMA thread
+// (generic-proxy stores -> fence.proxy.async -> mbarrier).  Plain convolutions / dgrad skip the fixers.
+//
+//   warp 0  TMA producer : per K block one A tile (4-D) + one weight tile (2-D) onto the same mbarrier
+//   warp 1  MMA issuer   : 4 x tcgen05.mma (K=16) per K block into one of two TMEM accumulator stages
+//   warps 2-5 fixers     : hole rows -> 0   (MODE 0 with masks only)
+//   warps 6-9 epilogue   : TMEM -> renormalise / mask -> bf16 NHWC
+// Every per-K-block loop is a handful of instructions: a lone thread executes dependent instructions at ~5 cycles each,
+// so index arithmetic in these loops (the old kernels did integer divisions there) directly throttles the tensor pipe.
+// -------------------------------------------------------------------------------------------------
+constexpr int TMA_THREADS = 320;
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
+    constexpr uint32_t B_BYTES = BLOCK_N * 128;
+    constexpr uint32_t STAGE = A_STAGE_BYTES + B_BYTES;               // multiple of 1024
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
+    const int S = P.stages;
+    const uint32_t sBar = smem_base + S * STAGE;
+    const uint32_t bar_full = sBar, bar_fixed = sBar + 8 * MAX_RING, bar_empty = sBar + 16 * MAX_RING;
+    const uint32_t bar_tmem_full = sBar + 24 * MAX_RING, bar_tmem_empty = bar_tmem_full + 16;
+    const uint32_t s_tmem_ptr = bar_tmem_empty + 16;
+    uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_gen + (s_tmem_ptr - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = P.kh * P.kw;
+    const int np = (MODE == 0) ? P.nparts : 1;
+    const int n_tiles = P.ncols / BLOCK_N;
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles;
+    const bool fix = (MODE == 0) && P.use_fix;
+
+    auto tile_active = [&](int n0) -> bool {
+        if (MODE == 0) return true;
+        for (int p = 0; p < P.nparts; ++p)
+            if (P.parts[p].dx && n0 < P.parts[p].koff + P.parts[p].kext && n0 + BLOCK_N > P.parts[p].koff) return true;
+        return false;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_RING; ++s) {
+            ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_fixed + 8 * s, 4); ptx::mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_tmem_full + 8 * s, 1); ptx::mbar_init(bar_tmem_empty + 8 * s, 128); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_w); ptx::prefetch_tmap(&tmap_a0); if (np > 1) ptx::prefetch_tmap(&tmap_a1); }
+    if (warp == 1) {
+        ptx::tmem_alloc<2 * BLOCK_N>(s_tmem_ptr);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 1;                                           // first pass over the ring: stages are free
+            const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
+            const int pwid = (MODE == 0) ? P.wo : P.w;
+            bool dead = false;
+            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+                if (!tile_active(n0)) continue;
+                const int img = m0 / plane, rem = m0 - img * plane;
+                const int oy = rem / pwid, ox = rem - oy * pwid;
+                const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : ox + P.pad_w;
+                const int y_org = (MODE == 0) ? oy * P.stride - P.pad_h : oy + P.pad_h;
+                const int dstep = (MODE == 0) ? P.dil : -P.dil;
+                int kidx = 0;                                          // K index of the weight tile: walks tap-major in 64s
+                for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep)
+                    for (int tc = 0, x = x_org; tc < P.kw && !dead; ++tc, x += dstep) {
+#pragma unroll
+                        for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                            if (p >= np) break;
+                            const CUtensorMap *ma = (p == 0) ? &tmap_a0 : &tmap_a1;
+                            const int kext = (MODE == 0) ? P.parts[p].kext : P.dc_kext;
+                            for (int c0 = 0; c0 < kext; c0 += BLOCK_K, kidx += BLOCK_K) {
+                                if (!ptx::mbar_wait(bar_empty + 8 * s, ph, P.abort_flag, 121)) { dead = true; break; }
+                                const uint32_t full = bar_full + 8 * s, dst = smem_base + s * STAGE;
+                                ptx::mbar_arrive_expect_tx(full, STAGE);
+                                ptx::tma_load_4d(dst, ma, c0, x, y, img, full);
+                                ptx::tma_load_2d(dst + A_STAGE_BYTES, &tmap_w, kidx, n0, full);
+                                if (++s == S) { s = 0; ph ^= 1; }
+                            }
+                            if (dead) break;
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            const int num_items = taps * (((MODE == 0) ? P.ktap : P.dc_kext) / BLOCK_K);
+            const uint32_t ready = fix ? bar_fixed : bar_full;
+            const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
+            const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
+            int s = 0, tile_iter = 0;
+            uint32_t ph = 0;
+            bool dead = false;
+            long long t_wait = 0, t_acc = 0, n_items = 0;
+            const long long t_begin = clock64();
+            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BLOCK_N;
+                if (!tile_active(n0)) continue;
+                const int acc = tile_iter & 1;
+                long long tq = P.dbg ? clock64() : 0;
+                if (!ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 126)) { dead = true; break; }
+                if (P.dbg) t_acc += clock64() - tq;
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int it = 0; it < num_items; ++it) {
+                    if (P.dbg) tq = clock64();
+                    if (!ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 124)) { dead = true; break; }
+                    if (P.dbg) t_wait += clock64() - tq;
+                    ptx::tc_fence_after();
+                    const uint64_t da = desc_a0 + static_cast<uint64_t>(s * (STAGE >> 4));
+                    const uint64_t db = desc_b0 + static_cast<uint64_t>(s * (STAGE >> 4));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                    ptx::umma_commit(bar_empty + 8 * s);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                n_items += num_items;
+                if (!dead) ptx::umma_commit(bar_tmem_full + 8 * acc);
+                ++tile_iter;
+            }
+            if (P.dbg) {
+                long long *d = P.dbg + 8 * blockIdx.x;
+                d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_wait; d[3] = 0; d[4] = 0; d[5] = tile_iter; d[6] = n_items; d[7] = n_items;
+            }
+        }
+    } else if (warp < 6) {
+        // ================================ fixers: zero the hole rows of every landed A tile ================================
+        if (fix) {
+            const int row = (warp - 2) * 32 + lane;
+            int s = 0;
+            uint32_t ph = 0;
+            bool dead = false;
+            uint64_t wnext[TC_MAX_PARTS];
+            auto load_words = [&](int tl) {
+#pragma unroll
+                for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                    wnext[p] = 0ull;
+                    const int m = (tl / n_tiles) * BLOCK_M + row;
+                    if (p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
+                }
+            };
+            load_words(blockIdx.x);
+            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                uint64_t wcur[TC_MAX_PARTS];
+#pragma unroll
+                for (int p = 0; p < TC_MAX_PARTS; ++p) wcur[p] = wnext[p];
+                load_words(tile + gridDim.x);                          // next tile's words travel while this tile streams
+                for (int tap = 0; tap < taps && !dead; ++tap) {
+#pragma unroll
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                        if (p >= np) break;
+                        const bool hole = ((wcur[p] >> tap) & 1ull) == 0ull;
+                        const bool any_hole = __any_sync(0xffffffffu, hole);
+                        const int nb = P.parts[p].kext / BLOCK_K;
+                        for (int cb = 0; cb < nb; ++cb) {
+                            if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 122)) { dead = true; break; }
+                            if (any_hole) {
+                                if (hole) {
+                                    uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + row * 128);
+                                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) r[k] = z;
+                                }
+                                ptx::fence_proxy_async_smem();
+                            }
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                            if (++s == S) { s = 0; ph ^= 1; }
+                        }
+                        if (dead) break;
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue warps (6-9) ================================
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            if (!tile_active(n0)) continue;
+            const int acc = tile_iter & 1;
+            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 123)) break;
+            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
+            ++tile_iter;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<2 * BLOCK_N>(tmem_base);
+    }
+}
+
+// nearest 2x upsample of one convolution source into a dense [n, 2hs, 2ws, c8] buffer (TMA cannot replicate pixels)
+__global__ void upsample_part_kernel(const bf16 *__restrict__ src, int cstride, int c8, long long pixels_src, int hs, int ws, bf16 *__restrict__ dst) {
+    const int chunks = c8 >> 3;
+    const long long total = pixels_src * chunks;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % chunks);
+        const long long pix = i / chunks;
+        const int x = static_cast<int>(pix % ws);
+        const long long t = pix / ws;
+        const int y = static_cast<int>(t % hs);
+        const long long n = t / hs;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + pix * cstride + ch * 8));
+        bf16 *d = dst + ((n * (2 * hs) + 2 * y) * (2ll * ws) + 2 * x) * c8 + ch * 8;
+        uint4 *d0 = reinterpret_cast<uint4 *>(d), *d1 = reinterpret_cast<uint4 *>(d + 2ll * ws * c8);
+        d0[0] = v; *reinterpret_cast<uint4 *>(d + c8) = v;
+        d1[0] = v; *reinterpret_cast<uint4 *>(d + 2ll * ws * c8 + c8) = v;
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // weight gradient
 // -------------------------------------------------------------------------------------------------
@@ -913,6 +1155,23 @@ int make_tmap_2d(CUtensorMap *tm, const void *base, long long rows, long long co
     return 0;
 }
 
+// 4D bf16 NHWC tensor viewed as (channels, x, y, image); box {64 ch, bx, by, bn} pixels visited with traversal stride `es`
+// along x and y.  `channels` may be smaller than 64: the rest of the 128-byte row is zero-filled (channel padding).
+int make_tmap_nhwc(CUtensorMap *tm, const void *base, int channels, int w, int h, int n, long long cstride, int bx, int by, int bn, int es) {
+    EncodeTiledFn enc = get_encode_fn();
+    PCB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(w) * cstride * 2, static_cast<cuuint64_t>(h) * w * cstride * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bx * es), static_cast<cuuint32_t>(by * es), static_cast<cuuint32_t>(bn)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4D) failed (%d) c=%d w=%d h=%d n=%d cstride=%lld box=%d,%d,%d es=%d base=%p", (int)r,
+              channels, w, h, n, cstride, bx, by, bn, es, base);
+    return 0;
+}
+
 int *abort_flag_ptr() {
     static int *flag = nullptr;
     if (!flag) {
@@ -1057,6 +1316,88 @@ int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     return 0;
 }
 
+
+// ---- TMA-fed path: eligibility, tile box, launch -------------------------------------------------
+// 128 consecutive pixels of a [n][ht][wt] grid as a box {bw, bh, bn}: possible when the extents nest in powers of two
+bool tile_box(int wt, int ht, int *bw, int *bh, int *bn) {
+    if (wt < 4) return false;
+    if (wt % 128 == 0) { *bw = 128; *bh = 1; *bn = 1; return true; }
+    if (128 % wt) return false;
+    const int rows = 128 / wt;
+    *bw = wt;
+    if (ht % rows == 0) { *bh = rows; *bn = 1; return true; }
+    if (rows % ht) return false;
+    *bh = ht; *bn = rows / ht;
+    return true;
+}
+
+bool tma_fwd_ok(const pcb_conv *c) {
+    if (getenv("PCB_DISABLE_TMA") || is_rowpack(c)) return false;
+    int bw, bh, bn;
+    if (!tile_box(c->wo, c->ho, &bw, &bh, &bn)) return false;
+    if (c->stride > 2 || bw * c->stride > 256 || bh * c->stride > 256) return false;
+    for (int p = 0; p < c->nparts; ++p)
+        if (c->parts[p].x_up && ((c->h | c->w) & 1)) return false;
+    return true;
+}
+
+bool tma_dgrad_ok(const pcb_conv *c) {
+    if (getenv("PCB_DISABLE_TMA") || is_rowpack(c) || c->stride != 1) return false;
+    int bw, bh, bn;
+    return tile_box(c->w, c->h, &bw, &bh, &bn);
+}
+
+size_t up_bytes(const pcb_conv *c, int p) {
+    return (static_cast<size_t>(c->n) * c->h * c->w * rup(c->parts[p].c, 8) * 2 + 255) / 256 * 256;
+}
+size_t tapmask_bytes(const pcb_conv *c) {
+    return (static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint64_t) + 255) / 256 * 256;
+}
+
+template <int BLOCK_N, int MODE>
+int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, cudaStream_t st) {
+    const size_t stage = A_STAGE_BYTES + BLOCK_N * 128;
+    P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (200 * 1024) / stage));
+    const size_t smem = 1024 + P.stages * stage + 24 * MAX_RING + 64;
+    auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
+    const int grid = std::min(num_tiles, pcb_num_sms());
+    P.dbg = debug_buffer();
+    kern<<<grid, TMA_THREADS, smem, st>>>(P, tw, ta0, ta1);
+    PCB_LAUNCH_CHECK();
+    if (P.dbg) {
+        static long long h[8 * 1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, P.dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        double tot = 0, acc = 0, wt = 0, tiles = 0, items = 0;
+        for (int i = 0; i < grid; ++i) { tot += h[8*i]; acc += h[8*i+1]; wt += h[8*i+2]; tiles += h[8*i+5]; items += h[8*i+6]; }
+        fprintf(stderr, "[tc-timing] TMA mode=%d N=%d cin=%d cout=%d %dx%d s%d grid=%d stages=%d fix=%d tiles/cta=%.1f items/tile=%.1f | per-CTA cycles: total=%.0f wait_acc=%.0f wait_ready=%.0f | per K block: %.0f cyc (wait %.0f)\n",
+                MODE, BLOCK_N, P.cin, P.cout, P.h, P.w, P.stride, grid, P.stages, P.use_fix, tiles / grid, items / std::max(1.0, tiles), tot / grid, acc / grid, wt / grid,
+                tot / std::max(1.0, items), wt / std::max(1.0, items));
+    }
+    return 0;
+}
+
+template <int MODE>
+int launch_tma(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, int bn, cudaStream_t st) {
+    if (bn == 256) return launch_tma_n<256, MODE>(P, tw, ta0, ta1, st);
+    if (bn == 128) return launch_tma_n<128, MODE>(P, tw, ta0, ta1, st);
+    return launch_tma_n<64, MODE>(P, tw, ta0, ta1, st);
+}
+
+// widest N tile that divides `cols` and still leaves at least one tile per SM
+int pick_bn(int cols, long long m_total) {
+    const long long m_tiles = (m_total + BLOCK_M - 1) / BLOCK_M;
+    if (cols % 256 == 0 && m_tiles * (cols / 256) >= pcb_num_sms()) return 256;
+    if (cols % 128 == 0) return 128;
+    return 64;
+}
+
 template <int MODE>
 int launch_tc(TcParams &P, const CUtensorMap &tm, int bn, cudaStream_t st) {
     if (P.hg) return (bn == 128) ? launch_persistent<128, MODE, true>(P, tm, st) : launch_persistent<64, MODE, true>(P, tm, st);
@@ -1069,7 +1410,11 @@ int launch_tc(TcParams &P, const CUtensorMap &tm, int bn, cudaStream_t st) {
 bool pcb_tc_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
 
 size_t pcb_tc_workspace(const pcb_conv *c) {
-    return static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint64_t);
+    size_t bytes = tapmask_bytes(c);
+    if (tma_fwd_ok(c))                                   // dense copies of the 2x-upsampled sources (TMA cannot replicate pixels)
+        for (int p = 0; p < c->nparts; ++p)
+            if (c->parts[p].x_up) bytes += up_bytes(c, p);
+    return bytes;
 }
 
 void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems) {
@@ -1114,6 +1459,33 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     P.bias = bias; P.msum = msum; P.y = static_cast<bf16 *>(y); P.y_cstride = y_cstride; P.abort_flag = flag;
     P.ncols = L.rows_f;
     CUtensorMap tm;
+    if (tma_fwd_ok(c)) {
+        tile_box(c->wo, c->ho, &P.box_w, &P.box_h, &P.box_n);
+        CUtensorMap ta[TC_MAX_PARTS];
+        memset(ta, 0, sizeof(ta));
+        uint8_t *extra = reinterpret_cast<uint8_t *>(tapmask) + tapmask_bytes(c);
+        for (int p = 0; p < c->nparts; ++p) {
+            const pcb_part &pt = c->parts[p];
+            const void *src = pt.x;
+            long long cs = pt.x_cstride;
+            const int c8 = rup(pt.c, 8);
+            if (pt.x_up) {
+                const long long pix = static_cast<long long>(c->n) * (c->h >> 1) * (c->w >> 1);
+                const long long work = pix * (c8 >> 3);
+                const int grid = static_cast<int>(std::min<long long>((work + 255) / 256, 16ll * pcb_num_sms()));
+                upsample_part_kernel<<<grid, 256, 0, st>>>(static_cast<const bf16 *>(pt.x), pt.x_cstride, c8, pix, c->h >> 1, c->w >> 1, reinterpret_cast<bf16 *>(extra));
+                PCB_LAUNCH_CHECK();
+                src = extra; cs = c8;
+                extra += up_bytes(c, p);
+            }
+            if (pt.mask) P.use_fix = 1;
+            if (int rc = make_tmap_nhwc(&ta[p], src, c8, c->w, c->h, c->n, cs, P.box_w, P.box_h, P.box_n, c->stride)) return rc;
+        }
+        if (c->nparts < 2) ta[1] = ta[0];
+        const int bn = pick_bn(L.rows_f, m_total);
+        if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, bn)) return rc;
+        return launch_tma<0>(P, tm, ta[0], ta[1], bn, st);
+    }
     if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
     P.hg = halo_hg(c, L.rowpack);
     return launch_tc<0>(P, tm, L.bn_f, st);
@@ -1141,9 +1513,17 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     }
     P.dc = static_cast<const bf16 *>(dc); P.dc_cstride = dc_cstride; P.dc_c8 = rup(c->cout, 8); P.dc_kext = L.cout64;
     P.abort_flag = flag;
-    const int bn = (L.ktap % 128 == 0) ? 128 : 64;
+    int bn = (L.ktap % 128 == 0) ? 128 : 64;
     P.ncols = L.ktap;
     CUtensorMap tm;
+    if (tma_dgrad_ok(c)) {
+        tile_box(c->w, c->h, &P.box_w, &P.box_h, &P.box_n);
+        CUtensorMap ta;
+        if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, P.box_w, P.box_h, P.box_n, 1)) return rc;
+        bn = pick_bn(L.ktap, m_total);
+        if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
+        return launch_tma<1>(P, tm, ta, ta, bn, st);
+    }
     if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
     P.hg = halo_hg(c, L.rowpack);
     return launch_tc<1>(P, tm, bn, st);

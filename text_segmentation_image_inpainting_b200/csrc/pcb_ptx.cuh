@@ -80,6 +80,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *m, 
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// 4-D tile (channels, x, y, image): out-of-range coordinates (negative included) are zero-filled -- the conv padding
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *m, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {   // whole warp

@@ -14,8 +14,11 @@ LAYERS = {  # name: (parts [(c, up)], cout, k, s, p, hw_out_res_in, same_holes)
     "dec3_1024_512": ([(512, 1), (512, 0)], 512, 3, 1, 1, 32, False),
     "enc1_64_128": ([(64, 0)], 128, 5, 2, 2, 256, True),
     "enc2_128_256": ([(128, 0)], 256, 5, 2, 2, 128, True),
+    "enc3_256_512": ([(256, 0)], 512, 3, 2, 1, 64, True),
+    "tail_67_3": ([(64, 1), (8, 0)], 8, 3, 1, 1, 512, False),
 }
-names = sys.argv[1:] or list(LAYERS)
+ONCE = "--once" in sys.argv
+names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(LAYERS)
 for name in names:
     parts, cout, k, s, p, hw, sh = LAYERS[name]
     n = 8
@@ -31,6 +34,8 @@ for name in names:
         return mod((x, m))[0]
     y = fwd(); gy = torch.randn_like(y)
     y.backward(gy); torch.cuda.synchronize()
+    if ONCE:
+        continue
     quiet = os.environ.pop("PCB_TC_DEBUG_TIMING", None)
     for tag, fn in (("fwd", lambda: fwd()), ("fwd+bwd", lambda: fwd().backward(gy))):
         for _ in range(3): fn()
