@@ -97,6 +97,16 @@ CONV_CASES = {
     "tc_cin72_padded_kblock": (72, 64, 3, 1, 1, 1, 1, True, False, 1, 16, 16, BF, "uniform", "pc"),
     "tc_cout24_padded_n": (64, 24, 3, 1, 1, 1, 1, True, False, 1, 16, 16, BF, "uniform", "pc"),
     "tc_cout3_tail_like": (64, 3, 3, 1, 1, 1, 1, True, False, 2, 16, 16, BF, "uniform", "pc"),
+    # ---- TMA-fed path (power-of-two pixel grids): row-halo tiles (w >= 128, stride 1), traversal stride 2, boxes spanning
+    #      image rows / several images, N tiles of 32 and 256
+    "tma_halo_k3_64_64": (64, 64, 3, 1, 1, 1, 1, True, False, 1, 8, 128, BF, "uniform", "pc"),
+    "tma_halo_k3_d2_64_128_w256": (64, 128, 3, 1, 2, 2, 1, False, False, 1, 6, 256, BF, "uniform", "pc"),
+    "tma_halo_k5_72_3_n32": (72, 3, 5, 1, 2, 1, 1, True, False, 1, 6, 128, BF, "uniform", "pc"),
+    "tma_halo_k3_192_64_two": (192, 64, 3, 1, 1, 1, 1, False, False, 2, 4, 128, BF, "two", "pc"),
+    "tma_k5_s2_64_128_box32x4": (64, 128, 5, 2, 2, 1, 1, False, True, 2, 32, 64, BF, "uniform", "pc"),
+    "tma_k3_s2_128_256_box_n": (128, 256, 3, 2, 1, 1, 1, False, True, 4, 8, 8, BF, "uniform", "pc"),
+    "tma_k3_64_256_n256": (64, 256, 3, 1, 1, 1, 1, False, False, 2, 128, 128, BF, "uniform", "pc"),
+    "tma_plain_1x1_128_64": (128, 64, 1, 1, 0, 1, 1, True, False, 2, 16, 16, BF, "uniform", "1x1"),
 }
 PADDED_X = {"tc_stem_rowpack_k7_s2", "tc_rowpack_k5_d2_cin4"}
 
@@ -194,7 +204,9 @@ def conv_case(tag, dev, dump_dir=None):
 
 # (ca at half resolution -> 2x nearest upsampled, cb at full resolution, cout, bias): the decoder / tail input pattern
 LAZYCAT_CASES = {"lc_128up_64_to_64": (128, 64, 64, False), "lc_256up_64_to_128": (256, 64, 128, False),
-                 "lc_tail_64up_3_to_3": (64, 3, 3, True), "lc_64up_8_to_16": (64, 8, 16, True)}
+                 "lc_tail_64up_3_to_3": (64, 3, 3, True), "lc_64up_8_to_16": (64, 8, 16, True),
+                 # TMA-fed path: the upsampled source is materialised in the workspace; second one uses row-halo tiles
+                 "lc_tma_128up_64_to_64": (128, 64, 64, False, (2, 32, 32)), "lc_tma_halo_tail_64up_3_to_3": (64, 3, 3, True, (1, 8, 128))}
 
 
 def lazycat_case(tag, dev, dtype=BF):
@@ -204,8 +216,8 @@ def lazycat_case(tag, dev, dtype=BF):
     from text_segmentation_image_inpainting_b200 import _lib, ops
     from text_segmentation_image_inpainting_b200.masks import HoleMask
     from text_segmentation_image_inpainting_b200.models import partial_convolution as PC
-    ca, cb, cout, bias = LAZYCAT_CASES[tag]
-    n, h, w = 2, 24, 20
+    ca, cb, cout, bias = LAZYCAT_CASES[tag][:4]
+    n, h, w = LAZYCAT_CASES[tag][4] if len(LAZYCAT_CASES[tag]) > 4 else (2, 24, 20)
     mod = PC.PartialConv(ca + cb, cout, 3, 1, 1, 1, 1, bias, False)
     sd = det_fill_state_dict(mod.state_dict()); mod.load_state_dict(sd)
     wq = sd["feature_conv.weight"].to(dtype).float()

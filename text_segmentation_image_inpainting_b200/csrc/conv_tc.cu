@@ -591,15 +591,26 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
 // -------------------------------------------------------------------------------------------------
 constexpr int TMA_THREADS = 320;
 
-template <int BLOCK_N, int MODE>
+// HALO = true (stride 1, tiles that are one image-row segment of 128 pixels): per kernel ROW one A tile of
+// 128 + (kw-1)*dil pixel rows is loaded, and the kw taps of that row are kw UMMA descriptors whose start address is
+// shifted by whole 128-byte rows (the 128B swizzle is a function of the absolute smem address, so a row-shifted start
+// reads the same image: probed in tools/ubench/tma_probe.cu) -- kw x less A traffic from L2 and kw x fewer barrier
+// round trips per MMA.  K steps that only cover channel padding (c8 <= 16*k) are skipped.
+template <int BLOCK_N, int MODE, bool HALO>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
     constexpr uint32_t B_BYTES = BLOCK_N * 128;
-    constexpr uint32_t STAGE = A_STAGE_BYTES + B_BYTES;               // multiple of 1024
+    constexpr int TCOLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
     const int S = P.stages;
+    const int nB = HALO ? P.kw : 1;                                    // weight tiles (taps) per stage
+    const int hx = HALO ? (P.kw - 1) * P.dil : 0;                      // extra pixel rows of a halo tile
+    const uint32_t A_BYTES = static_cast<uint32_t>(BLOCK_M + hx) * 128u;
+    const uint32_t A_ROOM = (A_BYTES + 1023u) & ~1023u;
+    const uint32_t STAGE = A_ROOM + nB * B_BYTES;                      // multiple of 1024
+    const uint32_t STAGE_TX = A_BYTES + nB * B_BYTES;
     const uint32_t sBar = smem_base + S * STAGE;
     const uint32_t bar_full = sBar, bar_fixed = sBar + 8 * MAX_RING, bar_empty = sBar + 16 * MAX_RING;
     const uint32_t bar_tmem_full = sBar + 24 * MAX_RING, bar_tmem_empty = bar_tmem_full + 16;
@@ -608,11 +619,11 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_gen + (s_tmem_ptr - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int taps = P.kh * P.kw;
     const int np = (MODE == 0) ? P.nparts : 1;
     const int n_tiles = P.ncols / BLOCK_N;
     const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles;
     const bool fix = (MODE == 0) && P.use_fix;
+    const int kwi = HALO ? 1 : P.kw;                                   // A items per kernel row
 
     auto tile_active = [&](int n0) -> bool {
         if (MODE == 0) return true;
@@ -630,7 +641,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     }
     if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_w); ptx::prefetch_tmap(&tmap_a0); if (np > 1) ptx::prefetch_tmap(&tmap_a1); }
     if (warp == 1) {
-        ptx::tmem_alloc<2 * BLOCK_N>(s_tmem_ptr);
+        ptx::tmem_alloc<TCOLS>(s_tmem_ptr);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -645,18 +656,21 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             uint32_t ph = 1;                                           // first pass over the ring: stages are free
             const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
             const int pwid = (MODE == 0) ? P.wo : P.w;
+            const int ktap_w = (MODE == 0) ? P.ktap : P.dc_kext;       // K extent of one tap in the weight matrix
             bool dead = false;
             for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
                 if (!tile_active(n0)) continue;
                 const int img = m0 / plane, rem = m0 - img * plane;
                 const int oy = rem / pwid, ox = rem - oy * pwid;
-                const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : ox + P.pad_w;
+                // leftmost / topmost source coordinate of tap column 0 (fwd) -- dgrad walks its taps right to left
+                const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : (HALO ? ox + P.pad_w - hx : ox + P.pad_w);
                 const int y_org = (MODE == 0) ? oy * P.stride - P.pad_h : oy + P.pad_h;
                 const int dstep = (MODE == 0) ? P.dil : -P.dil;
-                int kidx = 0;                                          // K index of the weight tile: walks tap-major in 64s
-                for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep)
-                    for (int tc = 0, x = x_org; tc < P.kw && !dead; ++tc, x += dstep) {
+                int krow = 0;                                          // weight K index of (tr, tap column 0, part 0, block 0)
+                for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep, krow += P.kw * ktap_w)
+                    for (int ti = 0, x = x_org; ti < kwi && !dead; ++ti, x += dstep) {
+                        int kidx = krow + ti * ktap_w;
 #pragma unroll
                         for (int p = 0; p < TC_MAX_PARTS; ++p) {
                             if (p >= np) break;
@@ -665,9 +679,10 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                             for (int c0 = 0; c0 < kext; c0 += BLOCK_K, kidx += BLOCK_K) {
                                 if (!ptx::mbar_wait(bar_empty + 8 * s, ph, P.abort_flag, 121)) { dead = true; break; }
                                 const uint32_t full = bar_full + 8 * s, dst = smem_base + s * STAGE;
-                                ptx::mbar_arrive_expect_tx(full, STAGE);
+                                ptx::mbar_arrive_expect_tx(full, STAGE_TX);
                                 ptx::tma_load_4d(dst, ma, c0, x, y, img, full);
-                                ptx::tma_load_2d(dst + A_STAGE_BYTES, &tmap_w, kidx, n0, full);
+                                for (int tc = 0; tc < nB; ++tc)
+                                    ptx::tma_load_2d(dst + A_ROOM + tc * B_BYTES, &tmap_w, kidx + tc * ktap_w, n0, full);
                                 if (++s == S) { s = 0; ph ^= 1; }
                             }
                             if (dead) break;
@@ -679,90 +694,167 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         // ================================ MMA issuer ================================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-            const int num_items = taps * (((MODE == 0) ? P.ktap : P.dc_kext) / BLOCK_K);
             const uint32_t ready = fix ? bar_fixed : bar_full;
             const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
-            const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
+            const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_ROOM, 16, 1024);
+            const uint32_t stage16 = STAGE >> 4;
+            // dgrad walks tap columns right to left inside a halo tile
+            const int shift0 = (HALO && MODE == 1) ? hx * 8 : 0;       // in 16-byte units: one pixel row = 128 B = 8 units
+            const int dshift = HALO ? ((MODE == 1) ? -P.dil * 8 : P.dil * 8) : 0;
+            const int rows_a = P.kh * kwi;                             // (kernel row, A item) pairs per tile
             int s = 0, tile_iter = 0;
             uint32_t ph = 0;
             bool dead = false;
-            long long t_wait = 0, t_acc = 0, n_items = 0;
+            long long n_items = 0;
             const long long t_begin = clock64();
             for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
                 const int n0 = (tile % n_tiles) * BLOCK_N;
                 if (!tile_active(n0)) continue;
                 const int acc = tile_iter & 1;
-                long long tq = P.dbg ? clock64() : 0;
                 if (!ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 126)) { dead = true; break; }
-                if (P.dbg) t_acc += clock64() - tq;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int it = 0; it < num_items; ++it) {
-                    if (P.dbg) tq = clock64();
-                    if (!ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 124)) { dead = true; break; }
-                    if (P.dbg) t_wait += clock64() - tq;
-                    ptx::tc_fence_after();
-                    const uint64_t da = desc_a0 + static_cast<uint64_t>(s * (STAGE >> 4));
-                    const uint64_t db = desc_b0 + static_cast<uint64_t>(s * (STAGE >> 4));
+                uint32_t accum = 0;
+                for (int r = 0; r < rows_a && !dead; ++r) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-                    ptx::umma_commit(bar_empty + 8 * s);
-                    if (++s == S) { s = 0; ph ^= 1; }
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                        if (p >= np) break;
+                        const int kext = (MODE == 0) ? P.parts[p].kext : P.dc_kext;
+                        const int c8 = (MODE == 0) ? P.parts[p].c8 : P.dc_c8;
+                        for (int c0 = 0; c0 < kext; c0 += BLOCK_K) {
+                            const int ksteps = min(BLOCK_K / 16, (c8 - c0 + 15) >> 4);     // K steps holding real channels
+                            if (!ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 124)) { dead = true; break; }
+                            ptx::tc_fence_after();
+                            uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16 + shift0);
+                            uint64_t db = desc_b0 + static_cast<uint64_t>(s * stage16);
+                            for (int tc = 0; tc < nB; ++tc, da += dshift, db += B_BYTES >> 4) {
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k)
+                                    if (k < ksteps) { ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum != 0); accum = 1; }
+                            }
+                            ptx::umma_commit(bar_empty + 8 * s);
+                            if (++s == S) { s = 0; ph ^= 1; }
+                            ++n_items;
+                        }
+                        if (dead) break;
+                    }
                 }
-                n_items += num_items;
                 if (!dead) ptx::umma_commit(bar_tmem_full + 8 * acc);
                 ++tile_iter;
             }
             if (P.dbg) {
                 long long *d = P.dbg + 8 * blockIdx.x;
-                d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_wait; d[3] = 0; d[4] = 0; d[5] = tile_iter; d[6] = n_items; d[7] = n_items;
+                d[0] = clock64() - t_begin; d[1] = 0; d[2] = 0; d[3] = 0; d[4] = 0; d[5] = tile_iter; d[6] = n_items; d[7] = n_items;
             }
         }
     } else if (warp < 6) {
         // ================================ fixers: zero the hole rows of every landed A tile ================================
         if (fix) {
-            const int row = (warp - 2) * 32 + lane;
+            const int t = (warp - 2) * 32 + lane;
             int s = 0;
             uint32_t ph = 0;
             bool dead = false;
-            uint64_t wnext[TC_MAX_PARTS];
-            auto load_words = [&](int tl) {
-#pragma unroll
-                for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                    wnext[p] = 0ull;
-                    const int m = (tl / n_tiles) * BLOCK_M + row;
-                    if (p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
-                }
-            };
-            load_words(blockIdx.x);
-            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
-                uint64_t wcur[TC_MAX_PARTS];
-#pragma unroll
-                for (int p = 0; p < TC_MAX_PARTS; ++p) wcur[p] = wnext[p];
-                load_words(tile + gridDim.x);                          // next tile's words travel while this tile streams
-                for (int tap = 0; tap < taps && !dead; ++tap) {
+            if (!HALO) {
+                // one thread per tile row; validity = the row's tap bit (bounds + hole)
+                uint64_t wnext[TC_MAX_PARTS];
+                auto load_words = [&](int tl) {
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                        if (p >= np) break;
-                        const bool hole = ((wcur[p] >> tap) & 1ull) == 0ull;
-                        const bool any_hole = __any_sync(0xffffffffu, hole);
-                        const int nb = P.parts[p].kext / BLOCK_K;
-                        for (int cb = 0; cb < nb; ++cb) {
-                            if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 122)) { dead = true; break; }
-                            if (any_hole) {
-                                if (hole) {
-                                    uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + row * 128);
-                                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        wnext[p] = 0ull;
+                        const int m = (tl / n_tiles) * BLOCK_M + t;
+                        if (p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
+                    }
+                };
+                load_words(blockIdx.x);
+                for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                    uint64_t wcur[TC_MAX_PARTS];
 #pragma unroll
-                                    for (int k = 0; k < 8; ++k) r[k] = z;
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) wcur[p] = wnext[p];
+                    load_words(tile + gridDim.x);                      // next tile's words travel while this tile streams
+                    const int taps = P.kh * P.kw;
+                    for (int tap = 0; tap < taps && !dead; ++tap) {
+#pragma unroll
+                        for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                            if (p >= np) break;
+                            const bool hole = ((wcur[p] >> tap) & 1ull) == 0ull;
+                            const bool any_hole = __any_sync(0xffffffffu, hole);
+                            const int nb = P.parts[p].kext / BLOCK_K;
+                            for (int cb = 0; cb < nb; ++cb) {
+                                if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 122)) { dead = true; break; }
+                                if (any_hole) {
+                                    if (hole) {
+                                        uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + t * 128);
+                                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) r[k] = z;
+                                    }
+                                    ptx::fence_proxy_async_smem();
                                 }
-                                ptx::fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                                if (++s == S) { s = 0; ph ^= 1; }
                             }
-                            __syncwarp();
-                            if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
-                            if (++s == S) { s = 0; ph ^= 1; }
+                            if (dead) break;
                         }
-                        if (dead) break;
+                    }
+                }
+            } else {
+                // one thread per halo pixel row (threads < hx own a second one); validity = the source mask at that pixel
+                const int plane = P.ho * P.wo;
+                auto load_bits = [&](int tl, uint32_t &b0, uint32_t &b1) {       // bit (p*8 + tr): pixel row is a hole
+                    b0 = b1 = 0;
+                    if (tl >= num_tiles) return;
+                    const int m0 = (tl / n_tiles) * BLOCK_M;
+                    const int img = m0 / plane, rem = m0 - img * plane;
+                    const int oy = rem / P.wo, ox = rem - oy * P.wo;
+#pragma unroll
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                        if (p >= P.nparts || P.parts[p].mask == nullptr) continue;
+                        const int mup = P.parts[p].mup;
+                        const uint8_t *mk = P.parts[p].mask + static_cast<long long>(img) * (P.h >> mup) * (P.w >> mup);
+                        for (int tr = 0; tr < P.kh; ++tr) {
+                            const int y = oy - P.pad_h + tr * P.dil;
+                            if (y < 0 || y >= P.h) continue;            // rows outside the image were zero-filled by TMA
+                            const int x0 = ox - P.pad_w + t, x1 = x0 + 128;
+                            if (x0 >= 0 && x0 < P.w && __ldg(mk + (y >> mup) * (P.w >> mup) + (x0 >> mup)) == 0) b0 |= 1u << (p * 8 + tr);
+                            if (t < hx && x1 < P.w && __ldg(mk + (y >> mup) * (P.w >> mup) + (x1 >> mup)) == 0) b1 |= 1u << (p * 8 + tr);
+                        }
+                    }
+                };
+                uint32_t n0b, n1b;
+                load_bits(blockIdx.x, n0b, n1b);
+                for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                    const uint32_t c0b = n0b, c1b = n1b;
+                    load_bits(tile + gridDim.x, n0b, n1b);
+                    for (int tr = 0; tr < P.kh && !dead; ++tr) {
+#pragma unroll
+                        for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                            if (p >= np) break;
+                            const bool h0 = (c0b >> (p * 8 + tr)) & 1u, h1 = (c1b >> (p * 8 + tr)) & 1u;
+                            const bool any_hole = __any_sync(0xffffffffu, h0 || h1);
+                            const int nb = P.parts[p].kext / BLOCK_K;
+                            for (int cb = 0; cb < nb; ++cb) {
+                                if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 122)) { dead = true; break; }
+                                if (any_hole) {
+                                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                                    if (h0) {
+                                        uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + t * 128);
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) r[k] = z;
+                                    }
+                                    if (h1) {
+                                        uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + (t + 128) * 128);
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) r[k] = z;
+                                    }
+                                    ptx::fence_proxy_async_smem();
+                                }
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                                if (++s == S) { s = 0; ph ^= 1; }
+                            }
+                            if (dead) break;
+                        }
                     }
                 }
             }
@@ -786,7 +878,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<2 * BLOCK_N>(tmem_base);
+        ptx::tmem_dealloc<TCOLS>(tmem_base);
     }
 }
 
@@ -1354,15 +1446,18 @@ size_t tapmask_bytes(const pcb_conv *c) {
     return (static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint64_t) + 255) / 256 * 256;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool HALO>
 int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, cudaStream_t st) {
-    const size_t stage = A_STAGE_BYTES + BLOCK_N * 128;
-    P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (200 * 1024) / stage));
+    const int nb = HALO ? P.kw : 1;
+    const size_t a_room = (static_cast<size_t>(BLOCK_M + (HALO ? (P.kw - 1) * P.dil : 0)) * 128 + 1023) / 1024 * 1024;
+    const size_t stage = a_room + static_cast<size_t>(nb) * BLOCK_N * 128;
+    P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (208 * 1024) / stage));
+    PCB_CHECK(P.stages >= 2, "TMA-fed conv: stage of %zu bytes does not fit twice", stage);
     const size_t smem = 1024 + P.stages * stage + 24 * MAX_RING + 64;
-    auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE>;
+    auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE, HALO>;
     static bool attr_done = false;
     if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_done = true;
     }
     const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
@@ -1374,20 +1469,36 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
         static long long h[8 * 1024];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, P.dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
-        double tot = 0, acc = 0, wt = 0, tiles = 0, items = 0;
-        for (int i = 0; i < grid; ++i) { tot += h[8*i]; acc += h[8*i+1]; wt += h[8*i+2]; tiles += h[8*i+5]; items += h[8*i+6]; }
-        fprintf(stderr, "[tc-timing] TMA mode=%d N=%d cin=%d cout=%d %dx%d s%d grid=%d stages=%d fix=%d tiles/cta=%.1f items/tile=%.1f | per-CTA cycles: total=%.0f wait_acc=%.0f wait_ready=%.0f | per K block: %.0f cyc (wait %.0f)\n",
-                MODE, BLOCK_N, P.cin, P.cout, P.h, P.w, P.stride, grid, P.stages, P.use_fix, tiles / grid, items / std::max(1.0, tiles), tot / grid, acc / grid, wt / grid,
-                tot / std::max(1.0, items), wt / std::max(1.0, items));
+        double tot = 0, tiles = 0, items = 0;
+        for (int i = 0; i < grid; ++i) { tot += h[8*i]; tiles += h[8*i+5]; items += h[8*i+6]; }
+        fprintf(stderr, "[tc-timing] TMA mode=%d halo=%d N=%d cin=%d cout=%d %dx%d s%d grid=%d stages=%d(%zu B) fix=%d tiles/cta=%.1f items/tile=%.1f | per-CTA cycles %.0f | per item %.0f cyc = %.0f per tap\n",
+                MODE, (int)HALO, BLOCK_N, P.cin, P.cout, P.h, P.w, P.stride, grid, P.stages, stage, P.use_fix, tiles / grid, items / std::max(1.0, tiles), tot / grid,
+                tot / std::max(1.0, items), tot / std::max(1.0, items) / nb);
     }
     return 0;
 }
 
 template <int MODE>
-int launch_tma(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, int bn, cudaStream_t st) {
-    if (bn == 256) return launch_tma_n<256, MODE>(P, tw, ta0, ta1, st);
-    if (bn == 128) return launch_tma_n<128, MODE>(P, tw, ta0, ta1, st);
-    return launch_tma_n<64, MODE>(P, tw, ta0, ta1, st);
+int launch_tma(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, int bn, bool halo, cudaStream_t st) {
+    if (halo) {
+        if (bn == 256) return launch_tma_n<256, MODE, true>(P, tw, ta0, ta1, st);
+        if (bn == 128) return launch_tma_n<128, MODE, true>(P, tw, ta0, ta1, st);
+        if (bn == 64) return launch_tma_n<64, MODE, true>(P, tw, ta0, ta1, st);
+        return launch_tma_n<32, MODE, true>(P, tw, ta0, ta1, st);
+    }
+    if (bn == 256) return launch_tma_n<256, MODE, false>(P, tw, ta0, ta1, st);
+    if (bn == 128) return launch_tma_n<128, MODE, false>(P, tw, ta0, ta1, st);
+    if (bn == 64) return launch_tma_n<64, MODE, false>(P, tw, ta0, ta1, st);
+    return launch_tma_n<32, MODE, false>(P, tw, ta0, ta1, st);
+}
+
+// halo tiles: stride 1, the M tile is one image-row segment, a kernel row's halo fits the 256-pixel TMA box, and at
+// least three stages of (halo tile + kw weight tiles) fit in shared memory for the chosen N tile
+bool tma_halo_ok(const pcb_conv *c, int bw, int bh, int bn, int block_n) {
+    if (getenv("PCB_DISABLE_TMA_HALO")) return false;
+    if (!(c->stride == 1 && bw == 128 && bh == 1 && bn == 1 && c->kw >= 2 && 128 + (c->kw - 1) * c->dil <= 256 && c->kh <= 8)) return false;
+    const size_t stage = (static_cast<size_t>(128 + (c->kw - 1) * c->dil) * 128 + 1023) / 1024 * 1024 + static_cast<size_t>(c->kw) * block_n * 128;
+    return 3 * stage <= 208 * 1024;
 }
 
 // widest N tile that divides `cols` and still leaves at least one tile per SM
@@ -1395,6 +1506,7 @@ int pick_bn(int cols, long long m_total) {
     const long long m_tiles = (m_total + BLOCK_M - 1) / BLOCK_M;
     if (cols % 256 == 0 && m_tiles * (cols / 256) >= pcb_num_sms()) return 256;
     if (cols % 128 == 0) return 128;
+    if (cols <= 32) return 32;
     return 64;
 }
 
@@ -1461,6 +1573,9 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     CUtensorMap tm;
     if (tma_fwd_ok(c)) {
         tile_box(c->wo, c->ho, &P.box_w, &P.box_h, &P.box_n);
+        const int bn = pick_bn(c->cout <= 32 ? 32 : L.rows_f, m_total);
+        const bool halo = tma_halo_ok(c, P.box_w, P.box_h, P.box_n, bn);
+        const int hx = halo ? (c->kw - 1) * c->dil : 0;
         CUtensorMap ta[TC_MAX_PARTS];
         memset(ta, 0, sizeof(ta));
         uint8_t *extra = reinterpret_cast<uint8_t *>(tapmask) + tapmask_bytes(c);
@@ -1479,12 +1594,12 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
                 extra += up_bytes(c, p);
             }
             if (pt.mask) P.use_fix = 1;
-            if (int rc = make_tmap_nhwc(&ta[p], src, c8, c->w, c->h, c->n, cs, P.box_w, P.box_h, P.box_n, c->stride)) return rc;
+            if (int rc = make_tmap_nhwc(&ta[p], src, c8, c->w, c->h, c->n, cs, P.box_w + hx, P.box_h, P.box_n, c->stride)) return rc;
         }
         if (c->nparts < 2) ta[1] = ta[0];
-        const int bn = pick_bn(L.rows_f, m_total);
+        P.ncols = (bn == 32) ? 32 : L.rows_f;
         if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, bn)) return rc;
-        return launch_tma<0>(P, tm, ta[0], ta[1], bn, st);
+        return launch_tma<0>(P, tm, ta[0], ta[1], bn, halo, st);
     }
     if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
     P.hg = halo_hg(c, L.rowpack);
@@ -1518,11 +1633,13 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     CUtensorMap tm;
     if (tma_dgrad_ok(c)) {
         tile_box(c->w, c->h, &P.box_w, &P.box_h, &P.box_n);
-        CUtensorMap ta;
-        if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, P.box_w, P.box_h, P.box_n, 1)) return rc;
         bn = pick_bn(L.ktap, m_total);
+        if (bn == 32) bn = 64;
+        const bool halo = tma_halo_ok(c, P.box_w, P.box_h, P.box_n, bn);
+        CUtensorMap ta;
+        if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, P.box_w + (halo ? (c->kw - 1) * c->dil : 0), P.box_h, P.box_n, 1)) return rc;
         if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
-        return launch_tma<1>(P, tm, ta, ta, bn, st);
+        return launch_tma<1>(P, tm, ta, ta, bn, halo, st);
     }
     if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
     P.hg = halo_hg(c, L.rowpack);
