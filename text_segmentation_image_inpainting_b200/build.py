@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         o = os.path.join(bdir, s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("PCB_EXTRA_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -618,7 +618,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_gen + (s_tmem_ptr - smem_base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     const int np = (MODE == 0) ? P.nparts : 1;
     const int n_tiles = P.ncols / BLOCK_N;
     const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles;
@@ -649,103 +649,157 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_generic;
 
+    // The two issuing roles run WARP-CONVERGED (all 32 lanes walk the loops and wait on the barriers; the warp index is a
+    // shuffle broadcast so the compiler knows the role branch is uniform) and only the TMA / MMA / commit instructions sit
+    // inside an elect.sync region.  Written as `if (lane == 0) { whole loop }` the compiler treats every such instruction as
+    // possibly divergent, wraps each in an ELECT/branch loop and keeps its operands in vector registers (R2UR per use):
+    // ~8 dependent uniform-datapath instructions = ~60 cycles per tcgen05.mma, more than the N<=128 MMA itself takes.
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 1;                                           // first pass over the ring: stages are free
-            const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
-            const int pwid = (MODE == 0) ? P.wo : P.w;
-            const int ktap_w = (MODE == 0) ? P.ktap : P.dc_kext;       // K extent of one tap in the weight matrix
-            bool dead = false;
-            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
-                if (!tile_active(n0)) continue;
-                const int img = m0 / plane, rem = m0 - img * plane;
-                const int oy = rem / pwid, ox = rem - oy * pwid;
-                // leftmost / topmost source coordinate of tap column 0 (fwd) -- dgrad walks its taps right to left
-                const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : (HALO ? ox + P.pad_w - hx : ox + P.pad_w);
-                const int y_org = (MODE == 0) ? oy * P.stride - P.pad_h : oy + P.pad_h;
-                const int dstep = (MODE == 0) ? P.dil : -P.dil;
-                int krow = 0;                                          // weight K index of (tr, tap column 0, part 0, block 0)
-                for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep, krow += P.kw * ktap_w)
-                    for (int ti = 0, x = x_org; ti < kwi && !dead; ++ti, x += dstep) {
-                        int kidx = krow + ti * ktap_w;
+        int s = 0;
+        uint32_t ph = 1;                                               // first pass over the ring: stages are free
+        const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
+        const int pwid = (MODE == 0) ? P.wo : P.w;
+        const int ktap_w = (MODE == 0) ? P.ktap : P.dc_kext;           // K extent of one tap in the weight matrix
+        const int kext0 = (MODE == 0) ? P.parts[0].kext : P.dc_kext, kext1 = (MODE == 0 && np > 1) ? P.parts[1].kext : 0;
+        const int dstep = (MODE == 0) ? P.dil : -P.dil;
+        const int row_k = P.kw * ktap_w;
+        bool dead = false;
+#ifdef PCB_TC_TIMING
+        long long tt_wait = 0, tt_issue = 0;
+        const long long tt0 = clock64();
+#endif
+        for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            if (!tile_active(n0)) continue;
+            const int img = m0 / plane, rem = m0 - img * plane;
+            const int oy = rem / pwid, ox = rem - oy * pwid;
+            // leftmost / topmost source coordinate of tap column 0 (fwd) -- dgrad walks its taps right to left
+            const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : (HALO ? ox + P.pad_w - hx : ox + P.pad_w);
+            const int y_org = (MODE == 0) ? oy * P.stride - P.pad_h : oy + P.pad_h;
+            int krow = 0;                                              // weight K index of (tr, tap column 0, part 0, block 0)
+            for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep, krow += row_k)
+                for (int ti = 0, x = x_org, kidx = krow; ti < kwi && !dead; ++ti, x += dstep, kidx = krow + ti * ktap_w) {
 #pragma unroll
-                        for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                            if (p >= np) break;
-                            const CUtensorMap *ma = (p == 0) ? &tmap_a0 : &tmap_a1;
-                            const int kext = (MODE == 0) ? P.parts[p].kext : P.dc_kext;
-                            for (int c0 = 0; c0 < kext; c0 += BLOCK_K, kidx += BLOCK_K) {
-                                if (!ptx::mbar_wait(bar_empty + 8 * s, ph, P.abort_flag, 121)) { dead = true; break; }
+                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                        const int kext = (p == 0) ? kext0 : kext1;
+                        const CUtensorMap *ma = (p == 0) ? &tmap_a0 : &tmap_a1;
+                        for (int c0 = 0; c0 < kext; c0 += BLOCK_K, kidx += BLOCK_K) {
+#ifdef PCB_TC_TIMING
+                            const long long tq0 = clock64();
+#endif
+                            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_empty + 8 * s, ph, P.abort_flag, 121))) { dead = true; break; }
+#ifdef PCB_TC_TIMING
+                            const long long tq1 = clock64();
+                            tt_wait += tq1 - tq0;
+#endif
+                            if (ptx::elect_one()) {
                                 const uint32_t full = bar_full + 8 * s, dst = smem_base + s * STAGE;
                                 ptx::mbar_arrive_expect_tx(full, STAGE_TX);
                                 ptx::tma_load_4d(dst, ma, c0, x, y, img, full);
-                                for (int tc = 0; tc < nB; ++tc)
-                                    ptx::tma_load_2d(dst + A_ROOM + tc * B_BYTES, &tmap_w, kidx + tc * ktap_w, n0, full);
-                                if (++s == S) { s = 0; ph ^= 1; }
+                                uint32_t bdst = dst + A_ROOM;
+                                for (int tc = 0, kb = kidx; tc < nB; ++tc, kb += ktap_w, bdst += B_BYTES)
+                                    ptx::tma_load_2d(bdst, &tmap_w, kb, n0, full);
                             }
-                            if (dead) break;
-                        }
-                    }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-            const uint32_t ready = fix ? bar_fixed : bar_full;
-            const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
-            const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_ROOM, 16, 1024);
-            const uint32_t stage16 = STAGE >> 4;
-            // dgrad walks tap columns right to left inside a halo tile
-            const int shift0 = (HALO && MODE == 1) ? hx * 8 : 0;       // in 16-byte units: one pixel row = 128 B = 8 units
-            const int dshift = HALO ? ((MODE == 1) ? -P.dil * 8 : P.dil * 8) : 0;
-            const int rows_a = P.kh * kwi;                             // (kernel row, A item) pairs per tile
-            int s = 0, tile_iter = 0;
-            uint32_t ph = 0;
-            bool dead = false;
-            long long n_items = 0;
-            const long long t_begin = clock64();
-            for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
-                const int n0 = (tile % n_tiles) * BLOCK_N;
-                if (!tile_active(n0)) continue;
-                const int acc = tile_iter & 1;
-                if (!ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 126)) { dead = true; break; }
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                uint32_t accum = 0;
-                for (int r = 0; r < rows_a && !dead; ++r) {
-#pragma unroll
-                    for (int p = 0; p < TC_MAX_PARTS; ++p) {
-                        if (p >= np) break;
-                        const int kext = (MODE == 0) ? P.parts[p].kext : P.dc_kext;
-                        const int c8 = (MODE == 0) ? P.parts[p].c8 : P.dc_c8;
-                        for (int c0 = 0; c0 < kext; c0 += BLOCK_K) {
-                            const int ksteps = min(BLOCK_K / 16, (c8 - c0 + 15) >> 4);     // K steps holding real channels
-                            if (!ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 124)) { dead = true; break; }
-                            ptx::tc_fence_after();
-                            uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16 + shift0);
-                            uint64_t db = desc_b0 + static_cast<uint64_t>(s * stage16);
-                            for (int tc = 0; tc < nB; ++tc, da += dshift, db += B_BYTES >> 4) {
-#pragma unroll
-                                for (int k = 0; k < BLOCK_K / 16; ++k)
-                                    if (k < ksteps) { ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum != 0); accum = 1; }
-                            }
-                            ptx::umma_commit(bar_empty + 8 * s);
+                            __syncwarp();
+#ifdef PCB_TC_TIMING
+                            tt_issue += clock64() - tq1;
+#endif
                             if (++s == S) { s = 0; ph ^= 1; }
-                            ++n_items;
                         }
                         if (dead) break;
                     }
                 }
-                if (!dead) ptx::umma_commit(bar_tmem_full + 8 * acc);
-                ++tile_iter;
+        }
+#ifdef PCB_TC_TIMING
+        if (P.dbg && lane == 0) { long long *d = P.dbg + 8 * blockIdx.x; d[2] = tt_wait; d[3] = tt_issue; d[4] = clock64() - tt0; }
+#endif
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        const uint32_t ready = fix ? bar_fixed : bar_full;
+        const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
+        const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_ROOM, 16, 1024);
+        const uint32_t stage16 = STAGE >> 4;
+        // dgrad walks tap columns right to left inside a halo tile
+        const int shift0 = (HALO && MODE == 1) ? hx * 8 : 0;           // in 16-byte units: one pixel row = 128 B = 8 units
+        const int dshift = HALO ? ((MODE == 1) ? -P.dil * 8 : P.dil * 8) : 0;
+        const int rows_a = P.kh * kwi;                                 // (kernel row, A item) pairs per tile
+        // per part: K blocks, and the K steps of the last block that hold real channels (channel padding is skipped)
+        int nb0, nb1 = 0, kl0, kl1 = 4;
+        {
+            const int kext = (MODE == 0) ? P.parts[0].kext : P.dc_kext, c8 = (MODE == 0) ? P.parts[0].c8 : P.dc_c8;
+            nb0 = kext / BLOCK_K; kl0 = min(4, (c8 - (nb0 - 1) * BLOCK_K + 15) >> 4);
+            if (MODE == 0 && np > 1) { nb1 = P.parts[1].kext / BLOCK_K; kl1 = min(4, (P.parts[1].c8 - (nb1 - 1) * BLOCK_K + 15) >> 4); }
+        }
+        int s = 0, tile_iter = 0;
+        uint32_t ph = 0;
+        bool dead = false;
+        long long n_items = 0;
+        long long tm_wait = 0, tm_acc = 0, tm_issue = 0, tm_commit = 0;
+        const long long t_begin = clock64();
+        for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+            const int n0 = (tile % n_tiles) * BLOCK_N;
+            if (!tile_active(n0)) continue;
+            const int acc = tile_iter & 1;
+#ifdef PCB_TC_TIMING
+            const long long ta0 = clock64();
+#endif
+            // the epilogue must have drained this accumulator stage (two tiles ago)
+            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 126))) { dead = true; break; }
+#ifdef PCB_TC_TIMING
+            tm_acc += clock64() - ta0;
+#endif
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t accum = 0;
+            for (int r = 0; r < rows_a && !dead; ++r) {
+#pragma unroll
+                for (int p = 0; p < TC_MAX_PARTS; ++p) {
+                    const int nbp = (p == 0) ? nb0 : nb1, klast = (p == 0) ? kl0 : kl1;
+                    for (int cb = 0; cb < nbp; ++cb) {
+#ifdef PCB_TC_TIMING
+                        const long long tq0 = clock64();
+#endif
+                        if (!__all_sync(0xffffffffu, ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 124))) { dead = true; break; }
+#ifdef PCB_TC_TIMING
+                        const long long tq1 = clock64();
+                        tm_wait += tq1 - tq0;
+#endif
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16 + shift0), db = desc_b0 + static_cast<uint64_t>(s * stage16);
+                            if (cb + 1 < nbp || klast == 4) {
+                                for (int tc = 0; tc < nB; ++tc, da += dshift, db += B_BYTES >> 4) {
+                                    ptx::umma_bf16(d_tmem, da, db, idesc, (accum | tc) != 0);
+                                    ptx::umma_bf16_acc(d_tmem, da + 2, db + 2, idesc);
+                                    ptx::umma_bf16_acc(d_tmem, da + 4, db + 4, idesc);
+                                    ptx::umma_bf16_acc(d_tmem, da + 6, db + 6, idesc);
+                                }
+                            } else {
+                                for (int tc = 0; tc < nB; ++tc, da += dshift, db += B_BYTES >> 4)
+                                    for (int k = 0; k < klast; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (accum | tc | k) != 0);
+                            }
+                            ptx::umma_commit(bar_empty + 8 * s);
+                        }
+                        __syncwarp();
+#ifdef PCB_TC_TIMING
+                        tm_issue += clock64() - tq1;
+#endif
+                        accum = 1;
+                        if (++s == S) { s = 0; ph ^= 1; }
+                        ++n_items;
+                    }
+                    if (dead) break;
+                }
             }
-            if (P.dbg) {
-                long long *d = P.dbg + 8 * blockIdx.x;
-                d[0] = clock64() - t_begin; d[1] = 0; d[2] = 0; d[3] = 0; d[4] = 0; d[5] = tile_iter; d[6] = n_items; d[7] = n_items;
-            }
+            if (!dead && ptx::elect_one()) ptx::umma_commit(bar_tmem_full + 8 * acc);
+            __syncwarp();
+            ++tile_iter;
+        }
+        if (P.dbg && lane == 0) {
+            long long *d = P.dbg + 8 * blockIdx.x;
+            d[0] = clock64() - t_begin; d[1] = tm_wait; d[5] = tile_iter; d[6] = n_items; d[7] = tm_acc; P.dbg[8 * 1024 + 2 * blockIdx.x] = tm_issue; P.dbg[8 * 1024 + 2 * blockIdx.x + 1] = tm_commit;
         }
     } else if (warp < 6) {
         // ================================ fixers: zero the hole rows of every landed A tile ================================
@@ -1370,7 +1424,7 @@ int halo_hg(const pcb_conv *c, bool rowpack) {
 // PCB_TC_DEBUG_TIMING=1: every forward/dgrad launch synchronises and prints where its MMA threads spent their cycles
 long long *debug_buffer() {
     static long long *buf = nullptr;
-    if (!buf && getenv("PCB_TC_DEBUG_TIMING")) cudaMalloc(&buf, sizeof(long long) * 8 * 1024);
+    if (!buf && getenv("PCB_TC_DEBUG_TIMING")) cudaMalloc(&buf, sizeof(long long) * 10 * 1024);
     return buf;
 }
 
@@ -1469,8 +1523,17 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
         static long long h[8 * 1024];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, P.dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
-        double tot = 0, tiles = 0, items = 0;
-        for (int i = 0; i < grid; ++i) { tot += h[8*i]; tiles += h[8*i+5]; items += h[8*i+6]; }
+        double tot = 0, tiles = 0, items = 0, mw = 0, tw = 0, ti = 0, ma = 0, mi = 0, mc = 0;
+        for (int i = 0; i < grid; ++i) { tot += h[8*i]; tiles += h[8*i+5]; items += h[8*i+6]; mw += h[8*i+1]; tw += h[8*i+2]; ti += h[8*i+3]; ma += h[8*i+7]; }
+#ifdef PCB_TC_TIMING
+        {
+            static long long h2[2 * 1024];
+            cudaMemcpy(h2, P.dbg + 8 * 1024, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
+            for (int i = 0; i < grid; ++i) { mi += h2[2*i]; mc += h2[2*i+1]; }
+        }
+        fprintf(stderr, "[tc-timing]   per item: MMA thread: wait data %.0f, wait accumulator %.0f, issue MMAs %.0f, commit %.0f | TMA thread: wait free stage %.0f, issue %.0f\n",
+                mw / std::max(1.0, items), ma / std::max(1.0, items), mi / std::max(1.0, items), mc / std::max(1.0, items), tw / std::max(1.0, items), ti / std::max(1.0, items));
+#endif
         fprintf(stderr, "[tc-timing] TMA mode=%d halo=%d N=%d cin=%d cout=%d %dx%d s%d grid=%d stages=%d(%zu B) fix=%d tiles/cta=%.1f items/tile=%.1f | per-CTA cycles %.0f | per item %.0f cyc = %.0f per tap\n",
                 MODE, (int)HALO, BLOCK_N, P.cin, P.cout, P.h, P.w, P.stride, grid, P.stages, stage, P.use_fix, tiles / grid, items / std::max(1.0, tiles), tot / grid,
                 tot / std::max(1.0, items), tot / std::max(1.0, items) / nb);

@@ -110,6 +110,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// same with the accumulate flag known at compile time (no predicate plumbing in the issuing thread's instruction stream)
+__device__ __forceinline__ void umma_bf16_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+// keep a value in a register: the compiler may not rematerialise it from constant memory (a lone thread pays the full
+// ~50-cycle LDC latency for every such reload inside its per-K-block loop)
+#define PCB_PIN(x) asm volatile("" : "+r"(x))
 // all previously issued MMAs of this thread complete -> one arrival on `bar`
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
