@@ -219,7 +219,7 @@ def layer_profile(ts, x, mask, peaks, verbose):
     fl, ms, n = dom[1]
     achieved = fl / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    return {"bound": "tensor", "kernel": {"tc_fwd": "pconv_tc_kernel<MODE=0>", "tc_dgrad": "pconv_tc_kernel<MODE=1>",
+    return {"bound": "tensor", "kernel": {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ pconv_tc_persistent_kernel for the stem)", "tc_dgrad": "pconv_tc_tma_kernel<MODE=1>",
                                           "tc_wgrad": "pconv_tc_wgrad_kernel"}[dom[0]],
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",

@@ -107,6 +107,10 @@ CONV_CASES = {
     "tma_k3_s2_128_256_box_n": (128, 256, 3, 2, 1, 1, 1, False, True, 4, 8, 8, BF, "uniform", "pc"),
     "tma_k3_64_256_n256": (64, 256, 3, 1, 1, 1, 1, False, False, 2, 128, 128, BF, "uniform", "pc"),
     "tma_plain_1x1_128_64": (128, 64, 1, 1, 0, 1, 1, True, False, 2, 16, 16, BF, "uniform", "1x1"),
+    # stride-2 data gradient = four stride-1 parity classes on the half-resolution grid (row-halo tiles when w/2 >= 128)
+    "tma_k5_s2_halo_dgrad_w256": (64, 64, 5, 2, 2, 1, 1, False, True, 1, 8, 256, BF, "uniform", "pc"),
+    "tma_k3_s2_halo_dgrad_w256": (64, 128, 3, 2, 1, 1, 1, True, True, 1, 4, 256, BF, "uniform", "pc"),
+    "tma_k7_s2_64_64": (64, 64, 7, 2, 3, 1, 1, False, True, 2, 16, 32, BF, "uniform", "pc"),
 }
 PADDED_X = {"tc_stem_rowpack_k7_s2", "tc_rowpack_k5_d2_cin4"}
 

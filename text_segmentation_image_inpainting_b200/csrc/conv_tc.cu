@@ -73,6 +73,10 @@ struct TcParams {
     long long *dbg;           // optional [grid][8] cycle counters written by the MMA thread (PCB_TC_DEBUG_TIMING)
     // TMA-fed kernel: the 128 pixels of an M tile form the box {box_w, box_h, box_n} of the (x, y, image) pixel grid
     int box_w, box_h, box_n, stages, use_fix;
+    int wk_base, wk_row, wk_col;   // weight-matrix K index of tap (a, b) of this launch: wk_base + a*wk_row + b*wk_col (+ part / block offset)
+    // dgrad output addressing: the tile grid (h, w above) is every `sub`-th pixel of the full-resolution [fh, fw] gradient,
+    // starting at (py, px) -- sub = 2 for the parity classes of a stride-2 layer, 1 otherwise
+    int sub, py, px, fh, fw;
 };
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
@@ -94,8 +98,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                     inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
                 }
                 int en = 0, eh = 0, ew = 0;
+                long long mo = m;                         // dgrad: pixel index in the full-resolution gradient
                 if (MODE == 1 && rvalid) {
                     en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
+                    eh = eh * P.sub + P.py; ew = ew * P.sub + P.px;
+                    mo = (static_cast<long long>(en) * P.fh + eh) * P.fw + ew;
                 }
     #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -114,10 +121,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                             const TcPart &pt = P.parts[p];
                             const int local = col - pt.koff;
                             if (local >= 0 && local < pt.kext && pt.dx != nullptr && local < pt.c8 && rvalid) {
-                                orow = pt.dx + static_cast<long long>(m) * pt.dx_cstride + local;
+                                orow = pt.dx + mo * pt.dx_cstride + local;
                                 nstore = min(32, pt.c8 - local);
                                 if (pt.mask != nullptr)          // dx = acc * input mask of this part
-                                    scale = pt.mask[(static_cast<long long>(en) * (P.h >> pt.mup) + (eh >> pt.mup)) * (P.w >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
+                                    scale = pt.mask[(static_cast<long long>(en) * (P.fh >> pt.mup) + (eh >> pt.mup)) * (P.fw >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
                             }
                         }
                     }
@@ -660,10 +667,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         uint32_t ph = 1;                                               // first pass over the ring: stages are free
         const int plane = (MODE == 0) ? P.ho * P.wo : P.h * P.w;
         const int pwid = (MODE == 0) ? P.wo : P.w;
-        const int ktap_w = (MODE == 0) ? P.ktap : P.dc_kext;           // K extent of one tap in the weight matrix
         const int kext0 = (MODE == 0) ? P.parts[0].kext : P.dc_kext, kext1 = (MODE == 0 && np > 1) ? P.parts[1].kext : 0;
         const int dstep = (MODE == 0) ? P.dil : -P.dil;
-        const int row_k = P.kw * ktap_w;
+        const int row_k = P.wk_row, col_k = P.wk_col;
         bool dead = false;
 #ifdef PCB_TC_TIMING
         long long tt_wait = 0, tt_issue = 0;
@@ -677,9 +683,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             // leftmost / topmost source coordinate of tap column 0 (fwd) -- dgrad walks its taps right to left
             const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : (HALO ? ox + P.pad_w - hx : ox + P.pad_w);
             const int y_org = (MODE == 0) ? oy * P.stride - P.pad_h : oy + P.pad_h;
-            int krow = 0;                                              // weight K index of (tr, tap column 0, part 0, block 0)
+            int krow = P.wk_base;                                      // weight K index of (tr, tap column 0, part 0, block 0)
             for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep, krow += row_k)
-                for (int ti = 0, x = x_org, kidx = krow; ti < kwi && !dead; ++ti, x += dstep, kidx = krow + ti * ktap_w) {
+                for (int ti = 0, x = x_org, kidx = krow; ti < kwi && !dead; ++ti, x += dstep, kidx = krow + ti * col_k) {
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) {
                         const int kext = (p == 0) ? kext0 : kext1;
@@ -698,7 +704,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                                 ptx::mbar_arrive_expect_tx(full, STAGE_TX);
                                 ptx::tma_load_4d(dst, ma, c0, x, y, img, full);
                                 uint32_t bdst = dst + A_ROOM;
-                                for (int tc = 0, kb = kidx; tc < nB; ++tc, kb += ktap_w, bdst += B_BYTES)
+                                for (int tc = 0, kb = kidx; tc < nB; ++tc, kb += col_k, bdst += B_BYTES)
                                     ptx::tma_load_2d(bdst, &tmap_w, kb, n0, full);
                             }
                             __syncwarp();
@@ -1410,6 +1416,7 @@ void base_params(TcParams &P, const pcb_conv *c, const Layout &L) {
     P.n = c->n; P.h = c->h; P.w = c->w; P.cin = c->cin; P.cout = c->cout; P.kh = c->kh; P.kw = c->kw; P.stride = c->stride;
     P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo;
     P.nparts = c->nparts; P.no_guard = c->no_guard; P.rowpack = L.rowpack; P.ktap = L.ktap;
+    P.sub = 1; P.py = 0; P.px = 0; P.fh = c->h; P.fw = c->w;
 }
 
 // row-halo eligibility: stride 1, output rows made of whole groups of 8 pixels, halo small enough
@@ -1491,6 +1498,14 @@ bool tma_dgrad_ok(const pcb_conv *c) {
     if (getenv("PCB_DISABLE_TMA") || is_rowpack(c) || c->stride != 1) return false;
     int bw, bh, bn;
     return tile_box(c->w, c->h, &bw, &bh, &bn);
+}
+
+// stride-2 data gradient as four stride-1 parity-class problems (see pcb_tc_dgrad)
+bool tma_dgrad_s2_ok(const pcb_conv *c) {
+    if (getenv("PCB_DISABLE_TMA") || getenv("PCB_DISABLE_TMA_S2") || is_rowpack(c)) return false;
+    if (c->stride != 2 || c->dil != 1 || c->kh < 2 || c->kw < 2 || ((c->h | c->w) & 1) || c->ho != c->h / 2 || c->wo != c->w / 2) return false;
+    int bw, bh, bn;
+    return tile_box(c->w / 2, c->h / 2, &bw, &bh, &bn);
 }
 
 size_t up_bytes(const pcb_conv *c, int p) {
@@ -1661,6 +1676,7 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
         }
         if (c->nparts < 2) ta[1] = ta[0];
         P.ncols = (bn == 32) ? 32 : L.rows_f;
+        P.wk_base = 0; P.wk_col = L.ktap; P.wk_row = c->kw * L.ktap;
         if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, bn)) return rc;
         return launch_tma<0>(P, tm, ta[0], ta[1], bn, halo, st);
     }
@@ -1699,10 +1715,39 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
         bn = pick_bn(L.ktap, m_total);
         if (bn == 32) bn = 64;
         const bool halo = tma_halo_ok(c, P.box_w, P.box_h, P.box_n, bn);
+        P.wk_base = 0; P.wk_col = L.cout64; P.wk_row = c->kw * L.cout64;
         CUtensorMap ta;
         if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, P.box_w + (halo ? (c->kw - 1) * c->dil : 0), P.box_h, P.box_n, 1)) return rc;
         if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
         return launch_tma<1>(P, tm, ta, ta, bn, halo, st);
+    }
+    if (tma_dgrad_s2_ok(c)) {
+        // Stride 2: an input pixel (y, x) only sees the taps with (y + pad - tr) even, so the four parity classes
+        // (y & 1, x & 1) are four independent STRIDE-1 problems on the half-resolution grid -- which is dc's own grid --
+        // each with its subset of taps (3x3 / 3x2 / 2x3 / 2x2 for a 5x5 kernel) and no multiplications by inserted zeros.
+        const int hh = c->h / 2, hw = c->w / 2;
+        const long long m_class = static_cast<long long>(c->n) * hh * hw;
+        tile_box(hw, hh, &P.box_w, &P.box_h, &P.box_n);
+        bn = pick_bn(L.ktap, m_class);
+        if (bn == 32) bn = 64;
+        if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
+        for (int cls = 0; cls < 4; ++cls) {
+            TcParams Q = P;
+            const int py = cls >> 1, px = cls & 1;
+            const int tr0 = (py + c->pad_h) & 1, tc0 = (px + c->pad_w) & 1;
+            Q.kh = (c->kh - tr0 + 1) / 2; Q.kw = (c->kw - tc0 + 1) / 2;
+            Q.pad_h = (py + c->pad_h - tr0) / 2; Q.pad_w = (px + c->pad_w - tc0) / 2;
+            Q.h = hh; Q.w = hw; Q.stride = 1; Q.dil = 1;
+            Q.m_total = static_cast<int>(m_class);
+            Q.sub = 2; Q.py = py; Q.px = px; Q.fh = c->h; Q.fw = c->w;
+            Q.wk_base = (tr0 * c->kw + tc0) * L.cout64; Q.wk_row = 2 * c->kw * L.cout64; Q.wk_col = 2 * L.cout64;
+            const size_t stage = (static_cast<size_t>(128 + (Q.kw - 1)) * 128 + 1023) / 1024 * 1024 + static_cast<size_t>(Q.kw) * bn * 128;
+            const bool halo = !getenv("PCB_DISABLE_TMA_HALO") && Q.box_w == 128 && Q.box_h == 1 && Q.box_n == 1 && Q.kw >= 2 && 3 * stage <= 208 * 1024;
+            CUtensorMap ta;
+            if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, Q.box_w + (halo ? Q.kw - 1 : 0), Q.box_h, Q.box_n, 1)) return rc;
+            if (int rc = launch_tma<1>(Q, tm, ta, ta, bn, halo, st)) return rc;
+        }
+        return 0;
     }
     if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
     P.hg = halo_hg(c, L.rowpack);
