@@ -1596,6 +1596,13 @@ int launch_tc(TcParams &P, const CUtensorMap &tm, int bn, cudaStream_t st) {
 
 }  // namespace
 
+static bool smallco_ok(const pcb_conv *c) { return common_ok(c) && !is_rowpack(c) && pcb_smallco_eligible(c); }
+static pcb_smallco_layout smallco_layout(const Layout &L) {
+    pcb_smallco_layout S;
+    S.ktap = L.ktap; S.koff[0] = L.koff[0]; S.koff[1] = L.koff[1]; S.cout64 = L.cout64; S.kf = L.kf; S.kd = L.kd;
+    return S;
+}
+
 // ---- eligibility / layouts -----------------------------------------------------------------------
 bool pcb_tc_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
 
@@ -1640,8 +1647,9 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(y_cstride % 8 == 0 && y_cstride >= c->cout, "tensor-core forward: y channel stride must be a multiple of 8 and >= cout");
-    if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     const Layout L = layout_of(c);
+    if (smallco_ok(c)) return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
+    if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     TcParams P;
     base_params(P, c, L);
     P.m_total = static_cast<int>(m_total);
@@ -1695,6 +1703,7 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= rup(c->cout, 8), "tensor-core dgrad: dc channel stride must be a multiple of 8");
     const Layout L = layout_of(c);
+    if (smallco_ok(c)) return pcb_smallco_dgrad(c, smallco_layout(L), dc, dc_cstride, w_dgrad, dx, dx_cstride, st);
     TcParams P;
     base_params(P, c, L);
     P.m_total = static_cast<int>(m_total);
@@ -1786,6 +1795,7 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= c->cout, "tensor-core wgrad: dc channel stride must be a multiple of 8");
+    if (smallco_ok(c)) return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, st);
     uint64_t *tapmask = static_cast<uint64_t *>(workspace);
     if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     const size_t dw_bytes = sizeof(float) * c->cout * c->kh * c->kw * c->cin;

@@ -130,6 +130,14 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
                  cudaStream_t st);
 int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, cudaStream_t st);
 int pcb_tc_read_abort_flag(int *value);
+// layers with <= 8 output channels (conv_smallco.cu); weights are read from the tensor-core operand layouts
+struct pcb_smallco_layout { int ktap, koff[2], cout64; long long kf, kd; };
+bool pcb_smallco_eligible(const pcb_conv *c);
+int pcb_smallco_forward(const pcb_conv *c, const pcb_smallco_layout &L, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
+                        cudaStream_t st);
+int pcb_smallco_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
+                      cudaStream_t st);
+int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, float *dw, cudaStream_t st);
 // depthwise fast path (dwconv.cu)
 bool pcb_dw_eligible(const pcb_conv *c);
 int pcb_dw_weight_prepare(const pcb_conv *c, const float *w_master, void *w_t, cudaStream_t st);
