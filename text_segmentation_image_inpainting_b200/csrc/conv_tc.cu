@@ -976,6 +976,8 @@ struct WgParams {
     int kb_per_split;
     float *dw;                // [cout][kh*kw][cin] fp32, pre-zeroed
     int *abort_flag;
+    // TMA-fed kernel: a K block of 64 consecutive output pixels is the box {box_w, box_h, box_n}; use_fix: some part has holes
+    int box_w, box_h, box_n, stages, use_fix;
 };
 
 template <int BLOCK_N, int T, int STAGES>
@@ -1203,6 +1205,226 @@ pconv_tc_wgrad_kernel(const __grid_constant__ WgParams P, const __grid_constant_
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// weight gradient, TMA-FED.  Same GEMM as pconv_tc_wgrad_kernel (D[ci][co] per tap, K = output pixels, split-K with fp32
+// red.global.add) but the gathered operand is no longer gathered: a K block of 64 consecutive output pixels is a box of the
+// pixel grid, so the x rows of tap (tr, tc) / 64-channel block are one 4-D TMA tile (padding = out-of-range zero fill,
+// stride-2 layers = traversal stride), written as exactly the MN-major 128B-swizzled block UMMA reads.  Holes are zeroed
+// in the landed tile by four fixer warps (the tap-validity words of the block's pixels), which then run the epilogue.
+//   HALO (stride 1, K block = one image-row segment): a CTA owns one kernel ROW; one tile of 64 + (kw-1)*dil pixel rows per
+//   channel block serves the kw taps of the row through row-shifted descriptors (T = kw accumulators in TMEM).
+//   otherwise: a CTA owns T taps, one tile per tap.
+//   warp 0 TMA producer | warp 1 MMA issuer (+ TMEM alloc) | warps 2-5 fixers, then epilogue
+// -------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;
+
+template <int BLOCK_N, int T, bool HALO>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+pconv_tc_wgrad_tma_kernel(const __grid_constant__ WgParams P, const __grid_constant__ CUtensorMap tmap_dc,
+                          const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
+    constexpr uint32_t B_BYTES = BLOCK_N * 128;               // [64 px][BLOCK_N co] as BLOCK_N/64 blocks of 8 KB
+    constexpr int TMEM_COLS = (T * BLOCK_N <= 64) ? 64 : (T * BLOCK_N <= 128) ? 128 : (T * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(T * BLOCK_N <= 512, "TMEM overflow");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
+    uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const int S = P.stages;
+    const int hx = HALO ? (P.kw - 1) * P.dil : 0;
+    const int rows_a = 64 + hx;                                // pixel rows of one A block
+    const uint32_t A_BLK = (static_cast<uint32_t>(rows_a) * 128u + 1023u) & ~1023u;
+    const uint32_t A_BYTES = (HALO ? 1 : T) * 2 * A_BLK;       // per stage: [tap][channel block]
+    const uint32_t STAGE = A_BYTES + B_BYTES;
+    const uint32_t sBar = smem_base + S * STAGE;
+    const uint32_t bar_full = sBar, bar_fixed = sBar + 8 * MAX_RING, bar_empty = sBar + 16 * MAX_RING, bar_tmem_full = sBar + 24 * MAX_RING;
+    const uint32_t s_tmem_ptr = bar_tmem_full + 8;
+    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_gen + (s_tmem_ptr - smem_base));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    // blockIdx.x = ((co_tile * tap_groups) + tap_group) * ci_tiles + ci_tile ; blockIdx.y = K split
+    int bx = blockIdx.x;
+    const int ci_tile = bx % P.ci_tiles; bx /= P.ci_tiles;
+    const int tap_group = bx % P.tap_groups;
+    const int co_tile = bx / P.tap_groups;
+    const int taps_full = P.kh * P.kw;
+    const int tap0 = tap_group * T;                             // HALO: tap_group = kernel row, T = kw
+    const int ntap = HALO ? T : min(T, taps_full - tap0);
+    const int n0 = co_tile * BLOCK_N;
+    const int total_kb = (P.m_total + 63) / 64;
+    const int kb_begin = blockIdx.y * P.kb_per_split;
+    const int num_kb = max(0, min(total_kb, kb_begin + P.kb_per_split) - kb_begin);
+    // the two 64-channel blocks of this M tile: part and first channel (-1: block does not exist)
+    int blk_part[2], blk_c0[2];
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        const int kpos = ci_tile * 128 + hb * 64;
+        blk_part[hb] = -1; blk_c0[hb] = 0;
+        for (int p = 0; p < P.nparts; ++p)
+            if (kpos >= P.parts[p].koff && kpos < P.parts[p].koff + P.parts[p].kext && kpos - P.parts[p].koff < P.parts[p].c8) {
+                blk_part[hb] = p; blk_c0[hb] = kpos - P.parts[p].koff;
+            }
+    }
+    const int nblk = (blk_part[0] >= 0 ? 1 : 0) + (blk_part[1] >= 0 ? 1 : 0);
+    const bool fix = P.use_fix != 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_RING; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_fixed + 8 * s, 4); ptx::mbar_init(bar_empty + 8 * s, 1); }
+        ptx::mbar_init(bar_tmem_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_dc); ptx::prefetch_tmap(&tmap_a0); ptx::prefetch_tmap(&tmap_a1); }
+    if (warp == 1) {
+        ptx::tmem_alloc<TMEM_COLS>(s_tmem_ptr);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        const int plane = P.ho * P.wo;
+        const uint32_t tx_bytes = static_cast<uint32_t>((HALO ? 1 : ntap) * nblk * rows_a * 128) + B_BYTES;
+        int s = 0;
+        uint32_t ph = 1;
+        for (int it = 0; it < num_kb; ++it) {
+            const int m0 = (kb_begin + it) * 64;
+            const int img = m0 / plane, rem = m0 - img * plane;
+            const int oy = rem / P.wo, ox = rem - oy * P.wo;
+            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_empty + 8 * s, ph, P.abort_flag, 221))) break;
+            if (ptx::elect_one()) {
+                const uint32_t full = bar_full + 8 * s, dst = smem_base + s * STAGE;
+                ptx::mbar_arrive_expect_tx(full, tx_bytes);
+                for (int tl = 0; tl < (HALO ? 1 : ntap); ++tl) {
+                    const int tap = tap0 + tl;
+                    const int tr = HALO ? tap_group : tap / P.kw, tc = HALO ? 0 : tap - tr * P.kw;
+                    const int y = oy * P.stride - P.pad_h + tr * P.dil, x = ox * P.stride - P.pad_w + tc * P.dil;
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb)
+                        if (blk_part[hb] >= 0)
+                            ptx::tma_load_4d(dst + (tl * 2 + hb) * A_BLK, blk_part[hb] == 0 ? &tmap_a0 : &tmap_a1, blk_c0[hb], x, y, img, full);
+                }
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                    ptx::tma_load_2d(dst + A_BYTES + j * 8192, &tmap_dc, n0 + j * 64, m0, full);
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer: both operands MN-major ================================
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N, 1, 1);
+        const uint32_t ready = fix ? bar_fixed : bar_full;
+        const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, A_BLK, 1024);      // LBO = distance between the two 64-channel blocks
+        const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_BYTES, 8192, 1024);
+        const uint32_t stage16 = STAGE >> 4;
+        const uint32_t tap16 = HALO ? static_cast<uint32_t>(P.dil * 8) : (2 * A_BLK) >> 4;   // per tap: row shift (halo) or next tile
+        int s = 0;
+        uint32_t ph = 0;
+        bool dead = false;
+        for (int it = 0; it < num_kb; ++it) {
+            if (!__all_sync(0xffffffffu, ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 224))) { dead = true; break; }
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16);
+                const uint64_t db = desc_b0 + static_cast<uint64_t>(s * stage16);
+                for (int tl = 0; tl < ntap; ++tl, da += tap16) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)                  // 16 pixels (two 8-row atoms = 2048 bytes) per step
+                        ptx::umma_bf16(tmem_base + tl * BLOCK_N, da + 128 * k, db + 128 * k, idesc, (it | k) != 0);
+                }
+                ptx::umma_commit(bar_empty + 8 * s);
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        if (!dead && num_kb > 0 && ptx::elect_one()) ptx::umma_commit(bar_tmem_full);
+        __syncwarp();
+    } else {
+        // ================================ fixers (hole rows -> 0), then epilogue ================================
+        const int f = (warp - 2) * 32 + lane;                   // pixel row of the A blocks owned by this thread
+        bool dead = false;
+        if (fix) {
+            // tap-validity word of the output pixel that looks at this row (halo rows past 63 belong to a later tap column)
+            int jpix = f, tcs = 0;
+            if (HALO && f > 63) { tcs = (f - 63 + P.dil - 1) / P.dil; jpix = f - tcs * P.dil; }
+            const bool row_used = f < rows_a;
+            uint64_t wnext[2];
+            auto load_words = [&](int kb) {
+                const int m = kb * 64 + jpix;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb)
+                    wnext[hb] = (row_used && blk_part[hb] >= 0 && m < P.m_total && kb < kb_begin + num_kb) ? __ldg(P.parts[blk_part[hb]].tapmask + m) : 0ull;
+            };
+            load_words(kb_begin);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < num_kb; ++it) {
+                const uint64_t w0 = wnext[0], w1 = wnext[1];
+                load_words(kb_begin + it + 1);
+                if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 222))) { dead = true; break; }
+                bool wrote = false;
+                if (row_used) {
+                    for (int tl = 0; tl < (HALO ? 1 : ntap); ++tl) {
+                        const int bit = HALO ? tap_group * P.kw + tcs : tap0 + tl;
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            if (blk_part[hb] < 0) continue;
+                            if ((((hb ? w1 : w0) >> bit) & 1ull) == 0ull) {
+                                uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + (tl * 2 + hb) * A_BLK + f * 128);
+                                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) r[k] = z;
+                                wrote = true;
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, wrote)) ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+        // ---- epilogue: D[ci][co] per tap -> red.global.add into dw[co][tap][ci]
+        if (!dead && num_kb > 0 && ptx::mbar_wait(bar_tmem_full, 0, P.abort_flag, 223)) {
+            ptx::tc_fence_after();
+            const int q = warp & 3;                               // TMEM lane quarter this warp may read
+            const int row = q * 32 + lane;
+            const int kpos = ci_tile * 128 + row;
+            int ci = -1;
+            for (int p = 0; p < P.nparts; ++p) {
+                const int local = kpos - P.parts[p].koff;
+                if (local >= 0 && local < P.parts[p].c) ci = P.parts[p].choff + local;
+            }
+            for (int tl = 0; tl < ntap; ++tl) {
+                const int tap = tap0 + tl;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * BLOCK_N + c0, r);
+                    ptx::tmem_ld_wait();
+                    if (ci >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = n0 + c0 + j;
+                            if (co < P.cout) atomicAdd(P.dw + (static_cast<long long>(co) * taps_full + tap) * P.cin + ci, __uint_as_float(r[j]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
     }
@@ -1606,9 +1828,11 @@ static pcb_smallco_layout smallco_layout(const Layout &L) {
 // ---- eligibility / layouts -----------------------------------------------------------------------
 bool pcb_tc_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DISABLE_TC"); }
 
+static bool tma_wgrad_ok(const pcb_conv *c);
+
 size_t pcb_tc_workspace(const pcb_conv *c) {
     size_t bytes = tapmask_bytes(c);
-    if (tma_fwd_ok(c))                                   // dense copies of the 2x-upsampled sources (TMA cannot replicate pixels)
+    if (tma_fwd_ok(c) || tma_wgrad_ok(c))                // dense copies of the 2x-upsampled sources (TMA cannot replicate pixels)
         for (int p = 0; p < c->nparts; ++p)
             if (c->parts[p].x_up) bytes += up_bytes(c, p);
     return bytes;
@@ -1763,6 +1987,59 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     return launch_tc<1>(P, tm, bn, st);
 }
 
+
+// ---- TMA-fed weight gradient ---------------------------------------------------------------------
+// 64 consecutive pixels of a [n][ht][wt] grid as a box {bw, bh, bn}
+static bool kblock_box(int wt, int ht, int *bw, int *bh, int *bn) {
+    if (wt < 4) return false;
+    if (wt % 64 == 0) { *bw = 64; *bh = 1; *bn = 1; return true; }
+    if (64 % wt) return false;
+    const int rows = 64 / wt;
+    *bw = wt;
+    if (ht % rows == 0) { *bh = rows; *bn = 1; return true; }
+    if (rows % ht) return false;
+    *bh = ht; *bn = rows / ht;
+    return true;
+}
+
+static bool tma_wgrad_ok(const pcb_conv *c) {
+    if (getenv("PCB_DISABLE_TMA") || getenv("PCB_DISABLE_TMA_WGRAD") || is_rowpack(c) || c->stride > 2) return false;
+    int bw, bh, bn;
+    if (!kblock_box(c->wo, c->ho, &bw, &bh, &bn)) return false;
+    for (int p = 0; p < c->nparts; ++p)
+        if (c->parts[p].x_up && ((c->h | c->w) & 1)) return false;
+    return true;
+}
+
+template <int BLOCK_N, int T, bool HALO>
+int launch_wgrad_tma(WgParams &P, const CUtensorMap &tdc, const CUtensorMap &ta0, const CUtensorMap &ta1, cudaStream_t st) {
+    const size_t a_blk = (static_cast<size_t>(64 + (HALO ? (P.kw - 1) * P.dil : 0)) * 128 + 1023) / 1024 * 1024;
+    const size_t stage = (HALO ? 1 : T) * 2 * a_blk + static_cast<size_t>(BLOCK_N) * 128;
+    P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (200 * 1024) / stage));
+    PCB_CHECK(P.stages >= 2, "TMA-fed wgrad: stage of %zu bytes does not fit twice", stage);
+    const size_t smem = 1024 + P.stages * stage + 24 * MAX_RING + 64;
+    auto kern = pconv_tc_wgrad_tma_kernel<BLOCK_N, T, HALO>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    P.tap_groups = HALO ? P.kh : (P.kh * P.kw + T - 1) / T;
+    P.ci_tiles = (P.ktap + 127) / 128;
+    const int co_tiles = (P.cout + BLOCK_N - 1) / BLOCK_N;
+    const int base_ctas = co_tiles * P.tap_groups * P.ci_tiles;
+    const int total_kb = (P.m_total + 63) / 64;
+    int splits = (2 * pcb_num_sms() + base_ctas - 1) / base_ctas;      // one CTA per SM at a time: ~2 waves
+    splits = std::max(1, std::min(splits, total_kb));
+    splits = std::min(splits, 65535);
+    P.kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + P.kb_per_split - 1) / P.kb_per_split;
+    dim3 grid(base_ctas, splits);
+    kern<<<grid, WG_THREADS, smem, st>>>(P, tdc, ta0, ta1);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int BLOCK_N, int T, int STAGES>
 static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream_t st) {
     constexpr size_t smem = 1024 + STAGES * (T * 16384 + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
@@ -1810,6 +2087,40 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
     P.dw = dw; P.abort_flag = flag;
     CUtensorMap tm;
     if (int rc = make_tmap_2d(&tm, dc, m_total, c->cout, dc_cstride, 64)) return rc;
+    if (tma_wgrad_ok(c)) {
+        kblock_box(c->wo, c->ho, &P.box_w, &P.box_h, &P.box_n);
+        const bool halo = !getenv("PCB_DISABLE_TMA_HALO") && c->stride == 1 && c->kw == 3 && P.box_w == 64 && P.box_h == 1 && P.box_n == 1 &&
+                          64 + 2 * c->dil <= 256;
+        const int hx = halo ? (c->kw - 1) * c->dil : 0;
+        CUtensorMap ta[TC_MAX_PARTS];
+        memset(ta, 0, sizeof(ta));
+        uint8_t *extra = reinterpret_cast<uint8_t *>(workspace) + tapmask_bytes(c);
+        for (int p = 0; p < c->nparts; ++p) {
+            const pcb_part &pt = c->parts[p];
+            const void *src = pt.x;
+            long long cs = pt.x_cstride;
+            const int c8 = rup(pt.c, 8);
+            if (pt.x_up) {
+                const long long pix = static_cast<long long>(c->n) * (c->h >> 1) * (c->w >> 1);
+                const long long work = pix * (c8 >> 3);
+                const int grid = static_cast<int>(std::min<long long>((work + 255) / 256, 16ll * pcb_num_sms()));
+                upsample_part_kernel<<<grid, 256, 0, st>>>(static_cast<const bf16 *>(pt.x), pt.x_cstride, c8, pix, c->h >> 1, c->w >> 1, reinterpret_cast<bf16 *>(extra));
+                PCB_LAUNCH_CHECK();
+                src = extra; cs = c8;
+                extra += up_bytes(c, p);
+            }
+            if (pt.mask) P.use_fix = 1;
+            if (int rc = make_tmap_nhwc(&ta[p], src, c8, c->w, c->h, c->n, cs, P.box_w + hx, P.box_h, P.box_n, c->stride)) return rc;
+        }
+        if (c->nparts < 2) ta[1] = ta[0];
+        if (halo) {
+            if (c->cout % 128 == 0) return launch_wgrad_tma<128, 3, true>(P, tm, ta[0], ta[1], st);
+            return launch_wgrad_tma<64, 3, true>(P, tm, ta[0], ta[1], st);
+        }
+        if (c->cout % 256 == 0) return launch_wgrad_tma<256, 2, false>(P, tm, ta[0], ta[1], st);
+        if (c->cout % 128 == 0) return launch_wgrad_tma<128, 3, false>(P, tm, ta[0], ta[1], st);
+        return launch_wgrad_tma<64, 3, false>(P, tm, ta[0], ta[1], st);
+    }
     if (c->cout % 256 == 0) return launch_wgrad<256, 2, 3>(P, tm, c->cout, st);
     if (c->cout % 128 == 0) return launch_wgrad<128, 3, 3>(P, tm, c->cout, st);
     return launch_wgrad<64, 3, 3>(P, tm, c->cout, st);
