@@ -1474,6 +1474,49 @@ struct WPrepParams {
     long long kf, kd;
 };
 
+// tiled variant: a block converts a [32 cout][32 cin] tile of one tap through shared memory, so the master is read and both
+// operand matrices are written along their contiguous dimension (w_dg is the transpose: written along cout)
+__global__ void __launch_bounds__(256) tc_weight_prepare_tiled_kernel(const float *__restrict__ wm, const WPrepParams P, bf16 *__restrict__ w_fwd,
+                                                                      bf16 *__restrict__ w_dg) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty + 8 * i, ci = ci0 + tx;
+        float v = 0.f;
+        if (co < P.cout && ci < P.cin) v = wm[(static_cast<long long>(co) * P.taps + tap) * P.cin + ci];
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+    {
+        const int ci = ci0 + tx;
+        if (ci < P.cin) {
+            int p = 0;
+            while (p + 1 < P.nparts && ci >= P.choff[p] + P.c[p]) ++p;
+            const int kpos = P.koff[p] + (ci - P.choff[p]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int co = co0 + ty + 8 * i;
+                if (co < P.cout) w_fwd[static_cast<long long>(co) * P.kf + static_cast<long long>(tap) * P.ktap + kpos] = __float2bfloat16_rn(tile[ty + 8 * i][tx]);
+            }
+        }
+    }
+    if (w_dg) {
+        const int co = co0 + tx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ci = ci0 + ty + 8 * i;
+            if (co < P.cout && ci < P.cin) {
+                int p = 0;
+                while (p + 1 < P.nparts && ci >= P.choff[p] + P.c[p]) ++p;
+                const int kpos = P.koff[p] + (ci - P.choff[p]);
+                w_dg[static_cast<long long>(kpos) * P.kd + static_cast<long long>(tap) * P.cout64 + co] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+            }
+        }
+    }
+}
+
 __global__ void tc_weight_prepare_kernel(const float *__restrict__ wm, const WPrepParams P, bf16 *__restrict__ w_fwd, bf16 *__restrict__ w_dg) {
     const long long total = static_cast<long long>(P.cout) * P.taps * P.cin;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1856,6 +1899,12 @@ int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd,
     W.ktap = L.ktap; W.cout64 = L.cout64; W.kf = L.kf; W.kd = L.kd;
     int off = 0;
     for (int p = 0; p < c->nparts; ++p) { W.choff[p] = off; W.c[p] = c->parts[p].c; W.koff[p] = L.koff[p]; off += c->parts[p].c; }
+    if (!L.rowpack && W.taps <= 65535 && c->cout >= 32 && c->cin >= 32) {
+        dim3 tg((c->cin + 31) / 32, (c->cout + 31) / 32, W.taps);
+        tc_weight_prepare_tiled_kernel<<<tg, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd), (w_dgrad && de) ? static_cast<bf16 *>(w_dgrad) : nullptr);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     const long long total = static_cast<long long>(c->cout) * W.taps * c->cin;
     const int grid = static_cast<int>(std::min<long long>((total + 1023) / 1024, 8ll * pcb_num_sms()));
     tc_weight_prepare_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd),

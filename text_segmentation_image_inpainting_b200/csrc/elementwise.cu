@@ -13,6 +13,14 @@ inline int ew_grid(long long work_items, int per_block) {
     return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// reductions end in one fp64 atomic per channel per block: a few blocks per SM keep the loads in flight, thousands of
+// blocks would serialise thousands of atomics on the same c addresses
+inline int ew_grid_red(long long work_items, int per_block) {
+    long long b = (work_items + per_block - 1) / per_block;
+    const long long cap = 4ll * pcb_num_sms();
+    return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-channel reductions over an NHWC tensor viewed as [count][c]; c % 8 == 0, c <= 2048.
 // Thread layout: tid -> (row-in-block r = tid / cv, channel vector v = tid % cv), cv = c / 8.
@@ -112,24 +120,32 @@ __global__ void bn_finalize_kernel(const double *sum, const double *sqsum, long 
     if (save_invstd) save_invstd[ch] = invstd;
 }
 
+// Thread layout as in the reductions: tid -> (row-in-block, channel vector), so the per-channel coefficients are loaded once
+// into registers instead of once per element (the element-wise passes were load-instruction bound, not bandwidth bound).
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const T *__restrict__ x, long long nvec, int c, const float *__restrict__ scale,
+__global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const T *__restrict__ x, long long count, int c, const float *__restrict__ scale,
                                                                 const float *__restrict__ shift, int act, float slope,
                                                                 const T *__restrict__ residual, T *__restrict__ y) {
-    const int cv = c >> 3;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ch = static_cast<int>(i % cv) * 8;
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    if (r >= rpb) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[v * 8 + j] : 1.f; sh[j] = scale ? shift[v * 8 + j] : 0.f; }
+    const long long step = static_cast<long long>(gridDim.x) * rpb;
+#pragma unroll 2
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
         float f[8], rres[8];
-        Vec8<T>::load(x + i * 8, f);
-        if (residual) Vec8<T>::load(residual + i * 8, rres);
+        Vec8<T>::load(x + row * c + v * 8, f);
+        if (residual) Vec8<T>::load(residual + row * c + v * 8, rres);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float z = scale ? f[j] * scale[ch + j] + shift[ch + j] : f[j];
+            float z = scale ? f[j] * sc[j] + sh[j] : f[j];
             z = apply_act(z, act, slope);
             if (residual) z += rres[j];
             f[j] = z;
         }
-        Vec8<T>::store(y + i * 8, f);
+        Vec8<T>::store(y + row * c + v * 8, f);
     }
 }
 
@@ -180,32 +196,44 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const T *__re
 }
 
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long nvec, long long count, int c,
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
                                                                   const float *__restrict__ scale, const float *__restrict__ shift,
                                                                   const float *__restrict__ mean, const float *__restrict__ invstd, int act,
                                                                   float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
                                                                   int training, T *__restrict__ dx) {
-    const int cv = c >> 3;
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    if (r >= rpb) return;
     const float inv_count = 1.0f / static_cast<float>(count);
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ch = static_cast<int>(i % cv) * 8;
+    const bool full = scale && training;
+    float sc[8], sh[8], mu[8], is[8], mg[8], mgx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = v * 8 + j;
+        sc[j] = scale ? scale[ch] : 1.f; sh[j] = scale ? shift[ch] : 0.f;
+        mu[j] = full ? mean[ch] : 0.f; is[j] = full ? invstd[ch] : 0.f;
+        mg[j] = full ? static_cast<float>(sum_g[ch]) * inv_count : 0.f;
+        mgx[j] = full ? static_cast<float>(sum_gx[ch]) * inv_count : 0.f;
+    }
+    const long long step = static_cast<long long>(gridDim.x) * rpb;
+#pragma unroll 2
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
         float g[8], f[8];
-        Vec8<T>::load(gy + i * 8, g);
-        Vec8<T>::load(x + i * 8, f);
+        Vec8<T>::load(gy + row * c + v * 8, g);
+        Vec8<T>::load(x + row * c + v * 8, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float sc = scale ? scale[ch + j] : 1.f, sh = shift ? shift[ch + j] : 0.f;
-            const float gz = g[j] * act_grad(f[j] * sc + sh, act, slope);
+            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
             float d;
             if (!scale) d = gz;
-            else if (!training) d = sc * gz;
+            else if (!training) d = sc[j] * gz;
             else {
-                const float xhat = (f[j] - mean[ch + j]) * invstd[ch + j];
-                d = sc * (gz - static_cast<float>(sum_g[ch + j]) * inv_count - xhat * static_cast<float>(sum_gx[ch + j]) * inv_count);
+                const float xhat = (f[j] - mu[j]) * is[j];
+                d = sc[j] * (gz - mg[j] - xhat * mgx[j]);
             }
             f[j] = d;
         }
-        Vec8<T>::store(dx + i * 8, f);
+        Vec8<T>::store(dx + row * c + v * 8, f);
     }
 }
 
@@ -302,6 +330,7 @@ __global__ void __launch_bounds__(EW_THREADS) renorm_bwd_vec_kernel(const T *__r
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (r < rpb) {
+#pragma unroll 2
         for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
             const float s = msum[row];
             float g[8], d[8];
@@ -479,7 +508,7 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_stats(const void *x
     PCB_CUDA(cudaMemsetAsync(sqsum, 0, sizeof(double) * c, ST));
     if (c % 8 == 0 && c <= 2048) {
         const int rpb = EW_THREADS / (c / 8);
-        const int grid = ew_grid(count, rpb * 16);
+        const int grid = ew_grid_red(count, rpb * 16);
         if (dtype == PCB_BF16) bn_stats_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sum, sqsum);
         else bn_stats_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sum, sqsum);
     } else {
@@ -505,10 +534,10 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_forward(const v
                                   float slope, const void *residual, void *y, pcb_stream_t stream) {
     PCB_CHECK(x && y && count > 0 && c > 0 && ((scale == nullptr) == (shift == nullptr)), "pcb_bn_act_forward: bad arguments");
     const long long numel = count * c;
-    if (c % 8 == 0) {
-        const int grid = ew_grid(numel / 8, EW_THREADS * 4);
-        if (dtype == PCB_BF16) bn_act_fwd_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), numel / 8, c, scale, shift, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y));
-        else bn_act_fwd_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), numel / 8, c, scale, shift, act, slope, static_cast<const float *>(residual), static_cast<float *>(y));
+    if (c % 8 == 0 && c <= 2048) {
+        const int grid = ew_grid(count, (EW_THREADS / (c / 8)) * 4);
+        if (dtype == PCB_BF16) bn_act_fwd_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, scale, shift, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y));
+        else bn_act_fwd_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, scale, shift, act, slope, static_cast<const float *>(residual), static_cast<float *>(y));
     } else {
         const int grid = ew_grid(numel, EW_THREADS * 8);
         if (dtype == PCB_BF16) bn_act_fwd_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), numel, c, scale, shift, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y));
@@ -531,7 +560,7 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
     PCB_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(double) * c, ST));
     PCB_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(double) * c, ST));
     const int rpb = EW_THREADS / (c / 8);
-    const int grid = ew_grid(count, rpb * 16);
+    const int grid = ew_grid_red(count, rpb * 16);
     if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
     else bn_bwd_reduce_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
     PCB_LAUNCH_CHECK();
@@ -544,13 +573,13 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply(
                                          pcb_stream_t stream) {
     PCB_CHECK(gy && x && dx && count > 0, "pcb_bn_act_backward_apply: bad arguments");
     PCB_CHECK(!(scale && training) || (mean && invstd && sum_g && sum_gx), "pcb_bn_act_backward_apply: training needs statistics");
-    const long long nvec = count * c / 8;
-    const int grid = ew_grid(c % 8 == 0 ? nvec : count * c, EW_THREADS * 4);
-    if (c % 8 != 0) {
+    const bool vec = c % 8 == 0 && c <= 2048;
+    const int grid = vec ? ew_grid(count, (EW_THREADS / (c / 8)) * 4) : ew_grid(count * c, EW_THREADS * 4);
+    if (!vec) {
         if (dtype == PCB_BF16) bn_bwd_apply_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
         else bn_bwd_apply_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
-    } else if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
-    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), nvec, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
+    } else if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
+    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
     PCB_LAUNCH_CHECK();
     if ((dgamma || dbeta) && sum_g && sum_gx) {
         bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sum_g, sum_gx, c, dgamma, dbeta);
