@@ -77,6 +77,11 @@ struct TcParams {
     // dgrad output addressing: the tile grid (h, w above) is every `sub`-th pixel of the full-resolution [fh, fw] gradient,
     // starting at (py, px) -- sub = 2 for the parity classes of a stride-2 layer, 1 otherwise
     int sub, py, px, fh, fw;
+    // split-K (layers with too few output tiles to fill the GPU): the 64-channel K blocks of every tap are dealt round-robin to
+    // `ksplit` CTAs per tile, which add their raw fp32 accumulators into `partial` [m_total][ncols]; a finish kernel applies
+    // the epilogue.  ksplit = 1: `partial` is null and the epilogue runs in the kernel.
+    int ksplit;
+    float *partial;
 };
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
@@ -103,6 +108,20 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                     en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
                     eh = eh * P.sub + P.py; ew = ew * P.sub + P.px;
                     mo = (static_cast<long long>(en) * P.fh + eh) * P.fw + ew;
+                }
+                if (P.partial != nullptr) {                // split-K: raw accumulators, reduced across CTAs with fp32 adds
+    #pragma unroll 1
+                    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+                        ptx::tmem_ld_wait();
+                        if (rvalid) {
+                            float *dst = P.partial + static_cast<long long>(m) * P.ncols + n0 + c0;
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+                        }
+                    }
+                    return;
                 }
     #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -628,7 +647,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     const int np = (MODE == 0) ? P.nparts : 1;
     const int n_tiles = P.ncols / BLOCK_N;
-    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles;
+    const int KS = P.ksplit;                                            // tile index = (m tile * n_tiles + n tile) * KS + split
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles * KS;
     const bool fix = (MODE == 0) && P.use_fix;
     const int kwi = HALO ? 1 : P.kw;                                   // A items per kernel row
 
@@ -676,7 +696,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         const long long tt0 = clock64();
 #endif
         for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int sp = tile % KS, mn = tile / KS;
+            const int m0 = (mn / n_tiles) * BLOCK_M, n0 = (mn % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int img = m0 / plane, rem = m0 - img * plane;
             const int oy = rem / pwid, ox = rem - oy * pwid;
@@ -690,7 +711,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                     for (int p = 0; p < TC_MAX_PARTS; ++p) {
                         const int kext = (p == 0) ? kext0 : kext1;
                         const CUtensorMap *ma = (p == 0) ? &tmap_a0 : &tmap_a1;
+                        const int gb0 = (p == 0) ? 0 : kext0 / BLOCK_K;          // global K-block index of the part's first block
                         for (int c0 = 0; c0 < kext; c0 += BLOCK_K, kidx += BLOCK_K) {
+                            if (KS > 1 && (gb0 + c0 / BLOCK_K) % KS != sp) continue;
 #ifdef PCB_TC_TIMING
                             const long long tq0 = clock64();
 #endif
@@ -745,7 +768,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         long long tm_wait = 0, tm_acc = 0, tm_issue = 0, tm_commit = 0;
         const long long t_begin = clock64();
         for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
-            const int n0 = (tile % n_tiles) * BLOCK_N;
+            const int sp = tile % KS;
+            const int n0 = ((tile / KS) % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int acc = tile_iter & 1;
 #ifdef PCB_TC_TIMING
@@ -763,7 +787,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #pragma unroll
                 for (int p = 0; p < TC_MAX_PARTS; ++p) {
                     const int nbp = (p == 0) ? nb0 : nb1, klast = (p == 0) ? kl0 : kl1;
+                    const int gb0 = (p == 0) ? 0 : nb0;
                     for (int cb = 0; cb < nbp; ++cb) {
+                        if (KS > 1 && (gb0 + cb) % KS != sp) continue;
 #ifdef PCB_TC_TIMING
                         const long long tq0 = clock64();
 #endif
@@ -821,12 +847,13 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) {
                         wnext[p] = 0ull;
-                        const int m = (tl / n_tiles) * BLOCK_M + t;
+                        const int m = (tl / KS / n_tiles) * BLOCK_M + t;
                         if (p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
                     }
                 };
                 load_words(blockIdx.x);
                 for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                    const int sp = tile % KS;
                     uint64_t wcur[TC_MAX_PARTS];
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) wcur[p] = wnext[p];
@@ -839,7 +866,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                             const bool hole = ((wcur[p] >> tap) & 1ull) == 0ull;
                             const bool any_hole = __any_sync(0xffffffffu, hole);
                             const int nb = P.parts[p].kext / BLOCK_K;
+                            const int gb0 = (p == 0) ? 0 : P.parts[0].kext / BLOCK_K;
                             for (int cb = 0; cb < nb; ++cb) {
+                                if (KS > 1 && (gb0 + cb) % KS != sp) continue;
                                 if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 122)) { dead = true; break; }
                                 if (any_hole) {
                                     if (hole) {
@@ -864,7 +893,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                 auto load_bits = [&](int tl, uint32_t &b0, uint32_t &b1) {       // bit (p*8 + tr): pixel row is a hole
                     b0 = b1 = 0;
                     if (tl >= num_tiles) return;
-                    const int m0 = (tl / n_tiles) * BLOCK_M;
+                    const int m0 = (tl / KS / n_tiles) * BLOCK_M;
                     const int img = m0 / plane, rem = m0 - img * plane;
                     const int oy = rem / P.wo, ox = rem - oy * P.wo;
 #pragma unroll
@@ -884,6 +913,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                 uint32_t n0b, n1b;
                 load_bits(blockIdx.x, n0b, n1b);
                 for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                    const int sp = tile % KS;
                     const uint32_t c0b = n0b, c1b = n1b;
                     load_bits(tile + gridDim.x, n0b, n1b);
                     for (int tr = 0; tr < P.kh && !dead; ++tr) {
@@ -893,7 +923,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                             const bool h0 = (c0b >> (p * 8 + tr)) & 1u, h1 = (c1b >> (p * 8 + tr)) & 1u;
                             const bool any_hole = __any_sync(0xffffffffu, h0 || h1);
                             const int nb = P.parts[p].kext / BLOCK_K;
+                            const int gb0 = (p == 0) ? 0 : P.parts[0].kext / BLOCK_K;
                             for (int cb = 0; cb < nb; ++cb) {
+                                if (KS > 1 && (gb0 + cb) % KS != sp) continue;
                                 if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 122)) { dead = true; break; }
                                 if (any_hole) {
                                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -923,7 +955,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         // ================================ epilogue warps (6-9) ================================
         int tile_iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int mn = tile / KS;
+            const int m0 = (mn / n_tiles) * BLOCK_M, n0 = (mn % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int acc = tile_iter & 1;
             if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 123)) break;
@@ -1735,6 +1768,84 @@ int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
 }
 
 
+// ---- split-K: scratch buffer and finish kernels --------------------------------------------------
+float *splitk_scratch(size_t bytes) {
+    static float *buf = nullptr;
+    static size_t cap = 0;
+    if (bytes > cap) {
+        if (buf) cudaFree(buf);
+        buf = nullptr; cap = 0;
+        const size_t want = std::max<size_t>(bytes, 16u << 20);
+        if (cudaMalloc(&buf, want) == cudaSuccess) cap = want;
+    }
+    return buf;
+}
+
+// y = hole ? 0 : acc / s + b over [m_total][y_cstride] (8 channels per thread)
+__global__ void splitk_finish_fwd_kernel(const float *__restrict__ part, int ncols, const float *__restrict__ msum, const float *__restrict__ bias, int cout,
+                                         int no_guard, long long m_total, bf16 *__restrict__ y, int y_cstride) {
+    const int cv = y_cstride >> 3;
+    const long long total = m_total * cv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / cv;
+        const int col = static_cast<int>(i - m * cv) * 8;
+        const float s = msum[m];
+        const bool hole = (s == 0.f) && !no_guard;
+        const float inv = hole ? 0.f : 1.0f / s;
+        uint4 o;
+        __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = col + 2 * j;
+            float a = (co < ncols) ? part[m * ncols + co] : 0.f, b = (co + 1 < ncols) ? part[m * ncols + co + 1] : 0.f;
+            a = (hole || co >= cout) ? 0.f : a * inv + (bias ? bias[co] : 0.f);
+            b = (hole || co + 1 >= cout) ? 0.f : b * inv + (bias ? bias[co + 1] : 0.f);
+            ob[j] = __floats2bfloat162_rn(a, b);
+        }
+        *reinterpret_cast<uint4 *>(y + m * y_cstride + col) = o;
+    }
+}
+
+// dx_part = acc * input mask of the part (8 channels per thread); the tile grid may be a parity class of the gradient
+__global__ void splitk_finish_dgrad_kernel(const float *__restrict__ part, const TcParams P) {
+    const int cv = P.ncols >> 3;
+    const long long total = static_cast<long long>(P.m_total) * cv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int m = static_cast<int>(i / cv);
+        const int col = static_cast<int>(i - static_cast<long long>(m) * cv) * 8;
+        const int en = m / (P.h * P.w), rem = m - en * P.h * P.w;
+        const int eh = (rem / P.w) * P.sub + P.py, ew = (rem % P.w) * P.sub + P.px;
+        const long long mo = (static_cast<long long>(en) * P.fh + eh) * P.fw + ew;
+        for (int p = 0; p < P.nparts; ++p) {
+            const TcPart &pt = P.parts[p];
+            const int local = col - pt.koff;
+            if (local < 0 || local >= pt.c8 || pt.dx == nullptr) continue;
+            float scale = 1.f;
+            if (pt.mask != nullptr)
+                scale = pt.mask[(static_cast<long long>(en) * (P.fh >> pt.mup) + (eh >> pt.mup)) * (P.fw >> pt.mup) + (ew >> pt.mup)] ? 1.f : 0.f;
+            const float *src = part + static_cast<long long>(m) * P.ncols + col;
+            uint4 o;
+            __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(src[2 * j] * scale, src[2 * j + 1] * scale);
+            *reinterpret_cast<uint4 *>(pt.dx + mo * pt.dx_cstride + local) = o;
+        }
+    }
+}
+
+// how many CTAs should share the K loop of one output tile
+int pick_ksplit(long long m_total, int ncols, int bn, int blocks_per_tap) {
+    // measured on B200 (8 x 512^2 U-Net, layers at 4x4..16x16): the shorter K loop is paid back by the memset + finish kernels,
+    // so the split is opt-in (PCB_SPLITK=1; the parity tests set it)
+    if (!getenv("PCB_SPLITK")) return 1;
+    const long long tiles = ((m_total + BLOCK_M - 1) / BLOCK_M) * (ncols / bn);
+    const int sms = pcb_num_sms();
+    if (tiles * 2 > sms) return 1;
+    int ks = static_cast<int>(std::min<long long>(16, sms / tiles));
+    ks = std::min(ks, blocks_per_tap);                   // every split keeps at least one K block per tap
+    return ks < 2 ? 1 : ks;
+}
+
 // ---- TMA-fed path: eligibility, tile box, launch -------------------------------------------------
 // 128 consecutive pixels of a [n][ht][wt] grid as a box {bw, bh, bn}: possible when the extents nest in powers of two
 bool tile_box(int wt, int ht, int *bw, int *bh, int *bn) {
@@ -1794,7 +1905,8 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
         PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_done = true;
     }
-    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
+    if (P.ksplit < 1) P.ksplit = 1;
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N) * P.ksplit;
     const int grid = std::min(num_tiles, pcb_num_sms());
     P.dbg = debug_buffer();
     kern<<<grid, TMA_THREADS, smem, st>>>(P, tw, ta0, ta1);
@@ -1922,7 +2034,14 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     PCB_CHECK(y_cstride % 8 == 0 && y_cstride >= c->cout, "tensor-core forward: y channel stride must be a multiple of 8 and >= cout");
     const Layout L = layout_of(c);
     if (smallco_ok(c)) return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
-    if (int rc = launch_tapmask(c, tapmask, st)) return rc;
+    bool need_tapmask = true;
+    if (tma_fwd_ok(c)) {                                  // row-halo tiles: the fixers read the mask planes themselves
+        int bw, bh, bn;
+        tile_box(c->wo, c->ho, &bw, &bh, &bn);
+        need_tapmask = !tma_halo_ok(c, bw, bh, bn, pick_bn(c->cout <= 32 ? 32 : L.rows_f, m_total));
+    }
+    if (need_tapmask)
+        if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     TcParams P;
     base_params(P, c, L);
     P.m_total = static_cast<int>(m_total);
@@ -1959,6 +2078,19 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
         P.ncols = (bn == 32) ? 32 : L.rows_f;
         P.wk_base = 0; P.wk_col = L.ktap; P.wk_row = c->kw * L.ktap;
         if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, bn)) return rc;
+        P.ksplit = pick_ksplit(m_total, P.ncols, bn, L.ktap / BLOCK_K);
+        if (P.ksplit > 1) {
+            const size_t bytes = static_cast<size_t>(m_total) * P.ncols * sizeof(float);
+            P.partial = splitk_scratch(bytes);
+            PCB_CHECK(P.partial != nullptr, "split-K scratch allocation failed");
+            PCB_CUDA(cudaMemsetAsync(P.partial, 0, bytes, st));
+            if (int rc = launch_tma<0>(P, tm, ta[0], ta[1], bn, halo, st)) return rc;
+            const long long work = m_total * (y_cstride / 8);
+            splitk_finish_fwd_kernel<<<static_cast<int>(std::min<long long>((work + 255) / 256, 8ll * pcb_num_sms())), 256, 0, st>>>(
+                P.partial, P.ncols, msum, bias, c->cout, c->no_guard, m_total, static_cast<bf16 *>(y), y_cstride);
+            PCB_LAUNCH_CHECK();
+            return 0;
+        }
         return launch_tma<0>(P, tm, ta[0], ta[1], bn, halo, st);
     }
     if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
@@ -2001,6 +2133,18 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
         CUtensorMap ta;
         if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, P.box_w + (halo ? (c->kw - 1) * c->dil : 0), P.box_h, P.box_n, 1)) return rc;
         if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
+        P.ksplit = pick_ksplit(m_total, P.ncols, bn, L.cout64 / BLOCK_K);
+        if (P.ksplit > 1) {
+            const size_t bytes = static_cast<size_t>(m_total) * P.ncols * sizeof(float);
+            P.partial = splitk_scratch(bytes);
+            PCB_CHECK(P.partial != nullptr, "split-K scratch allocation failed");
+            PCB_CUDA(cudaMemsetAsync(P.partial, 0, bytes, st));
+            if (int rc = launch_tma<1>(P, tm, ta, ta, bn, halo, st)) return rc;
+            const long long work = m_total * (P.ncols / 8);
+            splitk_finish_dgrad_kernel<<<static_cast<int>(std::min<long long>((work + 255) / 256, 8ll * pcb_num_sms())), 256, 0, st>>>(P.partial, P);
+            PCB_LAUNCH_CHECK();
+            return 0;
+        }
         return launch_tma<1>(P, tm, ta, ta, bn, halo, st);
     }
     if (tma_dgrad_s2_ok(c)) {

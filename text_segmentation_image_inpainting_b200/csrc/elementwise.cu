@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const T *__restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
     if (r < rpb) {
+#pragma unroll 4
         for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
             float f[8];
             Vec8<T>::load(x + row * c + v * 8, f);
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const T *__re
             sc[j] = scale ? scale[v * 8 + j] : 1.f; sh[j] = shift ? shift[v * 8 + j] : 0.f;
             mu[j] = mean ? mean[v * 8 + j] : 0.f; is[j] = invstd ? invstd[v * 8 + j] : 1.f;
         }
+#pragma unroll 4
         for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
             float g[8], f[8];
             Vec8<T>::load(gy + row * c + v * 8, g);
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(EW_THREADS) renorm_bwd_vec_kernel(const T *__r
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (r < rpb) {
-#pragma unroll 2
+#pragma unroll 4
         for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
             const float s = msum[row];
             float g[8], d[8];
