@@ -145,6 +145,14 @@ int pcb_bn_act_backward_apply(const void *gy, const void *x, int dtype, long lon
                               const float *shift, const float *mean, const float *invstd, int act, float slope,
                               const double *sum_g, const double *sum_gx, int training, void *dx, float *dgamma,
                               float *dbeta, pcb_stream_t stream);
+/* The same with the renormalisation backward of the partial convolution that produced x fused in
+ * (partial_convolution.py:71-77 under autograd): dc = dx / msum, 0 where msum == 0 -- one pass instead of
+ * pcb_bn_act_backward_apply + pcb_pconv_renorm_backward.  Only valid when that convolution has no bias, one mask
+ * group, the zero guard (not PartialConvNoHoles) and c % 8 == 0; msum is the [count] fp32 plane pcb_pconv_forward wrote. */
+int pcb_bn_act_backward_apply_renorm(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                     const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                     const double *sum_g, const double *sum_gx, int training, const float *msum, void *dc,
+                                     float *dgamma, float *dbeta, pcb_stream_t stream);
 
 /* ---- resampling / glue ------------------------------------------------------------------ */
 /* nn.Upsample(scale_factor=2, mode='nearest') on NHWC (DoubleUpSample, partial_convolution.py:224-231). */

@@ -50,6 +50,8 @@ _SIGS = {
                                            c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "pcb_bn_act_backward_apply": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_bn_act_backward_apply_renorm": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_upsample2x_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pcb_upsample2x_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pcb_concat_forward": (c_int, [ctypes.POINTER(Part), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__res
                                                                   const float *__restrict__ scale, const float *__restrict__ shift,
                                                                   const float *__restrict__ mean, const float *__restrict__ invstd, int act,
                                                                   float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
-                                                                  int training, T *__restrict__ dx) {
+                                                                  int training, const float *__restrict__ msum, T *__restrict__ dx) {
     const int cv = c >> 3, rpb = EW_THREADS / cv;
     const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
     if (r >= rpb) return;
@@ -218,11 +218,15 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__res
         mgx[j] = full ? static_cast<float>(sum_gx[ch]) * inv_count : 0.f;
     }
     const long long step = static_cast<long long>(gridDim.x) * rpb;
-#pragma unroll 2
+    const bool renorm = msum != nullptr;
+#pragma unroll 4
     for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
         float g[8], f[8];
+        // optional fused renormalisation backward of the producing partial convolution: dc = d / s, 0 at holes
+        const float s = renorm ? __ldg(msum + row) : 1.f;
         Vec8<T>::load(gy + row * c + v * 8, g);
         Vec8<T>::load(x + row * c + v * 8, f);
+        const float rs = (s == 0.f) ? 0.f : __frcp_rn(s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__res
                 const float xhat = (f[j] - mu[j]) * is[j];
                 d = sc[j] * (gz - mg[j] - xhat * mgx[j]);
             }
-            f[j] = d;
+            f[j] = renorm ? d * rs : d;
         }
         Vec8<T>::store(dx + row * c + v * 8, f);
     }
@@ -318,6 +322,40 @@ __global__ void renorm_bwd_kernel(const T *__restrict__ dy, int dys, const float
     __syncthreads();
     if (dbias)
         for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, s_db[i]);
+}
+
+// c <= 8 in an 8-channel-padded buffer (the RGB tail): one 16-byte pixel per thread and iteration, bias-gradient partials in
+// registers -> warp shuffle -> one atomic per channel per warp (the scalar kernel above serialises on 3 shared atomics)
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) renorm_bwd_pixel8_kernel(const T *__restrict__ dy, int dys, const float *__restrict__ msum, long long count, int c,
+                                                                       int no_guard, T *__restrict__ dc, float *dbias) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < count; row += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float s = msum[row];
+        float g[8], d[8];
+        if (dys == 8) Vec8<T>::load(dy + row * 8, g);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = j < c ? to_f32(dy[row * dys + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j >= c) { d[j] = 0.f; continue; }
+            if (no_guard) { d[j] = g[j] / s; acc[j] += (d[j] - d[j]) + g[j]; }
+            else { const bool hole = (s == 0.f); d[j] = hole ? 0.f : g[j] / s; acc[j] += hole ? 0.f : g[j]; }
+        }
+        Vec8<T>::store(dc + row * 8, d);
+    }
+    if (dbias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = warp_sum(acc[j]);
+            if ((threadIdx.x & 31) == 0 && j < c) atomicAdd(dbias + j, t);
+        }
+    }
 }
 
 // vector path of the renormalisation backward: 8 channels per thread, rows strided like bn_stats (one msum load per row,
@@ -569,25 +607,41 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
-                                         const float *shift, const float *mean, const float *invstd, int act, float slope,
-                                         const double *sum_g, const double *sum_gx, int training, void *dx, float *dgamma, float *dbeta,
-                                         pcb_stream_t stream) {
+static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                      const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                      const double *sum_g, const double *sum_gx, int training, const float *msum, void *dx, float *dgamma,
+                                      float *dbeta, pcb_stream_t stream) {
     PCB_CHECK(gy && x && dx && count > 0, "pcb_bn_act_backward_apply: bad arguments");
+    PCB_CHECK(!msum || (c % 8 == 0 && c <= 2048), "pcb_bn_act_backward_apply_renorm: channel count must be a multiple of 8 (<= 2048)");
     PCB_CHECK(!(scale && training) || (mean && invstd && sum_g && sum_gx), "pcb_bn_act_backward_apply: training needs statistics");
     const bool vec = c % 8 == 0 && c <= 2048;
     const int grid = vec ? ew_grid(count, (EW_THREADS / (c / 8)) * 4) : ew_grid(count * c, EW_THREADS * 4);
     if (!vec) {
         if (dtype == PCB_BF16) bn_bwd_apply_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
         else bn_bwd_apply_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
-    } else if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
-    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
+    } else if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx));
+    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx));
     PCB_LAUNCH_CHECK();
     if ((dgamma || dbeta) && sum_g && sum_gx) {
         bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sum_g, sum_gx, c, dgamma, dbeta);
         PCB_LAUNCH_CHECK();
     }
     return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                         const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                         const double *sum_g, const double *sum_gx, int training, void *dx, float *dgamma, float *dbeta,
+                                         pcb_stream_t stream) {
+    return bn_act_backward_apply_impl(gy, x, dtype, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, nullptr, dx, dgamma, dbeta, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply_renorm(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                         const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                         const double *sum_g, const double *sum_gx, int training, const float *msum, void *dc, float *dgamma,
+                                         float *dbeta, pcb_stream_t stream) {
+    PCB_CHECK(msum != nullptr, "pcb_bn_act_backward_apply_renorm: msum required");
+    return bn_act_backward_apply_impl(gy, x, dtype, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, dc, dgamma, dbeta, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, int dy_cstride, const float *msum, void *dc, int dc_cstride, float *dbias, pcb_stream_t stream) {
@@ -600,6 +654,13 @@ extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(
         const int vgrid = ew_grid(count, rpb * 8);
         if (c->dtype == PCB_BF16) renorm_bwd_vec_kernel<bf16><<<vgrid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(dy), dy_cstride, msum, count, c->cout, c->no_guard, static_cast<bf16 *>(dc), dc_cstride, dbias);
         else renorm_bwd_vec_kernel<float><<<vgrid, EW_THREADS, 0, ST>>>(static_cast<const float *>(dy), dy_cstride, msum, count, c->cout, c->no_guard, static_cast<float *>(dc), dc_cstride, dbias);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
+    if (mg == 1 && c->cout <= 8 && dc_cstride == 8 && (reinterpret_cast<uintptr_t>(dc) & 15) == 0 && (dy_cstride != 8 || (reinterpret_cast<uintptr_t>(dy) & 15) == 0)) {
+        const int pgrid = ew_grid_red(count, EW_THREADS * 4);
+        if (c->dtype == PCB_BF16) renorm_bwd_pixel8_kernel<bf16><<<pgrid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(dy), dy_cstride, msum, count, c->cout, c->no_guard, static_cast<bf16 *>(dc), dbias);
+        else renorm_bwd_pixel8_kernel<float><<<pgrid, EW_THREADS, 0, ST>>>(static_cast<const float *>(dy), dy_cstride, msum, count, c->cout, c->no_guard, static_cast<float *>(dc), dbias);
         PCB_LAUNCH_CHECK();
         return 0;
     }

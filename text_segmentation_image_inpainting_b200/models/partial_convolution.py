@@ -42,14 +42,14 @@ class PartialConv(BaseModule):
             p.requires_grad = False
         self._wcache = {}
 
-    def _conv(self, x, mask, no_guard=False):
+    def _conv(self, x, mask, no_guard=False, handoff=None):
         fc = self.feature_conv
         return ops.partial_conv(x, mask, fc.weight, fc.bias, fc.stride, fc.padding, fc.dilation, fc.groups,
-                                same_holes=self.same_holes, no_guard=no_guard, cache=self._wcache)
+                                same_holes=self.same_holes, no_guard=no_guard, cache=self._wcache, handoff=handoff)
 
-    def forward(self, args):
+    def forward(self, args, handoff=None):
         x, mask = args
-        return self._conv(x, mask)
+        return self._conv(x, mask, handoff=handoff)
 
 
 class PartialConv1x1(BaseModule):
@@ -96,7 +96,19 @@ def partial_convolution_block(in_channels, out_channels, kernel_size, stride=1, 
         m.append(PartialActivatedBN(out_channels, activation))
     if not BN and activation:
         m.append(PartialActivation(activation))
-    return nn.Sequential(*m)
+    return PartialBlock(*m)
+
+
+class PartialBlock(nn.Sequential):
+    """The nn.Sequential of the reference's factory (same children, same state_dict keys).  When it is exactly
+    [PartialConv, PartialActivatedBN] the convolution output has a single consumer by construction, so the BatchNorm
+    backward may absorb the convolution's renormalisation backward (ops.RenormHandoff)."""
+
+    def forward(self, args):
+        if len(self) == 2 and type(self[0]) is PartialConv and isinstance(self[1], PartialActivatedBN):
+            h = ops.RenormHandoff()
+            return self[1](self[0](args, handoff=h), handoff=h)
+        return super().forward(args)
 
 
 class PartialActivatedBN(BaseModule):
@@ -106,10 +118,10 @@ class PartialActivatedBN(BaseModule):
         super().__init__()
         self.bn_act = nn.Sequential(nn.BatchNorm2d(channel), act_fn) if act_fn else nn.Sequential(nn.BatchNorm2d(channel))
 
-    def forward(self, args, residual=None):
+    def forward(self, args, residual=None, handoff=None):
         x, mask = args
         act = self.bn_act[1] if len(self.bn_act) > 1 else None
-        return ops.bn_act(x, self.bn_act[0], act, residual=residual), mask
+        return ops.bn_act(x, self.bn_act[0], act, residual=residual, handoff=handoff), mask
 
 
 class PartialActivation(BaseModule):

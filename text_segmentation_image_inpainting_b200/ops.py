@@ -205,7 +205,7 @@ class PartialConvFn(torch.autograd.Function):
     """y, msum, newmask = pconv(cat(up?(x_i)), W, b | mask)   (models/partial_convolution.py:49-80 / :121-137)."""
 
     @staticmethod
-    def forward(ctx, geom: ConvGeom, wprep, weight, bias, *xs):
+    def forward(ctx, geom: ConvGeom, wprep, weight, bias, handoff, *xs):
         lib = _lib.load()
         w_fwd, w_dg = wprep
         c = geom.struct(xs)
@@ -222,6 +222,11 @@ class PartialConvFn(torch.autograd.Function):
             _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
                                              newmask.data_ptr(), ws.data_ptr(), _stream()))
         ctx.geom, ctx.wprep, ctx.has_bias, ctx.weight_ref = geom, wprep, bias is not None, weight
+        ctx.handoff = handoff
+        if handoff is not None:
+            handoff.msum = msum
+            handoff.eligible = (geom.mg == 1 and not geom.no_guard and not geom.plain and bias is None and geom.cout % 8 == 0
+                                and geom.dtype == PCB_BF16)
         ctx.save_for_backward(msum, *xs)
         ctx.mark_non_differentiable(msum, newmask)
         return y, msum, newmask
@@ -235,19 +240,25 @@ class PartialConvFn(torch.autograd.Function):
         dev, tdtype = xs[0].device, xs[0].dtype
         gy = as_feature_padded(gy if gy.dtype == tdtype else gy.to(tdtype))
         c = geom.struct(xs)
-        dc = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, tdtype, dev) if geom.dtype == PCB_BF16 else \
-            torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=tdtype, device=dev, memory_format=CL)
-        dcs = nhwc_layout(dc)
-        dbias = torch.empty((geom.cout,), dtype=torch.float32, device=dev) if ctx.has_bias else None
-        _lib.check(lib.pcb_pconv_renorm_backward(ctypes.byref(c), gy.data_ptr(), nhwc_layout(gy), msum.data_ptr(), dc.data_ptr(), dcs,
-                                                 _ptr(dbias), _stream()))
+        dbias = None
+        if ctx.handoff is not None and ctx.handoff.fused:
+            # the BatchNorm backward of the block already divided by the mask sums (RenormHandoff): gy IS dc
+            dc = gy
+            dcs = nhwc_layout(dc)
+        else:
+            dc = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, tdtype, dev) if geom.dtype == PCB_BF16 else \
+                torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=tdtype, device=dev, memory_format=CL)
+            dcs = nhwc_layout(dc)
+            dbias = torch.empty((geom.cout,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+            _lib.check(lib.pcb_pconv_renorm_backward(ctypes.byref(c), gy.data_ptr(), nhwc_layout(gy), msum.data_ptr(), dc.data_ptr(), dcs,
+                                                     _ptr(dbias), _stream()))
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty((geom.cout, geom.cin // geom.groups, geom.kh, geom.kw), dtype=torch.float32, device=dev, memory_format=CL)
             ws = _workspace(lib, c, dev)
             with _Timed("wgrad", geom):
                 _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
-        need = [ctx.needs_input_grad[4 + i] for i in range(len(xs))]
+        need = [ctx.needs_input_grad[5 + i] for i in range(len(xs))]
         gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
         if any(need):
             # full-resolution gradient buffer per source tensor; parts write their channel slices
@@ -283,7 +294,7 @@ class PartialConvFn(torch.autograd.Function):
                     gxs[i] = g
                 else:
                     gxs[i] = full[i]
-        return (None, None, dw, dbias, *gxs)
+        return (None, None, dw, dbias, None, *gxs)
 
 
 _WEIGHT_EPOCH = 0
@@ -318,8 +329,17 @@ def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
     return cache["val"]
 
 
+class RenormHandoff:
+    """Links a partial convolution to the BatchNorm(+activation) that is the ONLY consumer of its output (the blocks of
+    models/partial_convolution.py): the BN backward then writes dc = dy / mask_sum directly (one pass less over every conv
+    output) and the convolution's backward skips its renormalisation step.  Never use it when y has another consumer."""
+
+    def __init__(self):
+        self.msum, self.eligible, self.fused = None, False, False
+
+
 def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_holes=False, no_guard=False, cache=None,
-                 plain=False):
+                 plain=False, handoff=None):
     """Returns (y, new_mask: HoleMask).  `x` is a tensor or a LazyCat; `mask` a HoleMask or a dense tensor; with
     ``plain=True`` the mask is ignored and an ordinary convolution is computed (same kernels, renormaliser 1)."""
     if isinstance(x, LazyCat):
@@ -345,7 +365,7 @@ def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_
         raise _lib.PcbError(f"weight expects {weight.shape[1] * groups} input channels, got {cin}")
     geom = ConvGeom(xs, ups, cout, tuple(weight.shape[2:]), stride, padding, dilation, groups, same_holes, no_guard, parts, plain=plain)
     wprep = prepare_weight(weight, geom, cache if cache is not None else {})
-    y, msum, newmask = PartialConvFn.apply(geom, wprep, weight, bias, *xs)
+    y, msum, newmask = PartialConvFn.apply(geom, wprep, weight, bias, handoff, *xs)
     if geom.mg == 1:
         new = HoleMask.from_plane(newmask[0], cout, 0)
     else:
@@ -361,7 +381,7 @@ class BNActFn(torch.autograd.Function):
     """y = act(BN(x)) [+ residual]; BN optional (gamma None => plain activation)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope, msum=None):
         lib = _lib.load()
         n, c, h, w = x.shape
         count = n * h * w
@@ -392,13 +412,13 @@ class BNActFn(torch.autograd.Function):
         _lib.check(lib.pcb_bn_act_forward(x.data_ptr(), code, count, c, _ptr(scale), _ptr(shift), act, float(slope),
                                           _ptr(residual), y.data_ptr(), _stream()))
         ctx.cfg = (count, c, code, act, float(slope), has_bn, mean is not None, residual is not None)
-        ctx.save_for_backward(x, scale, shift, mean, invstd)
+        ctx.save_for_backward(x, scale, shift, mean, invstd, msum)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         lib = _lib.load()
-        x, scale, shift, mean, invstd = ctx.saved_tensors
+        x, scale, shift, mean, invstd, msum = ctx.saved_tensors
         count, c, code, act, slope, has_bn, batch_stats, has_res = ctx.cfg
         gy = gy.contiguous(memory_format=CL)
         if gy.dtype != x.dtype:
@@ -412,20 +432,27 @@ class BNActFn(torch.autograd.Function):
                                                       sums[1].data_ptr(), _stream()))
             dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
             dbeta = torch.empty_like(dgamma)
-            _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
-                                                     mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
-                                                     sums[1].data_ptr(), 1, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()))
+            if msum is not None:
+                _lib.check(lib.pcb_bn_act_backward_apply_renorm(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
+                                                                mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
+                                                                sums[1].data_ptr(), 1, msum.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
+                                                                dbeta.data_ptr(), _stream()))
+            else:
+                _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
+                                                         mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
+                                                         sums[1].data_ptr(), 1, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()))
         elif has_bn:   # eval-mode BN: a fixed affine map (parameter grads not produced in eval)
             _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
                                                      None, None, act, slope, None, None, 0, dx.data_ptr(), None, None, _stream()))
         else:
             _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, None, None, None, None, act, slope,
                                                      None, None, 0, dx.data_ptr(), None, None, _stream()))
-        return dx, dgamma, dbeta, (gy if has_res else None), None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, (gy if has_res else None), None, None, None, None, None, None, None, None, None
 
 
-def bn_act(x, bn, act, residual=None):
-    """`bn`: nn.BatchNorm2d or None; `act`: nn activation module / None."""
+def bn_act(x, bn, act, residual=None, handoff=None):
+    """`bn`: nn.BatchNorm2d or None; `act`: nn activation module / None.  `handoff`: the RenormHandoff of the partial
+    convolution whose output `x` is, when this call is that output's only consumer."""
     x = as_feature(x)
     code, slope = act_code(act)
     if residual is not None:
@@ -433,8 +460,12 @@ def bn_act(x, bn, act, residual=None):
     if bn is None:
         return BNActFn.apply(x, None, None, residual, None, None, None, False, 0.0, 0.0, code, slope)
     momentum = 0.1 if bn.momentum is None else bn.momentum
+    msum = None
+    if handoff is not None and handoff.eligible and bn.training and x.requires_grad and x.shape[1] % 8 == 0 and x.shape[1] <= 2048 \
+            and x.is_contiguous(memory_format=CL):
+        msum, handoff.fused = handoff.msum, True
     return BNActFn.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                         bn.training, momentum, bn.eps, code, slope)
+                         bn.training, momentum, bn.eps, code, slope, msum)
 
 
 def activation_only(x, act, residual=None):
