@@ -77,6 +77,10 @@ size_t pcb_pconv_workspace(const pcb_conv *c);
  * (= an OIHW nn.Conv2d weight in torch.channels_last memory format).                              */
 void pcb_conv_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems);
 int pcb_conv_weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream);
+/* The same for buffers that pcb_conv_weight_prepare already filled for this very problem description: only the weight
+ * entries are rewritten, the zero padding is left alone (no memsets).  For training loops that update the fp32 masters
+ * every step (the reference's optimiser step, train loop of SURVEY 8d).                                          */
+int pcb_conv_weight_refresh(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream);
 
 /* PartialConv.forward / PartialConvNoHoles.forward (models/partial_convolution.py:49-80, :121-137):
  *   y = where(s==0, 0, conv(x*m; W)/s + b),  s = box-sum of the mask (all-ones mask_conv, :41-47,59-66),

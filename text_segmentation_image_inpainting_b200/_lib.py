@@ -34,6 +34,7 @@ _SIGS = {
     "pcb_pconv_workspace": (c_size_t, [ctypes.POINTER(Conv)]),
     "pcb_conv_weight_layout": (None, [ctypes.POINTER(Conv), ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "pcb_conv_weight_prepare": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_conv_weight_refresh": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_pconv_forward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_pconv_renorm_backward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pcb_pconv_backward_data": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p),

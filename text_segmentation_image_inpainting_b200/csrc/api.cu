@@ -65,12 +65,20 @@ PCB_API void pcb_conv_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t
 
 int pcb_cast_weights(const float *src, void *dst, long long n, int dtype, cudaStream_t st);   // elementwise.cu
 
-PCB_API int pcb_conv_weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream) {
+static int weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, bool zero_padding, pcb_stream_t stream) {
     PCB_CHECK(c && w_master_krsc && w_fwd, "pcb_conv_weight_prepare: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (use_dw(c)) return pcb_dw_weight_prepare(c, w_master_krsc, w_fwd, st);
-    if (use_tc(c)) return pcb_tc_weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, st);
+    if (use_tc(c)) return pcb_tc_weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, zero_padding, st);
     return pcb_cast_weights(w_master_krsc, w_fwd, static_cast<long long>(c->cout) * c->kh * c->kw * (c->cin / c->groups), c->dtype, st);
+}
+
+PCB_API int pcb_conv_weight_prepare(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream) {
+    return weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, true, stream);
+}
+
+PCB_API int pcb_conv_weight_refresh(const pcb_conv *c, const float *w_master_krsc, void *w_fwd, void *w_dgrad, pcb_stream_t stream) {
+    return weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, false, stream);
 }
 
 PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,

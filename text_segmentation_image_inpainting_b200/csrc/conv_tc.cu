@@ -1999,12 +1999,14 @@ void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_el
     *dgrad_elems = L.rowpack ? 0 : static_cast<size_t>(rup(L.ktap, 128)) * L.kd;
 }
 
-int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, cudaStream_t st) {
+int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st) {
     const Layout L = layout_of(c);
     size_t fe, de;
     pcb_tc_weight_layout(c, &fe, &de);
-    PCB_CUDA(cudaMemsetAsync(w_fwd, 0, fe * 2, st));
-    if (w_dgrad && de) PCB_CUDA(cudaMemsetAsync(w_dgrad, 0, de * 2, st));
+    if (zero_padding) {                                  // a refresh of buffers filled before leaves the (never written) padding alone
+        PCB_CUDA(cudaMemsetAsync(w_fwd, 0, fe * 2, st));
+        if (w_dgrad && de) PCB_CUDA(cudaMemsetAsync(w_dgrad, 0, de * 2, st));
+    }
     WPrepParams W;
     memset(&W, 0, sizeof(W));
     W.cout = c->cout; W.taps = c->kh * c->kw; W.cin = c->cin; W.kw = c->kw; W.rowpack = L.rowpack; W.nparts = c->nparts;

@@ -544,8 +544,11 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
 
 extern "C" __attribute__((visibility("default"))) int pcb_bn_stats(const void *x, int dtype, long long count, int c, double *sum, double *sqsum, pcb_stream_t stream) {
     PCB_CHECK(x && sum && sqsum && count > 0 && c > 0, "pcb_bn_stats: bad arguments");
-    PCB_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * c, ST));
-    PCB_CUDA(cudaMemsetAsync(sqsum, 0, sizeof(double) * c, ST));
+    if (sqsum == sum + c) PCB_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * c, ST));       // one [2][c] buffer: one memset
+    else {
+        PCB_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * c, ST));
+        PCB_CUDA(cudaMemsetAsync(sqsum, 0, sizeof(double) * c, ST));
+    }
     if (c % 8 == 0 && c <= 2048) {
         const int rpb = EW_THREADS / (c / 8);
         const int grid = ew_grid_red(count, rpb * 16);
@@ -597,8 +600,11 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
         PCB_LAUNCH_CHECK();
         return 0;
     }
-    PCB_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(double) * c, ST));
-    PCB_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(double) * c, ST));
+    if (sum_gx == sum_g + c) PCB_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(double) * 2 * c, ST));
+    else {
+        PCB_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(double) * c, ST));
+        PCB_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(double) * c, ST));
+    }
     const int rpb = EW_THREADS / (c / 8);
     const int grid = ew_grid_red(count, rpb * 16);
     if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);

@@ -123,7 +123,7 @@ bool pcb_tc_eligible(const pcb_conv *c);
 bool pcb_tc_dgrad_supported(const pcb_conv *c);
 size_t pcb_tc_workspace(const pcb_conv *c);
 void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems);
-int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, cudaStream_t st);
+int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st);
 int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
                       uint64_t *tapmask, cudaStream_t st);
 int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,

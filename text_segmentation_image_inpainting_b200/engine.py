@@ -57,6 +57,7 @@ class TrainStep:
     def __init__(self, net: torch.nn.Module, compute_dtype=torch.bfloat16, lr=2e-4, momentum=0.9, weight_decay=1e-4,
                  nesterov=True, process_group=None, use_graph=True, bucket_mb=32):
         self.net = net.train()
+        ops.set_inplace_weight_refresh(True)          # one optimiser step per forward/backward pair: operand buffers are reused
         self.dtype = compute_dtype
         self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
         self.flat = FlatParams(net)

@@ -253,12 +253,22 @@ class PartialConvFn(torch.autograd.Function):
             _lib.check(lib.pcb_pconv_renorm_backward(ctypes.byref(c), gy.data_ptr(), nhwc_layout(gy), msum.data_ptr(), dc.data_ptr(), dcs,
                                                      _ptr(dbias), _stream()))
         dw = None
+        need = [ctx.needs_input_grad[5 + i] for i in range(len(xs))]
+        side = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty((geom.cout, geom.cin // geom.groups, geom.kh, geom.kw), dtype=torch.float32, device=dev, memory_format=CL)
             ws = _workspace(lib, c, dev)
-            with _Timed("wgrad", geom):
-                _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
-        need = [ctx.needs_input_grad[5 + i] for i in range(len(xs))]
+            # weight and data gradient only share their input dc: run the weight gradient on a side stream so that the two
+            # kernels of a low-resolution layer (far fewer tiles than SMs each) fill the GPU together.  Buffers are
+            # allocated on the main stream before the fork and the streams re-join before this function returns.
+            if _OVERLAP_WGRAD and any(need) and _PROFILE is None:
+                side = _side_stream(dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
+            else:
+                with _Timed("wgrad", geom):
+                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
         gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
         if any(need):
             # full-resolution gradient buffer per source tensor; parts write their channel slices
@@ -294,6 +304,8 @@ class PartialConvFn(torch.autograd.Function):
                     gxs[i] = g
                 else:
                     gxs[i] = full[i]
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         return (None, None, dw, dbias, None, *gxs)
 
 
@@ -305,6 +317,17 @@ def bump_weight_epoch():
     e.g. `sgd_step`, which does not bump tensor version counters)."""
     global _WEIGHT_EPOCH
     _WEIGHT_EPOCH += 1
+
+
+_INPLACE_WEIGHT_REFRESH = False
+
+
+def set_inplace_weight_refresh(enabled: bool):
+    """Training engines that update the masters once per step (after every backward of that step has run) may let
+    `prepare_weight` rewrite the cached operand buffers in place instead of allocating + zero-filling new ones each step.
+    Off by default: a backward that runs after a later weight update would otherwise read the new weights."""
+    global _INPLACE_WEIGHT_REFRESH
+    _INPLACE_WEIGHT_REFRESH = bool(enabled)
 
 
 def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
@@ -322,11 +345,33 @@ def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
     fe, de = ctypes.c_size_t(0), ctypes.c_size_t(0)
     lib.pcb_conv_weight_layout(ctypes.byref(c), ctypes.byref(fe), ctypes.byref(de))
     tdt = torch.bfloat16 if geom.dtype == PCB_BF16 else torch.float32
-    w_fwd = torch.empty((fe.value,), dtype=tdt, device=wm.device)
-    w_dg = torch.empty((de.value,), dtype=tdt, device=wm.device) if de.value else None
-    _lib.check(lib.pcb_conv_weight_prepare(ctypes.byref(c), wm.data_ptr(), w_fwd.data_ptr(), _ptr(w_dg), _stream()))
+    old = cache.get("val")
+    if _INPLACE_WEIGHT_REFRESH and old is not None and cache.get("sig") == (geom.signature, str(wm.device), fe.value, de.value):
+        w_fwd, w_dg = old
+        _lib.check(lib.pcb_conv_weight_refresh(ctypes.byref(c), wm.data_ptr(), w_fwd.data_ptr(), _ptr(w_dg), _stream()))
+    else:
+        w_fwd = torch.empty((fe.value,), dtype=tdt, device=wm.device)
+        w_dg = torch.empty((de.value,), dtype=tdt, device=wm.device) if de.value else None
+        _lib.check(lib.pcb_conv_weight_prepare(ctypes.byref(c), wm.data_ptr(), w_fwd.data_ptr(), _ptr(w_dg), _stream()))
+    cache["sig"] = (geom.signature, str(wm.device), fe.value, de.value)
     cache["key"], cache["val"] = key, (w_fwd, w_dg)
     return cache["val"]
+
+
+_OVERLAP_WGRAD = True
+_SIDE_STREAMS = {}
+
+
+def set_overlap_wgrad(enabled: bool):
+    global _OVERLAP_WGRAD
+    _OVERLAP_WGRAD = bool(enabled)
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 class RenormHandoff:
