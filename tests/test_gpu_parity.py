@@ -161,6 +161,40 @@ def test_train_step_engine_graph_matches_eager(dev):
     assert losses[0][0] > 0 and all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(*losses)), losses
 
 
+def test_gradient_sink_matches_autograd_accumulation(dev):
+    """engine.FlatParams registers in-place gradient sinks on the conv weights (ops.GradSink, written from a side stream and
+    joined by ops.join_side_streams): the arena must hold the gradients autograd would have accumulated (fp32 split-K adds
+    are unordered: compare to 1e-4 of max)."""
+    from text_segmentation_image_inpainting_b200 import ops
+    from text_segmentation_image_inpainting_b200.engine import FlatParams
+    from text_segmentation_image_inpainting_b200.masks import HoleMask
+    from text_segmentation_image_inpainting_b200.models.image_inpainting import ImageFillOrigin
+    from text_segmentation_image_inpainting_b200.synthetic import random_hole_masks
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(7)).to(dev)      # 8 stride-2 levels: >= 256
+    mask = torch.from_numpy(random_hole_masks(2, 256, 256, seed=9)).to(dev)
+
+    def run(with_sinks):
+        torch.manual_seed(0)
+        net = ImageFillOrigin().to(dev).train()
+        flat = FlatParams(net) if with_sinks else None
+        buf = torch.zeros((2, 8, 256, 256), dtype=torch.bfloat16, device=dev).contiguous(memory_format=torch.channels_last)
+        xin = buf[:, :3]
+        xin.copy_(x * mask)
+        ops.bump_weight_epoch()
+        out = net((xin, HoleMask.from_dense(mask, channel_uniform=True)))
+        ops.l1_mean(out).backward()
+        ops.join_side_streams()
+        torch.cuda.synchronize()
+        if with_sinks:
+            unused = [i for i, sk in enumerate(flat.sinks) if not sk.used]
+            assert flat.sinks and not unused, unused
+        return {n: p.grad.detach().float().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    ref, got = run(False), run(True)
+    bad = {n: relerr(got[n], ref[n]) for n in ref if relerr(got[n], ref[n]) > 1e-4}
+    assert not bad, bad
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # dense segmentation path (Conv_block / DSConvBlock / InvertedResidual / scSE / RFB / ASP / pooling / bilinear)
 # ---------------------------------------------------------------------------------------------------------------

@@ -51,6 +51,12 @@ class FlatParams:
                 p.data = v
                 p.grad = _flat_view(self.flat_g, o, p.data)
         self.true_numel = total
+        # convolution weights: the weight-gradient kernels write straight into the arena (ops.GradSink)
+        self.sinks = []
+        for p in self.params:
+            if p.dim() == 4 and p.grad.is_contiguous(memory_format=CL) and (p.grad.data_ptr() % 16) == 0:
+                p._pcb_grad_sink = ops.GradSink(p.grad)
+                self.sinks.append(p._pcb_grad_sink)
 
 
 class TrainStep:
@@ -93,11 +99,14 @@ class TrainStep:
 
     def _fwd_bwd(self, x, mask):
         self.flat.flat_g.zero_()
+        for sk in self.flat.sinks:
+            sk.used = False
         ops.bump_weight_epoch()
         xin, hm = self._prepare(x, mask)
         out = self.net((xin, hm))
         loss = ops.l1_mean(out)
         loss.backward()
+        ops.join_side_streams()
         return loss.detach()
 
     def _update(self, first_step: bool):

@@ -255,20 +255,36 @@ class PartialConvFn(torch.autograd.Function):
         dw = None
         need = [ctx.needs_input_grad[5 + i] for i in range(len(xs))]
         side = None
+        deferred = False
         if ctx.needs_input_grad[2]:
-            dw = torch.empty((geom.cout, geom.cin // geom.groups, geom.kh, geom.kw), dtype=torch.float32, device=dev, memory_format=CL)
+            # A training engine may register a gradient sink on the parameter (engine.FlatParams: a view of its flat fp32
+            # gradient arena with the weight's physical layout).  The kernel then writes the gradient in place (it overwrites:
+            # no accumulation pass) and autograd gets no tensor; with the side stream below the join can then wait until
+            # the engine calls join_side_streams(), so the weight gradient also overlaps the element-wise backward kernels
+            # of the layers that follow.  A second use of the same weight in one pass falls back to autograd accumulation.
+            sink = getattr(ctx.weight_ref, "_pcb_grad_sink", None)
+            shape = (geom.cout, geom.cin // geom.groups, geom.kh, geom.kw)
+            if sink is not None and not sink.used and tuple(sink.view.shape) == shape and sink.view.dtype == torch.float32 \
+                    and sink.view.is_contiguous(memory_format=CL):
+                dw_buf, sink.used = sink.view, True
+            else:
+                sink = None
+                dw_buf = dw = torch.empty(shape, dtype=torch.float32, device=dev, memory_format=CL)
             ws = _workspace(lib, c, dev)
             # weight and data gradient only share their input dc: run the weight gradient on a side stream so that the two
             # kernels of a low-resolution layer (far fewer tiles than SMs each) fill the GPU together.  Buffers are
             # allocated on the main stream before the fork and the streams re-join before this function returns.
-            if _OVERLAP_WGRAD and any(need) and _PROFILE is None:
+            if _OVERLAP_WGRAD and (any(need) or sink is not None) and _PROFILE is None:
                 side = _side_stream(dev)
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
+                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
+                if sink is not None:
+                    deferred = True
+                    _DEFERRED.append((dc, ws, xs))            # keep the side stream's operands alive until the join
             else:
                 with _Timed("wgrad", geom):
-                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw.data_ptr(), ws.data_ptr(), _stream()))
+                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
         gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
         if any(need):
             # full-resolution gradient buffer per source tensor; parts write their channel slices
@@ -304,7 +320,7 @@ class PartialConvFn(torch.autograd.Function):
                     gxs[i] = g
                 else:
                     gxs[i] = full[i]
-        if side is not None:
+        if side is not None and not deferred:
             torch.cuda.current_stream().wait_stream(side)
         return (None, None, dw, dbias, None, *gxs)
 
@@ -360,6 +376,22 @@ def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
 
 _OVERLAP_WGRAD = True
 _SIDE_STREAMS = {}
+_DEFERRED = []
+
+
+class GradSink:
+    """In-place destination for a convolution weight gradient (see PartialConvFn.backward).  The owner resets `used` before
+    every backward pass and calls join_side_streams() after it."""
+
+    def __init__(self, view: torch.Tensor):
+        self.view, self.used = view, False
+
+
+def join_side_streams():
+    """Make the current stream wait for every weight gradient still running on a side stream (gradient sinks only)."""
+    for st in _SIDE_STREAMS.values():
+        torch.cuda.current_stream().wait_stream(st)
+    _DEFERRED.clear()
 
 
 def set_overlap_wgrad(enabled: bool):
