@@ -219,11 +219,20 @@ def layer_profile(ts, x, mask, peaks, verbose):
     fl, ms, n = dom[1]
     achieved = fl / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    return {"bound": "tensor", "kernel": {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ pconv_tc_persistent_kernel for the stem)", "tc_dgrad": "pconv_tc_tma_kernel<MODE=1>",
-                                          "tc_wgrad": "pconv_tc_wgrad_kernel"}[dom[0]],
+    # DRAM bytes per launch of that family from the committed `ncu --set full` capture of one step (profiles/README.md)
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic_final.json")))[dom[0]]
+        traffic = t["dram_bytes"] / max(t["launches"], 1)
+    except Exception:  # noqa: BLE001
+        pass
+    return {"bound": "tensor", "kernel": {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ smallco_fwd / pconv_tc_persistent_kernel for tail / stem)",
+                                          "tc_dgrad": "pconv_tc_tma_kernel<MODE=1> (+ smallco_dgrad for the tail)",
+                                          "tc_wgrad": "pconv_tc_wgrad_tma_kernel (+ smallco_wgrad / pconv_tc_wgrad_kernel for tail / stem)"}[dom[0]],
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",
-            "launches_per_step": n, "flops_per_step": fl, "ms_per_step_in_kernel": ms, "traffic": None}, fam
+            "launches_per_step": n, "flops_per_step": fl, "ms_per_step_in_kernel": ms, "traffic": traffic,
+            "traffic_note": "mean dram__bytes_read+write per TMA-path launch of the family, ncu --set full of one step"}, fam
 
 
 def run_b200(args):
