@@ -93,6 +93,13 @@ int pcb_conv_weight_refresh(const pcb_conv *c, const float *w_master_krsc, void 
  * workspace : pcb_pconv_workspace(c) bytes (may be NULL when that is 0)                        */
 int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
                       uint8_t *newmask, void *workspace, pcb_stream_t stream);
+/* The same in two calls, for callers that run a network's mask chain ahead of its feature path on another stream
+ * (mask updates never depend on features, partial_convolution.py:59-77): pcb_pconv_mask_pass computes what depends only
+ * on the masks (msum, newmask and, in `workspace`, the tap-validity words the chosen kernel wants);
+ * pcb_pconv_forward_premasked is the rest and must be ordered after it (same arguments as pcb_pconv_forward). */
+int pcb_pconv_mask_pass(const pcb_conv *c, float *msum, uint8_t *newmask, void *workspace, pcb_stream_t stream);
+int pcb_pconv_forward_premasked(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                      uint8_t *newmask, void *workspace, pcb_stream_t stream);
 
 /* Backward of the renormalisation (autograd of partial_convolution.py:71-72):
  *   dc = dy * [s>0] / s          (NHWC [n,ho,wo,dc_cstride]; channels [cout, dc_cstride) zeroed)

@@ -81,12 +81,13 @@ PCB_API int pcb_conv_weight_refresh(const pcb_conv *c, const float *w_master_krs
     return weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, false, stream);
 }
 
-PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
-                              uint8_t *newmask, void *workspace, pcb_stream_t stream) {
+static int pconv_forward_impl(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                              uint8_t *newmask, void *workspace, bool mask_pass_done, pcb_stream_t stream) {
     if (int rc = validate(c, true)) return rc;
     PCB_CHECK(w_fwd && y && msum && newmask && y_cstride >= c->cout, "pcb_pconv_forward: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
+    if (!mask_pass_done)
+        if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
     if (use_dw(c)) {
         PCB_CHECK(y_cstride % 8 == 0, "depthwise forward: y channel stride must be a multiple of 8");
         return pcb_dw_forward(c, w_fwd, bias, y, y_cstride, msum, st);
@@ -94,9 +95,34 @@ PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float 
     if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr, "pcb_pconv_forward: workspace required for the tensor-core path");
         PCB_CHECK((reinterpret_cast<uintptr_t>(w_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "w / y must be 16-byte aligned");
-        return pcb_tc_forward_ws(c, w_fwd, bias, y, y_cstride, msum, static_cast<uint64_t *>(workspace), st);
+        return pcb_tc_forward_ws(c, w_fwd, bias, y, y_cstride, msum, static_cast<uint64_t *>(workspace), mask_pass_done, st);
     }
     return pcb_generic_forward(c, w_fwd, bias, y, y_cstride, msum, st);
+}
+
+PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                              uint8_t *newmask, void *workspace, pcb_stream_t stream) {
+    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, false, stream);
+}
+
+// The forward in two calls, for callers that run the mask chain of a network ahead of the feature path on another stream:
+// pcb_pconv_mask_pass computes everything that depends only on the masks (msum, newmask, the tap-validity words in
+// `workspace`); pcb_pconv_forward_premasked is the rest and must be ordered after it.
+PCB_API int pcb_pconv_mask_pass(const pcb_conv *c, float *msum, uint8_t *newmask, void *workspace, pcb_stream_t stream) {
+    if (int rc = validate(c, false)) return rc;
+    PCB_CHECK(msum && newmask, "pcb_pconv_mask_pass: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
+    if (use_tc(c) && !use_dw(c)) {
+        PCB_CHECK(workspace != nullptr, "pcb_pconv_mask_pass: workspace required for the tensor-core path");
+        return pcb_tc_forward_mask_pass(c, static_cast<uint64_t *>(workspace), st);
+    }
+    return 0;
+}
+
+PCB_API int pcb_pconv_forward_premasked(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                                        uint8_t *newmask, void *workspace, pcb_stream_t stream) {
+    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, true, stream);
 }
 
 PCB_API int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_fwd, const void *w_dgrad,

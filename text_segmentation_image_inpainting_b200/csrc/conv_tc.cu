@@ -2027,23 +2027,31 @@ int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd,
     return 0;
 }
 
+// the part of the forward that only depends on the masks: tap-validity words for the kernels that want them
+int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t st) {
+    const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
+    PCB_CHECK(m_total < (1ll << 31), "problem too large");
+    const Layout L = layout_of(c);
+    if (smallco_ok(c)) return 0;
+    if (tma_fwd_ok(c)) {                                  // row-halo tiles: the fixers read the mask planes themselves
+        int bw, bh, bn;
+        tile_box(c->wo, c->ho, &bw, &bh, &bn);
+        if (tma_halo_ok(c, bw, bh, bn, pick_bn(c->cout <= 32 ? 32 : L.rows_f, m_total))) return 0;
+    }
+    return launch_tapmask(c, tapmask, st);
+}
+
 int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
-                      uint64_t *tapmask, cudaStream_t st) {
+                      uint64_t *tapmask, bool mask_pass_done, cudaStream_t st) {
     int *flag = abort_flag_ptr();
     PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(y_cstride % 8 == 0 && y_cstride >= c->cout, "tensor-core forward: y channel stride must be a multiple of 8 and >= cout");
     const Layout L = layout_of(c);
+    if (!mask_pass_done)
+        if (int rc = pcb_tc_forward_mask_pass(c, tapmask, st)) return rc;
     if (smallco_ok(c)) return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
-    bool need_tapmask = true;
-    if (tma_fwd_ok(c)) {                                  // row-halo tiles: the fixers read the mask planes themselves
-        int bw, bh, bn;
-        tile_box(c->wo, c->ho, &bw, &bh, &bn);
-        need_tapmask = !tma_halo_ok(c, bw, bh, bn, pick_bn(c->cout <= 32 ? 32 : L.rows_f, m_total));
-    }
-    if (need_tapmask)
-        if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     TcParams P;
     base_params(P, c, L);
     P.m_total = static_cast<int>(m_total);

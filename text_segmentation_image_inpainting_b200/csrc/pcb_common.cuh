@@ -124,8 +124,9 @@ bool pcb_tc_dgrad_supported(const pcb_conv *c);
 size_t pcb_tc_workspace(const pcb_conv *c);
 void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems);
 int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st);
+int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t st);
 int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
-                      uint64_t *tapmask, cudaStream_t st);
+                      uint64_t *tapmask, bool mask_pass_done, cudaStream_t st);
 int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
                  cudaStream_t st);
 int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, cudaStream_t st);

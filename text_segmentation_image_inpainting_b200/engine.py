@@ -64,6 +64,7 @@ class TrainStep:
                  nesterov=True, process_group=None, use_graph=True, bucket_mb=32):
         self.net = net.train()
         ops.set_inplace_weight_refresh(True)          # one optimiser step per forward/backward pair: operand buffers are reused
+        ops.set_mask_chain_stream(True)               # mask passes run ahead on their own stream; joined in _fwd_bwd
         self.dtype = compute_dtype
         self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
         self.flat = FlatParams(net)

@@ -214,13 +214,42 @@ class PartialConvFn(torch.autograd.Function):
             y = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, xs[0].dtype, dev)
         else:
             y = torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=xs[0].dtype, device=dev, memory_format=CL)
-        msum = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.float32, device=dev)
-        newmask = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.uint8, device=dev)
-        ws = _workspace(lib, c, dev)
         b32 = bias.detach().float().contiguous() if bias is not None else None
-        with _Timed("fwd", geom):
-            _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
-                                             newmask.data_ptr(), ws.data_ptr(), _stream()))
+        global _LAST_MASK_EVENT
+        _LAST_MASK_EVENT = None
+        if _MASK_CHAIN_STREAM and _PROFILE is None and not geom.plain:
+            # Mask updates never depend on features (partial_convolution.py:59-77): the mask pass of this layer runs on the
+            # mask stream, ordered only after the passes that produced its input planes, i.e. ahead of the feature path.
+            # Its buffers are allocated on that stream and kept alive until join_side_streams() (engine, once per step).
+            main, ms = torch.cuda.current_stream(), _mask_stream(dev)
+            for (_, _, _, pl, _) in geom.parts:
+                if pl is None:
+                    continue
+                ev_in = getattr(pl, "_pcb_ev", None)
+                if ev_in is None:                        # a plane written on the main stream (the network's input mask): mark it
+                    ev_in = torch.cuda.Event()           # ready from here on, so later consumers (the tail) need not wait for main
+                    ev_in.record(main)
+                    pl._pcb_ev = ev_in
+                ms.wait_event(ev_in)
+            with torch.cuda.stream(ms):
+                msum = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.float32, device=dev)
+                newmask = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.uint8, device=dev)
+                ws = _workspace(lib, c, dev)
+                _lib.check(lib.pcb_pconv_mask_pass(ctypes.byref(c), msum.data_ptr(), newmask.data_ptr(), ws.data_ptr(), _stream()))
+                ev = torch.cuda.Event()
+                ev.record()
+            main.wait_event(ev)
+            _DEFERRED.append((msum, newmask, ws))
+            _LAST_MASK_EVENT = ev
+            _lib.check(lib.pcb_pconv_forward_premasked(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y),
+                                                       msum.data_ptr(), newmask.data_ptr(), ws.data_ptr(), _stream()))
+        else:
+            msum = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.float32, device=dev)
+            newmask = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.uint8, device=dev)
+            ws = _workspace(lib, c, dev)
+            with _Timed("fwd", geom):
+                _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
+                                                 newmask.data_ptr(), ws.data_ptr(), _stream()))
         ctx.geom, ctx.wprep, ctx.has_bias, ctx.weight_ref = geom, wprep, bias is not None, weight
         ctx.handoff = handoff
         if handoff is not None:
@@ -375,8 +404,25 @@ def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
 
 
 _OVERLAP_WGRAD = True
+_MASK_CHAIN_STREAM = False
+_LAST_MASK_EVENT = None
 _SIDE_STREAMS = {}
+_MASK_STREAMS = {}
 _DEFERRED = []
+
+
+def set_mask_chain_stream(enabled: bool):
+    """Run every layer's mask pass (mask box sums, new mask, tap-validity words) on a dedicated stream ahead of the feature
+    path.  Only for callers that call join_side_streams() once per step (the buffers of the pass live until then)."""
+    global _MASK_CHAIN_STREAM
+    _MASK_CHAIN_STREAM = bool(enabled)
+
+
+def _mask_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _MASK_STREAMS:
+        _MASK_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _MASK_STREAMS[key]
 
 
 class GradSink:
@@ -389,7 +435,7 @@ class GradSink:
 
 def join_side_streams():
     """Make the current stream wait for every weight gradient still running on a side stream (gradient sinks only)."""
-    for st in _SIDE_STREAMS.values():
+    for st in list(_SIDE_STREAMS.values()) + list(_MASK_STREAMS.values()):
         torch.cuda.current_stream().wait_stream(st)
     _DEFERRED.clear()
 
@@ -443,11 +489,15 @@ def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_
     geom = ConvGeom(xs, ups, cout, tuple(weight.shape[2:]), stride, padding, dilation, groups, same_holes, no_guard, parts, plain=plain)
     wprep = prepare_weight(weight, geom, cache if cache is not None else {})
     y, msum, newmask = PartialConvFn.apply(geom, wprep, weight, bias, handoff, *xs)
+    planes = [newmask[g] for g in range(geom.mg)]
+    if _LAST_MASK_EVENT is not None:                      # written on the mask stream: consumers there wait on this event
+        for pl in planes:
+            pl._pcb_ev = _LAST_MASK_EVENT
     if geom.mg == 1:
-        new = HoleMask.from_plane(newmask[0], cout, 0)
+        new = HoleMask.from_plane(planes[0], cout, 0)
     else:
         cog = cout // groups
-        new = HoleMask([(newmask[g], cog, 0) for g in range(groups)], n, geom.ho, geom.wo)
+        new = HoleMask([(planes[g], cog, 0) for g in range(groups)], n, geom.ho, geom.wo)
     return y, new
 
 
