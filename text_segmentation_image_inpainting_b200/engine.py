@@ -63,8 +63,6 @@ class TrainStep:
     def __init__(self, net: torch.nn.Module, compute_dtype=torch.bfloat16, lr=2e-4, momentum=0.9, weight_decay=1e-4,
                  nesterov=True, process_group=None, use_graph=True, bucket_mb=32):
         self.net = net.train()
-        ops.set_inplace_weight_refresh(True)          # one optimiser step per forward/backward pair: operand buffers are reused
-        ops.set_mask_chain_stream(True)               # mask passes run ahead on their own stream; joined in _fwd_bwd
         self.dtype = compute_dtype
         self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
         self.flat = FlatParams(net)
@@ -103,11 +101,19 @@ class TrainStep:
         for sk in self.flat.sinks:
             sk.used = False
         ops.bump_weight_epoch()
-        xin, hm = self._prepare(x, mask)
-        out = self.net((xin, hm))
-        loss = ops.l1_mean(out)
-        loss.backward()
-        ops.join_side_streams()
+        # scheduling switches that are only safe inside a loop that joins once per step (scoped to this call):
+        # operand buffers refreshed in place, mask passes running ahead on their own stream
+        ops.set_inplace_weight_refresh(True)
+        ops.set_mask_chain_stream(True)
+        try:
+            xin, hm = self._prepare(x, mask)
+            out = self.net((xin, hm))
+            loss = ops.l1_mean(out)
+            loss.backward()
+        finally:
+            ops.set_mask_chain_stream(False)
+            ops.set_inplace_weight_refresh(False)
+            ops.join_side_streams()
         return loss.detach()
 
     def _update(self, first_step: bool):
