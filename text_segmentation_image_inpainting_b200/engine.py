@@ -66,6 +66,7 @@ class TrainStep:
         self.dtype = compute_dtype
         self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
         self.flat = FlatParams(net)
+        self._wcaches = [m._wcache for m in net.modules() if isinstance(getattr(m, "_wcache", None), dict)]
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
@@ -106,6 +107,7 @@ class TrainStep:
         ops.set_inplace_weight_refresh(True)
         ops.set_mask_chain_stream(True)
         try:
+            ops.prefetch_weights(self._wcaches)        # operand re-layout of all layers runs ahead on its own stream
             xin, hm = self._prepare(x, mask)
             out = self.net((xin, hm))
             loss = ops.l1_mean(out)

@@ -380,6 +380,10 @@ def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
     (pcb_conv_weight_layout / pcb_conv_weight_prepare), cached per parameter version and problem signature."""
     key = (weight.data_ptr(), weight._version, str(weight.device), _WEIGHT_EPOCH, geom.signature)
     if cache.get("key") == key:
+        ev = cache.get("ready")
+        if ev is not None:                                # refreshed ahead of time on the prefetch stream (prefetch_weights)
+            torch.cuda.current_stream().wait_event(ev)
+            cache["ready"] = None
         return cache["val"]
     lib = _lib.load()
     wm = weight.detach()
@@ -400,7 +404,43 @@ def prepare_weight(weight: torch.Tensor, geom: ConvGeom, cache: dict):
         _lib.check(lib.pcb_conv_weight_prepare(ctypes.byref(c), wm.data_ptr(), w_fwd.data_ptr(), _ptr(w_dg), _stream()))
     cache["sig"] = (geom.signature, str(wm.device), fe.value, de.value)
     cache["key"], cache["val"] = key, (w_fwd, w_dg)
+    cache["ready"] = None
+    cache["geom"], cache["weight"] = geom, weight         # remembered for prefetch_weights()
     return cache["val"]
+
+
+_PREFETCH_STREAMS = {}
+
+
+def prefetch_weights(caches):
+    """Re-lay-out the convolution weights behind `caches` (the per-module operand caches) on a prefetch stream, ahead of the layers' forward calls (training
+    engines call this right after the optimiser step / epoch bump; requires the in-place refresh mode).  Each layer's
+    forward then only waits on its own event, so the re-layout of layer k overlaps the forward of the layers before it."""
+    caches = [c for c in caches if c.get("val") is not None and c.get("weight") is not None]
+    if not _INPLACE_WEIGHT_REFRESH or not caches:
+        return
+    lib = _lib.load()
+    dev = caches[0]["weight"].device
+    key_dev = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key_dev not in _PREFETCH_STREAMS:
+        _PREFETCH_STREAMS[key_dev] = torch.cuda.Stream(device=dev)
+    ps = _PREFETCH_STREAMS[key_dev]
+    ps.wait_stream(torch.cuda.current_stream())           # after the optimiser step, and after every reader of the old buffers
+    with torch.cuda.stream(ps):
+        for cache in caches:
+            weight, geom = cache["weight"], cache["geom"]
+            if weight.device != dev or weight.dtype != torch.float32:
+                continue
+            key = (weight.data_ptr(), weight._version, str(weight.device), _WEIGHT_EPOCH, geom.signature)
+            if cache.get("key") == key:
+                continue
+            wm = weight.detach().contiguous(memory_format=CL)
+            c = geom.struct(None)
+            w_fwd, w_dg = cache["val"]
+            _lib.check(lib.pcb_conv_weight_refresh(ctypes.byref(c), wm.data_ptr(), w_fwd.data_ptr(), _ptr(w_dg), _stream()))
+            ev = torch.cuda.Event()
+            ev.record()
+            cache["key"], cache["ready"] = key, ev
 
 
 _OVERLAP_WGRAD = True
@@ -435,7 +475,7 @@ class GradSink:
 
 def join_side_streams():
     """Make the current stream wait for every weight gradient still running on a side stream (gradient sinks only)."""
-    for st in list(_SIDE_STREAMS.values()) + list(_MASK_STREAMS.values()):
+    for st in list(_SIDE_STREAMS.values()) + list(_MASK_STREAMS.values()) + list(_PREFETCH_STREAMS.values()):
         torch.cuda.current_stream().wait_stream(st)
     _DEFERRED.clear()
 
