@@ -2167,6 +2167,21 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
         bn = pick_bn(L.ktap, m_class);
         if (bn == 32) bn = 64;
         if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
+        // The classes write disjoint pixels.  When one class does not fill the GPU (low-resolution layers) the four launches
+        // run concurrently: fork onto three internal streams after an event on `st`, join before returning (also valid
+        // inside a stream capture: the internal streams join the capture and leave it again).
+        const long long class_tiles = ((m_class + BLOCK_M - 1) / BLOCK_M) * (L.ktap / bn);
+        const bool fork = class_tiles < pcb_num_sms() && !getenv("PCB_DISABLE_CLASS_STREAMS");
+        static cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+        static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+        if (fork && aux[0] == nullptr) {
+            for (int i = 0; i < 3; ++i) {
+                PCB_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+                PCB_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+            }
+            PCB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        }
+        if (fork) PCB_CUDA(cudaEventRecord(ev_fork, st));
         for (int cls = 0; cls < 4; ++cls) {
             TcParams Q = P;
             const int py = cls >> 1, px = cls & 1;
@@ -2181,7 +2196,13 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
             const bool halo = !getenv("PCB_DISABLE_TMA_HALO") && Q.box_w == 128 && Q.box_h == 1 && Q.box_n == 1 && Q.kw >= 2 && 3 * stage <= 208 * 1024;
             CUtensorMap ta;
             if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, Q.box_w + (halo ? Q.kw - 1 : 0), Q.box_h, Q.box_n, 1)) return rc;
-            if (int rc = launch_tma<1>(Q, tm, ta, ta, bn, halo, st)) return rc;
+            cudaStream_t cs = (fork && cls > 0) ? aux[cls - 1] : st;
+            if (fork && cls > 0) PCB_CUDA(cudaStreamWaitEvent(cs, ev_fork, 0));
+            if (int rc = launch_tma<1>(Q, tm, ta, ta, bn, halo, cs)) return rc;
+            if (fork && cls > 0) {
+                PCB_CUDA(cudaEventRecord(ev_join[cls - 1], cs));
+                PCB_CUDA(cudaStreamWaitEvent(st, ev_join[cls - 1], 0));
+            }
         }
         return 0;
     }
