@@ -5,25 +5,32 @@
 // `masked_fill_`, `(out-b)/mask_sum+b`, `masked_fill_`, `ones_like`+`masked_fill_` -- and, in the U-Net
 // decoders, the `nn.Upsample` + `torch.cat` in front of it (models/image_inpainting.py:183-185).
 //
-// Forward / data-gradient kernel (one kernel, MODE template):
-//   GEMM view   M = output pixels (n*ho*wo) [fwd]  or input pixels (n*h*w) [dgrad]
-//               N = cout [fwd] / input channels [dgrad],  K walked tap-major in 64-element blocks
-//   A operand   im2col rows gathered by 4 producer warps with 16-byte cp.async (LDGSTS), zero-filled where
-//               the tap falls on padding or on a HOLE (x*mask folded into the load: no masked copy of x is
-//               ever materialised), across up to 2 concatenated sources, each optionally 2x nearest-upsampled
-//               (torch.cat + DoubleUpSample become index math) and optionally channel-padded.  Written
-//               straight into the 128B-swizzled K-major layout UMMA reads.
-//               Small-Cin "row-packed" mode (cin <= 8, e.g. the RGB stem): one K block = one kernel ROW,
-//               its eight 16-byte chunks are the taps of that row, so a 7x7x3 stem costs 7 K blocks, not 49.
-//   B operand   weights [N][K] bf16 (K padded to the same block structure), TMA 2D tiles (SWIZZLE_128B).
-//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BLOCK_N x K=16, fp32 accumulators in TMEM,
-//               issued by one thread; smem stages recycled through tcgen05.commit -> mbarrier.
-//   epilogue    TMEM -> registers (tcgen05.ld 32x32b), fwd: y = hole ? 0 : acc / s + bias (s = mask box
-//               sum), dgrad: dx_part = acc * input-mask of that part; bf16 NHWC stores.
+// Two generations of kernels live in this file:
 //
-// Weight-gradient kernel: D[k][co] (+)= sum_pixels x_gathered[p][k] * dc[p][co] per tap: both operands are
-// "pixel-row x 128-byte channel chunk" tiles, i.e. MN-major UMMA operands with the same swizzled smem image
-// as above; split-K over pixels with fp32 red.global.add into the (logical, unpadded) KRSC gradient.
+// (1) TMA-FED kernels (pconv_tc_tma_kernel, pconv_tc_wgrad_tma_kernel) -- the shipped hot path for power-of-two pixel grids.
+//     GEMM view   M = output pixels (n*ho*wo) [fwd]  or input pixels (n*h*w) [dgrad];  N = cout [fwd] / input channels [dgrad];
+//                 K walked tap-major in 64-element blocks.
+//     A operand   the im2col rows of a tap are ONE 4-D TMA tile of the NHWC tensor (a 128-pixel M tile is a box of the
+//                 pixel grid): padding = out-of-range zero fill, stride 2 = traversal stride, channel padding = map extent.
+//                 Holes (x*mask) are zeroed in the landed tile by fixer warps.  Row-halo tiles serve the kw taps of a kernel row
+//                 through row-shifted SWIZZLE_128B descriptors.  2x-upsampled sources are first copied densely into the
+//                 workspace (TMA cannot replicate pixels).
+//     B operand   weights [N][K] bf16 (K padded to the same block structure), TMA 2D tiles (SWIZZLE_128B).
+//     MMA         tcgen05.mma.cta_group::1.kind::f16, M=128 x N in {32,64,128,256} x K=16, fp32 accumulators in TMEM (two
+//                 stages), issued from an elect.sync region of a warp-converged issuer warp; stages recycled through
+//                 tcgen05.commit -> mbarrier.
+//     epilogue    TMEM -> registers (tcgen05.ld 32x32b), fwd: y = hole ? 0 : acc / s + bias (s = mask box sum),
+//                 dgrad: dx_part = acc * input-mask of that part; bf16 NHWC stores.  Stride-2 dgrad = four stride-1 parity classes.
+//     wgrad       D[k][co] (+)= sum_pixels x[p+tap][k] * dc[p][co]: both operands MN-major "pixel row x 128-byte channel chunk"
+//                 tiles by TMA, split-K over pixels with fp32 red.global.add into the (logical, unpadded) KRSC gradient.
+//
+// (2) cp.async-GATHER kernels (pconv_tc_persistent_kernel, pconv_tc_wgrad_kernel) -- the first generation, kept for shapes (1)
+//     does not take: arbitrary pixel grids, and the row-packed small-Cin mode (cin <= 8, e.g. the RGB stem: one K block = one
+//     kernel ROW, its eight 16-byte chunks are the taps of that row, so a 7x7x3 stem costs 7 K blocks, not 49).  Their A
+//     operand is gathered by 4 producer warps with 16-byte zero-filling cp.async from up to 2 concatenated, optionally
+//     2x-upsampled sources, driven by per-pixel tap-validity words (tapmask_kernel).
+//
+// DESIGN.md section 4 has the anatomy, the measured bounds and the microbenchmarks behind these choices.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
