@@ -629,11 +629,13 @@ constexpr int TMA_THREADS = 320;
 // shifted by whole 128-byte rows (the 128B swizzle is a function of the absolute smem address, so a row-shifted start
 // reads the same image: probed in tools/ubench/tma_probe.cu) -- kw x less A traffic from L2 and kw x fewer barrier
 // round trips per MMA.  K steps that only cover channel padding (c8 <= 16*k) are skipped.
-template <int BLOCK_N, int MODE, bool HALO>
+// PAIR: two CTAs of a cluster work on two adjacent M tiles with cta_group::2 MMAs (M = 256) issued by the leader (rank 0); each
+// CTA stages its own A tile and HALF of every weight tile.  The peer's MMA warp only relays "my stage is ready" to the leader.
+template <int BLOCK_N, int MODE, bool HALO, bool PAIR>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
-    constexpr uint32_t B_BYTES = BLOCK_N * 128;
+    constexpr uint32_t B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // this CTA's share of one weight tile
     constexpr int TCOLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
@@ -646,7 +648,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     const uint32_t STAGE_TX = A_BYTES + nB * B_BYTES;
     const uint32_t sBar = smem_base + S * STAGE;
     const uint32_t bar_full = sBar, bar_fixed = sBar + 8 * MAX_RING, bar_empty = sBar + 16 * MAX_RING;
-    const uint32_t bar_tmem_full = sBar + 24 * MAX_RING, bar_tmem_empty = bar_tmem_full + 16;
+    const uint32_t bar_peer = sBar + 24 * MAX_RING;                     // PAIR, leader only: the peer's stage s is ready
+    const uint32_t bar_tmem_full = sBar + 32 * MAX_RING, bar_tmem_empty = bar_tmem_full + 16;
     const uint32_t s_tmem_ptr = bar_tmem_empty + 16;
     uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_gen + (s_tmem_ptr - smem_base));
@@ -654,8 +657,13 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     const int np = (MODE == 0) ? P.nparts : 1;
     const int n_tiles = P.ncols / BLOCK_N;
-    const int KS = P.ksplit;                                            // tile index = (m tile * n_tiles + n tile) * KS + split
-    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * n_tiles * KS;
+    const int KS = PAIR ? 1 : P.ksplit;                                 // tile index = (m tile * n_tiles + n tile) * KS + split
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const int m_tiles = (P.m_total + BLOCK_M - 1) / BLOCK_M;
+    const int num_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * n_tiles * KS;      // PAIR: a tile is a pair of adjacent M tiles
+    const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tstep = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto m0_of = [&](int mt) -> int { return (PAIR ? mt * 2 + static_cast<int>(rank) : mt) * BLOCK_M; };
     const bool fix = (MODE == 0) && P.use_fix;
     const int kwi = HALO ? 1 : P.kw;                                   // A items per kernel row
 
@@ -669,17 +677,20 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_RING; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_fixed + 8 * s, 4); ptx::mbar_init(bar_empty + 8 * s, 1);
+            ptx::mbar_init(bar_peer + 8 * s, 1);
         }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_tmem_full + 8 * s, 1); ptx::mbar_init(bar_tmem_empty + 8 * s, 128); }
+        // PAIR: the leader's accumulator-drained barrier collects the epilogue threads of both CTAs
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_tmem_full + 8 * s, 1); ptx::mbar_init(bar_tmem_empty + 8 * s, PAIR ? 256 : 128); }
         ptx::fence_mbar_init();
     }
     if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_w); ptx::prefetch_tmap(&tmap_a0); if (np > 1) ptx::prefetch_tmap(&tmap_a1); }
     if (warp == 1) {
-        ptx::tmem_alloc<TCOLS>(s_tmem_ptr);
-        ptx::tmem_relinquish();
+        if (PAIR) { ptx::tmem_alloc_pair<TCOLS>(s_tmem_ptr); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc<TCOLS>(s_tmem_ptr); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (PAIR) ptx::cluster_sync();                                     // barriers of both CTAs initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_generic;
 
@@ -702,9 +713,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         long long tt_wait = 0, tt_issue = 0;
         const long long tt0 = clock64();
 #endif
-        for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
             const int sp = tile % KS, mn = tile / KS;
-            const int m0 = (mn / n_tiles) * BLOCK_M, n0 = (mn % n_tiles) * BLOCK_N;
+            const int m0 = m0_of(mn / n_tiles), n0 = (mn % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int img = m0 / plane, rem = m0 - img * plane;
             const int oy = rem / pwid, ox = rem - oy * pwid;
@@ -735,7 +746,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                                 ptx::tma_load_4d(dst, ma, c0, x, y, img, full);
                                 uint32_t bdst = dst + A_ROOM;
                                 for (int tc = 0, kb = kidx; tc < nB; ++tc, kb += col_k, bdst += B_BYTES)
-                                    ptx::tma_load_2d(bdst, &tmap_w, kb, n0, full);
+                                    ptx::tma_load_2d(bdst, &tmap_w, kb, n0 + (PAIR ? static_cast<int>(rank) * (BLOCK_N / 2) : 0), full);
                             }
                             __syncwarp();
 #ifdef PCB_TC_TIMING
@@ -752,7 +763,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #endif
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, 0, 0);
         const uint32_t ready = fix ? bar_fixed : bar_full;
         const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
         const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_ROOM, 16, 1024);
@@ -774,7 +785,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         long long n_items = 0;
         long long tm_wait = 0, tm_acc = 0, tm_issue = 0, tm_commit = 0;
         const long long t_begin = clock64();
-        for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
             const int sp = tile % KS;
             const int n0 = ((tile / KS) % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
@@ -782,8 +793,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #ifdef PCB_TC_TIMING
             const long long ta0 = clock64();
 #endif
-            // the epilogue must have drained this accumulator stage (two tiles ago)
-            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 126))) { dead = true; break; }
+            // the epilogue must have drained this accumulator stage (two tiles ago); PAIR: the peer only relays
+            if (!(PAIR && rank == 1))
+                if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 126))) { dead = true; break; }
 #ifdef PCB_TC_TIMING
             tm_acc += clock64() - ta0;
 #endif
@@ -805,21 +817,42 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                         const long long tq1 = clock64();
                         tm_wait += tq1 - tq0;
 #endif
+                        if (PAIR && rank == 1) {
+                            // peer: its stage (operands landed, holes fixed) is ready -> tell the leader, which issues for both
+                            if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(bar_peer + 8 * s, 0));
+                            __syncwarp();
+                            accum = 1;
+                            if (++s == S) { s = 0; ph ^= 1; }
+                            continue;
+                        }
+                        if (PAIR)
+                            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_peer + 8 * s, ph, P.abort_flag, 127))) { dead = true; break; }
                         ptx::tc_fence_after();
                         if (ptx::elect_one()) {
                             uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16 + shift0), db = desc_b0 + static_cast<uint64_t>(s * stage16);
                             if (cb + 1 < nbp || klast == 4) {
                                 for (int tc = 0; tc < nB; ++tc, da += dshift, db += B_BYTES >> 4) {
-                                    ptx::umma_bf16(d_tmem, da, db, idesc, (accum | tc) != 0);
-                                    ptx::umma_bf16_acc(d_tmem, da + 2, db + 2, idesc);
-                                    ptx::umma_bf16_acc(d_tmem, da + 4, db + 4, idesc);
-                                    ptx::umma_bf16_acc(d_tmem, da + 6, db + 6, idesc);
+                                    if (PAIR) {
+                                        ptx::umma_bf16_pair(d_tmem, da, db, idesc, (accum | tc) != 0);
+                                        ptx::umma_bf16_pair_acc(d_tmem, da + 2, db + 2, idesc);
+                                        ptx::umma_bf16_pair_acc(d_tmem, da + 4, db + 4, idesc);
+                                        ptx::umma_bf16_pair_acc(d_tmem, da + 6, db + 6, idesc);
+                                    } else {
+                                        ptx::umma_bf16(d_tmem, da, db, idesc, (accum | tc) != 0);
+                                        ptx::umma_bf16_acc(d_tmem, da + 2, db + 2, idesc);
+                                        ptx::umma_bf16_acc(d_tmem, da + 4, db + 4, idesc);
+                                        ptx::umma_bf16_acc(d_tmem, da + 6, db + 6, idesc);
+                                    }
                                 }
                             } else {
                                 for (int tc = 0; tc < nB; ++tc, da += dshift, db += B_BYTES >> 4)
-                                    for (int k = 0; k < klast; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (accum | tc | k) != 0);
+                                    for (int k = 0; k < klast; ++k) {
+                                        if (PAIR) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (accum | tc | k) != 0);
+                                        else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (accum | tc | k) != 0);
+                                    }
                             }
-                            ptx::umma_commit(bar_empty + 8 * s);
+                            if (PAIR) ptx::umma_commit_pair(bar_empty + 8 * s);
+                            else ptx::umma_commit(bar_empty + 8 * s);
                         }
                         __syncwarp();
 #ifdef PCB_TC_TIMING
@@ -832,7 +865,10 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                     if (dead) break;
                 }
             }
-            if (!dead && ptx::elect_one()) ptx::umma_commit(bar_tmem_full + 8 * acc);
+            if (!dead && !(PAIR && rank == 1) && ptx::elect_one()) {
+                if (PAIR) ptx::umma_commit_pair(bar_tmem_full + 8 * acc);
+                else ptx::umma_commit(bar_tmem_full + 8 * acc);
+            }
             __syncwarp();
             ++tile_iter;
         }
@@ -854,17 +890,17 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) {
                         wnext[p] = 0ull;
-                        const int m = (tl / KS / n_tiles) * BLOCK_M + t;
+                        const int m = m0_of(tl / KS / n_tiles) + t;
                         if (p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
                     }
                 };
-                load_words(blockIdx.x);
-                for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                load_words(tile0);
+                for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
                     const int sp = tile % KS;
                     uint64_t wcur[TC_MAX_PARTS];
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) wcur[p] = wnext[p];
-                    load_words(tile + gridDim.x);                      // next tile's words travel while this tile streams
+                    load_words(tile + tstep);                      // next tile's words travel while this tile streams
                     const int taps = P.kh * P.kw;
                     for (int tap = 0; tap < taps && !dead; ++tap) {
 #pragma unroll
@@ -900,7 +936,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                 auto load_bits = [&](int tl, uint32_t &b0, uint32_t &b1) {       // bit (p*8 + tr): pixel row is a hole
                     b0 = b1 = 0;
                     if (tl >= num_tiles) return;
-                    const int m0 = (tl / KS / n_tiles) * BLOCK_M;
+                    const int m0 = m0_of(tl / KS / n_tiles);
+                    if (m0 >= P.m_total) return;                   // PAIR: the peer's half of the last (odd) tile pair is empty
                     const int img = m0 / plane, rem = m0 - img * plane;
                     const int oy = rem / P.wo, ox = rem - oy * P.wo;
 #pragma unroll
@@ -918,11 +955,11 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                     }
                 };
                 uint32_t n0b, n1b;
-                load_bits(blockIdx.x, n0b, n1b);
-                for (int tile = blockIdx.x; tile < num_tiles && !dead; tile += gridDim.x) {
+                load_bits(tile0, n0b, n1b);
+                for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
                     const int sp = tile % KS;
                     const uint32_t c0b = n0b, c1b = n1b;
-                    load_bits(tile + gridDim.x, n0b, n1b);
+                    load_bits(tile + tstep, n0b, n1b);
                     for (int tr = 0; tr < P.kh && !dead; ++tr) {
 #pragma unroll
                         for (int p = 0; p < TC_MAX_PARTS; ++p) {
@@ -961,24 +998,27 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     } else {
         // ================================ epilogue warps (6-9) ================================
         int tile_iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tstep) {
             const int mn = tile / KS;
-            const int m0 = (mn / n_tiles) * BLOCK_M, n0 = (mn % n_tiles) * BLOCK_N;
+            const int m0 = m0_of(mn / n_tiles), n0 = (mn % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int acc = tile_iter & 1;
             if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 123)) break;
             tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0);
             ptx::tc_fence_before();
-            ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
+            if (PAIR && rank == 1) ptx::mbar_arrive_cluster(ptx::mapa(bar_tmem_empty + 8 * acc, 0));   // the leader waits for both epilogues
+            else ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
             ++tile_iter;
         }
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (PAIR) ptx::cluster_sync();                                     // no CTA leaves while its partner may still touch its smem / TMEM
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<TCOLS>(tmem_base);
+        if (PAIR) ptx::tmem_dealloc_pair<TCOLS>(tmem_base);
+        else ptx::tmem_dealloc<TCOLS>(tmem_base);
     }
 }
 
@@ -1898,26 +1938,43 @@ size_t tapmask_bytes(const pcb_conv *c) {
     return (static_cast<size_t>(c->nparts) * c->n * c->ho * c->wo * sizeof(uint64_t) + 255) / 256 * 256;
 }
 
-template <int BLOCK_N, int MODE, bool HALO>
+template <int BLOCK_N, int MODE, bool HALO, bool PAIR>
 int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, cudaStream_t st) {
     const int nb = HALO ? P.kw : 1;
     const size_t a_room = (static_cast<size_t>(BLOCK_M + (HALO ? (P.kw - 1) * P.dil : 0)) * 128 + 1023) / 1024 * 1024;
-    const size_t stage = a_room + static_cast<size_t>(nb) * BLOCK_N * 128;
+    const size_t stage = a_room + static_cast<size_t>(nb) * (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;
     P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (208 * 1024) / stage));
     PCB_CHECK(P.stages >= 2, "TMA-fed conv: stage of %zu bytes does not fit twice", stage);
-    const size_t smem = 1024 + P.stages * stage + 24 * MAX_RING + 64;
-    auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE, HALO>;
+    const size_t smem = 1024 + P.stages * stage + 32 * MAX_RING + 64;
+    auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE, HALO, PAIR>;
     static bool attr_done = false;
     if (!attr_done) {
         PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_done = true;
     }
     if (P.ksplit < 1) P.ksplit = 1;
-    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N) * P.ksplit;
-    const int grid = std::min(num_tiles, pcb_num_sms());
+    const int m_tiles = (P.m_total + BLOCK_M - 1) / BLOCK_M;
     P.dbg = debug_buffer();
-    kern<<<grid, TMA_THREADS, smem, st>>>(P, tw, ta0, ta1);
-    PCB_LAUNCH_CHECK();
+    int grid;
+    if (PAIR) {
+        // clusters of two CTAs (same TPC): the pair shares every weight tile, the leader issues M = 256 MMAs for both
+        const int pair_tiles = ((m_tiles + 1) / 2) * (P.ncols / BLOCK_N);
+        grid = 2 * std::min(pair_tiles, pcb_num_sms() / 2);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TMA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PCB_CUDA(cudaLaunchKernelEx(&cfg, kern, P, tw, ta0, ta1));
+        pcb_count_launch();
+    } else {
+        const int num_tiles = m_tiles * (P.ncols / BLOCK_N) * P.ksplit;
+        grid = std::min(num_tiles, pcb_num_sms());
+        kern<<<grid, TMA_THREADS, smem, st>>>(P, tw, ta0, ta1);
+        PCB_LAUNCH_CHECK();
+    }
     if (P.dbg) {
         static long long h[8 * 1024];
         cudaStreamSynchronize(st);
@@ -1941,17 +1998,31 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
 }
 
 template <int MODE>
-int launch_tma(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, int bn, bool halo, cudaStream_t st) {
-    if (halo) {
-        if (bn == 256) return launch_tma_n<256, MODE, true>(P, tw, ta0, ta1, st);
-        if (bn == 128) return launch_tma_n<128, MODE, true>(P, tw, ta0, ta1, st);
-        if (bn == 64) return launch_tma_n<64, MODE, true>(P, tw, ta0, ta1, st);
-        return launch_tma_n<32, MODE, true>(P, tw, ta0, ta1, st);
+int launch_tma(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, int bn, bool halo, cudaStream_t st, bool pair = false) {
+    if (pair) {
+        if (halo) {
+            if (bn == 128) return launch_tma_n<128, MODE, true, true>(P, tw, ta0, ta1, st);
+            return launch_tma_n<64, MODE, true, true>(P, tw, ta0, ta1, st);
+        }
+        if (bn == 256) return launch_tma_n<256, MODE, false, true>(P, tw, ta0, ta1, st);
+        if (bn == 128) return launch_tma_n<128, MODE, false, true>(P, tw, ta0, ta1, st);
+        return launch_tma_n<64, MODE, false, true>(P, tw, ta0, ta1, st);
     }
-    if (bn == 256) return launch_tma_n<256, MODE, false>(P, tw, ta0, ta1, st);
-    if (bn == 128) return launch_tma_n<128, MODE, false>(P, tw, ta0, ta1, st);
-    if (bn == 64) return launch_tma_n<64, MODE, false>(P, tw, ta0, ta1, st);
-    return launch_tma_n<32, MODE, false>(P, tw, ta0, ta1, st);
+    if (halo) {
+        if (bn == 256) return launch_tma_n<256, MODE, true, false>(P, tw, ta0, ta1, st);
+        if (bn == 128) return launch_tma_n<128, MODE, true, false>(P, tw, ta0, ta1, st);
+        if (bn == 64) return launch_tma_n<64, MODE, true, false>(P, tw, ta0, ta1, st);
+        return launch_tma_n<32, MODE, true, false>(P, tw, ta0, ta1, st);
+    }
+    if (bn == 256) return launch_tma_n<256, MODE, false, false>(P, tw, ta0, ta1, st);
+    if (bn == 128) return launch_tma_n<128, MODE, false, false>(P, tw, ta0, ta1, st);
+    if (bn == 64) return launch_tma_n<64, MODE, false, false>(P, tw, ta0, ta1, st);
+    return launch_tma_n<32, MODE, false, false>(P, tw, ta0, ta1, st);
+}
+
+// CTA pairs (opt-in, PCB_CTA_PAIR=1): N tiles of at least 64 columns, at least two M tiles, no split-K
+bool use_pair(int bn, long long m_total, int ksplit) {
+    return getenv("PCB_CTA_PAIR") != nullptr && bn >= 64 && bn <= 256 && m_total > BLOCK_M && ksplit <= 1;
 }
 
 // halo tiles: stride 1, the M tile is one image-row segment, a kernel row's halo fits the 256-pixel TMA box, and at
@@ -2108,6 +2179,10 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
             PCB_LAUNCH_CHECK();
             return 0;
         }
+        if (use_pair(bn, m_total, P.ksplit)) {            // each CTA of a pair loads half of every weight tile
+            if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, bn / 2)) return rc;
+            return launch_tma<0>(P, tm, ta[0], ta[1], bn, halo, st, true);
+        }
         return launch_tma<0>(P, tm, ta[0], ta[1], bn, halo, st);
     }
     if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, L.bn_f)) return rc;
@@ -2161,6 +2236,10 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
             splitk_finish_dgrad_kernel<<<static_cast<int>(std::min<long long>((work + 255) / 256, 8ll * pcb_num_sms())), 256, 0, st>>>(P.partial, P);
             PCB_LAUNCH_CHECK();
             return 0;
+        }
+        if (use_pair(bn, m_total, P.ksplit)) {
+            if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn / 2)) return rc;
+            return launch_tma<1>(P, tm, ta, ta, bn, halo, st, true);
         }
         return launch_tma<1>(P, tm, ta, ta, bn, halo, st);
     }
