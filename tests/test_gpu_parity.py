@@ -34,6 +34,17 @@ def test_partial_conv_module_fwd_bwd(tag, dev):
         assert res[k] <= res["tol"], (k, res)
 
 
+@pytest.mark.parametrize("tag", ["tma_halo_k3_192_64_two", "tma_halo_k3_d2_64_128_w256", "tma_k3_64_256_n256", "tma_k5_s2_64_128_box32x4"])
+def test_partial_conv_cta_pair_path(tag, dev, monkeypatch):
+    """The opt-in CTA-pair kernels (cluster of 2, tcgen05 cta_group::2, PCB_CTA_PAIR=1) must stay parity-green."""
+    monkeypatch.setenv("PCB_CTA_PAIR", "1")
+    res = conv_case(tag, dev)
+    assert _pipeline_clean(), "a tensor-core pipeline wait timed out"
+    assert res["mask_equal"] and res["tc"] == 1
+    for k in ("y", "gx", "gw", "gb"):
+        assert res[k] <= res["tol"], (k, res)
+
+
 @pytest.mark.parametrize("tag", sorted(LAZYCAT_CASES))
 def test_partial_conv_over_lazy_upsample_concat(tag, dev):
     """The decoder pattern: conv(cat([up2x(a), b])) without materialising the upsample or the concat."""
