@@ -676,7 +676,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_RING; ++s) {
-            ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_fixed + 8 * s, 4); ptx::mbar_init(bar_empty + 8 * s, 1);
+            ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_fixed + 8 * s, PAIR ? 8 : 4); ptx::mbar_init(bar_empty + 8 * s, 1);
             ptx::mbar_init(bar_peer + 8 * s, 1);
         }
         // PAIR: the leader's accumulator-drained barrier collects the epilogue threads of both CTAs
@@ -764,7 +764,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, 0, 0);
-        const uint32_t ready = fix ? bar_fixed : bar_full;
+        // PAIR: stage s is ready when the four fixer warps of BOTH CTAs arrived on the leader's bar_fixed (they run as plain
+        // relays when there are no holes to fix), so no extra hop sits between the peer's TMA landing and the leader's MMA
+        const uint32_t ready = (fix || PAIR) ? bar_fixed : bar_full;
         const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
         const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_ROOM, 16, 1024);
         const uint32_t stage16 = STAGE >> 4;
@@ -785,7 +787,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         long long n_items = 0;
         long long tm_wait = 0, tm_acc = 0, tm_issue = 0, tm_commit = 0;
         const long long t_begin = clock64();
-        for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
+        for (int tile = tile0; tile < num_tiles && !dead && !(PAIR && rank == 1); tile += tstep) {
             const int sp = tile % KS;
             const int n0 = ((tile / KS) % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
@@ -817,16 +819,6 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                         const long long tq1 = clock64();
                         tm_wait += tq1 - tq0;
 #endif
-                        if (PAIR && rank == 1) {
-                            // peer: its stage (operands landed, holes fixed) is ready -> tell the leader, which issues for both
-                            if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(bar_peer + 8 * s, 0));
-                            __syncwarp();
-                            accum = 1;
-                            if (++s == S) { s = 0; ph ^= 1; }
-                            continue;
-                        }
-                        if (PAIR)
-                            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_peer + 8 * s, ph, P.abort_flag, 127))) { dead = true; break; }
                         ptx::tc_fence_after();
                         if (ptx::elect_one()) {
                             uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16 + shift0), db = desc_b0 + static_cast<uint64_t>(s * stage16);
@@ -878,8 +870,9 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         }
     } else if (warp < 6) {
         // ================================ fixers: zero the hole rows of every landed A tile ================================
-        if (fix) {
+        if (fix || PAIR) {
             const int t = (warp - 2) * 32 + lane;
+            const uint32_t fixed_remote = PAIR ? ptx::mapa(bar_fixed, 0) : 0u;    // the leader's barriers
             int s = 0;
             uint32_t ph = 0;
             bool dead = false;
@@ -891,7 +884,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                     for (int p = 0; p < TC_MAX_PARTS; ++p) {
                         wnext[p] = 0ull;
                         const int m = m0_of(tl / KS / n_tiles) + t;
-                        if (p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
+                        if (fix && p < P.nparts && tl < num_tiles && m < P.m_total) wnext[p] = __ldg(P.parts[p].tapmask + m);
                     }
                 };
                 load_words(tile0);
@@ -901,14 +894,15 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #pragma unroll
                     for (int p = 0; p < TC_MAX_PARTS; ++p) wcur[p] = wnext[p];
                     load_words(tile + tstep);                      // next tile's words travel while this tile streams
+                    if (MODE == 1 && !tile_active(((tile / KS) % n_tiles) * BLOCK_N)) continue;
                     const int taps = P.kh * P.kw;
                     for (int tap = 0; tap < taps && !dead; ++tap) {
 #pragma unroll
                         for (int p = 0; p < TC_MAX_PARTS; ++p) {
                             if (p >= np) break;
-                            const bool hole = ((wcur[p] >> tap) & 1ull) == 0ull;
+                            const bool hole = fix && ((wcur[p] >> tap) & 1ull) == 0ull;
                             const bool any_hole = __any_sync(0xffffffffu, hole);
-                            const int nb = P.parts[p].kext / BLOCK_K;
+                            const int nb = ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
                             const int gb0 = (p == 0) ? 0 : P.parts[0].kext / BLOCK_K;
                             for (int cb = 0; cb < nb; ++cb) {
                                 if (KS > 1 && (gb0 + cb) % KS != sp) continue;
@@ -923,7 +917,10 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                                     ptx::fence_proxy_async_smem();
                                 }
                                 __syncwarp();
-                                if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                                if (lane == 0) {
+                                    if (PAIR && rank == 1) ptx::mbar_arrive_cluster(fixed_remote + 8 * s);
+                                    else ptx::mbar_arrive(bar_fixed + 8 * s);
+                                }
                                 if (++s == S) { s = 0; ph ^= 1; }
                             }
                             if (dead) break;
@@ -935,7 +932,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                 const int plane = P.ho * P.wo;
                 auto load_bits = [&](int tl, uint32_t &b0, uint32_t &b1) {       // bit (p*8 + tr): pixel row is a hole
                     b0 = b1 = 0;
-                    if (tl >= num_tiles) return;
+                    if (!fix || tl >= num_tiles) return;
                     const int m0 = m0_of(tl / KS / n_tiles);
                     if (m0 >= P.m_total) return;                   // PAIR: the peer's half of the last (odd) tile pair is empty
                     const int img = m0 / plane, rem = m0 - img * plane;
@@ -960,13 +957,14 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                     const int sp = tile % KS;
                     const uint32_t c0b = n0b, c1b = n1b;
                     load_bits(tile + tstep, n0b, n1b);
+                    if (MODE == 1 && !tile_active(((tile / KS) % n_tiles) * BLOCK_N)) continue;
                     for (int tr = 0; tr < P.kh && !dead; ++tr) {
 #pragma unroll
                         for (int p = 0; p < TC_MAX_PARTS; ++p) {
                             if (p >= np) break;
                             const bool h0 = (c0b >> (p * 8 + tr)) & 1u, h1 = (c1b >> (p * 8 + tr)) & 1u;
                             const bool any_hole = __any_sync(0xffffffffu, h0 || h1);
-                            const int nb = P.parts[p].kext / BLOCK_K;
+                            const int nb = ((MODE == 0) ? P.parts[p].kext : P.dc_kext) / BLOCK_K;
                             const int gb0 = (p == 0) ? 0 : P.parts[0].kext / BLOCK_K;
                             for (int cb = 0; cb < nb; ++cb) {
                                 if (KS > 1 && (gb0 + cb) % KS != sp) continue;
@@ -986,7 +984,10 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                                     ptx::fence_proxy_async_smem();
                                 }
                                 __syncwarp();
-                                if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                                if (lane == 0) {
+                                    if (PAIR && rank == 1) ptx::mbar_arrive_cluster(fixed_remote + 8 * s);
+                                    else ptx::mbar_arrive(bar_fixed + 8 * s);
+                                }
                                 if (++s == S) { s = 0; ph ^= 1; }
                             }
                             if (dead) break;
