@@ -97,8 +97,12 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB
-        if not os.path.exists(path) or (os.environ.get("PCB_REBUILD") == "1"):
-            path = _build.build()      # raises if nvcc is missing: no silent fallback
+        # stale or missing library -> rebuild (content fingerprint, file-locked: safe under torchrun); raises if nvcc is
+        # missing: no silent fallback, and never a silently stale .so
+        if os.environ.get("PCB_REBUILD") == "1":
+            path = _build.build(force=True)
+        elif _build.needs_build():
+            path = _build.build()
         lib = ctypes.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)    # AttributeError if the .so does not export what the header declares

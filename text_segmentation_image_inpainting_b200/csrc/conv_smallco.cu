@@ -402,10 +402,12 @@ bool fill(ScParams &P, const pcb_conv *c, const pcb_smallco_layout &L, bool grid
     return true;
 }
 
-int launch(void (*kern)(const ScParams), bool &attr_done, const ScParams &P, size_t smem, int ctas_per_sm, cudaStream_t st) {
-    if (!attr_done) {
+// `attr_done`: one flag per device for this kernel instantiation (function attributes are per device context)
+int launch(void (*kern)(const ScParams), bool (&attr_done)[PCB_MAX_DEVICES], const ScParams &P, size_t smem, int ctas_per_sm, cudaStream_t st) {
+    const int dev = pcb_cur_device();
+    if (!attr_done[dev]) {
         PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     const int grid = std::min(P.num_tiles, ctas_per_sm * pcb_num_sms());
     kern<<<grid, SC_THREADS, smem, st>>>(P);
@@ -438,7 +440,7 @@ int pcb_smallco_forward(const pcb_conv *c, const pcb_smallco_layout &L, const vo
     P.w_fwd = static_cast<const bf16 *>(w_fwd); P.bias = bias; P.msum = msum; P.y = static_cast<bf16 *>(y); P.y_cstride = y_cstride;
     const int taps = c->kh * c->kw, npix = (TH + c->kh - 1) * (TW + c->kw - 1);
     const size_t smem = static_cast<size_t>(npix) * P.ps + 8 * static_cast<size_t>((taps * P.ks * 32 + 16) | 16) + 2 * npix + 16;
-    static bool attr[3] = {false, false, false};
+    static bool attr[3][PCB_MAX_DEVICES] = {};
     if (c->kh == 3 && c->kw == 3 && P.ks == 5) return launch(smallco_fwd_kernel<5>, attr[0], P, smem, 3, st);
     if (c->kh == 3 && c->kw == 3 && P.ks == 3) return launch(smallco_fwd_kernel<3>, attr[1], P, smem, 3, st);
     return launch(smallco_fwd_kernel<0>, attr[2], P, smem, 3, st);
@@ -458,7 +460,7 @@ int pcb_smallco_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void
     const int kst = (c->kh * c->kw + 1) / 2;
     const size_t smem = static_cast<size_t>(TH + c->kh - 1) * (TW + c->kw - 1) * 16 + 16 + static_cast<size_t>(TH) * TW * P.cp * 2 +
                         static_cast<size_t>(P.cp) * ((kst * 32 + 16) | 16) + 2 * TH * TW + 16;
-    static bool attr[3] = {false, false, false};
+    static bool attr[3][PCB_MAX_DEVICES] = {};
     if (c->kh == 3 && c->kw == 3 && P.cp == 72) return launch(smallco_dgrad_kernel<9>, attr[0], P, smem, 2, st);
     if (c->kh == 3 && c->kw == 3 && P.cp == 40) return launch(smallco_dgrad_kernel<5>, attr[1], P, smem, 2, st);
     return launch(smallco_dgrad_kernel<0>, attr[2], P, smem, 2, st);
@@ -472,6 +474,6 @@ int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void
     P.dc = static_cast<const bf16 *>(dc); P.dc_cstride = dc_cstride; P.dw = dw;
     const int npix = (TH + c->kh - 1) * (TW + c->kw - 1);
     const size_t smem = static_cast<size_t>(npix) * P.ps + static_cast<size_t>(TH) * TW * 16 + 2 * npix + 16;
-    static bool attr = false;
+    static bool attr[PCB_MAX_DEVICES] = {};
     return launch(smallco_wgrad_kernel, attr, P, smem, 3, st);
 }

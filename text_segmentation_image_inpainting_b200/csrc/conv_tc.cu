@@ -1670,13 +1670,15 @@ int make_tmap_nhwc(CUtensorMap *tm, const void *base, int channels, int w, int h
     return 0;
 }
 
+// one abort flag per device (a flag allocated on the first-used device is an illegal address on every other one)
 int *abort_flag_ptr() {
-    static int *flag = nullptr;
-    if (!flag) {
-        if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(flag, 0, sizeof(int));
+    static int *flag[PCB_MAX_DEVICES] = {};
+    const int dev = pcb_cur_device();
+    if (!flag[dev]) {
+        if (cudaMalloc(&flag[dev], sizeof(int)) != cudaSuccess) { flag[dev] = nullptr; return nullptr; }
+        cudaMemset(flag[dev], 0, sizeof(int));
     }
-    return flag;
+    return flag[dev];
 }
 
 bool is_rowpack(const pcb_conv *c) { return c->nparts == 1 && c->cin <= 8 && c->kw <= 8 && c->parts[0].x_up == 0; }
@@ -1776,9 +1778,10 @@ int halo_hg(const pcb_conv *c, bool rowpack) {
 
 // PCB_TC_DEBUG_TIMING=1: every forward/dgrad launch synchronises and prints where its MMA threads spent their cycles
 long long *debug_buffer() {
-    static long long *buf = nullptr;
-    if (!buf && getenv("PCB_TC_DEBUG_TIMING")) cudaMalloc(&buf, sizeof(long long) * 10 * 1024);
-    return buf;
+    static long long *buf[PCB_MAX_DEVICES] = {};
+    const int dev = pcb_cur_device();
+    if (!buf[dev] && getenv("PCB_TC_DEBUG_TIMING")) cudaMalloc(&buf[dev], sizeof(long long) * 10 * 1024);
+    return buf[dev];
 }
 
 template <int BLOCK_N, int MODE, bool HALO>
@@ -1792,11 +1795,7 @@ int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     while (P.ring_a * a_stage + P.ring_b * b_stage > budget && P.ring_a > 2) --P.ring_a;
     const size_t smem = 1024 + P.ring_a * a_stage + P.ring_b * b_stage + 40 * MAX_RING + 64;
     auto kern = pconv_tc_persistent_kernel<BLOCK_N, MODE, HALO>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
-    }
+    PCB_SMEM_OPT_IN(kern, 220 * 1024);
     const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
     const int grid = std::min(num_tiles, pcb_num_sms());
     P.dbg = debug_buffer();
@@ -1817,16 +1816,18 @@ int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
 
 
 // ---- split-K: scratch buffer and finish kernels --------------------------------------------------
+// (opt-in debug path, PCB_SPLITK=1: one scratch buffer per device, single host thread / stream per device assumed)
 float *splitk_scratch(size_t bytes) {
-    static float *buf = nullptr;
-    static size_t cap = 0;
-    if (bytes > cap) {
-        if (buf) cudaFree(buf);
-        buf = nullptr; cap = 0;
+    static float *buf[PCB_MAX_DEVICES] = {};
+    static size_t cap[PCB_MAX_DEVICES] = {};
+    const int dev = pcb_cur_device();
+    if (bytes > cap[dev]) {
+        if (buf[dev]) cudaFree(buf[dev]);
+        buf[dev] = nullptr; cap[dev] = 0;
         const size_t want = std::max<size_t>(bytes, 16u << 20);
-        if (cudaMalloc(&buf, want) == cudaSuccess) cap = want;
+        if (cudaMalloc(&buf[dev], want) == cudaSuccess) cap[dev] = want;
     }
-    return buf;
+    return buf[dev];
 }
 
 // y = hole ? 0 : acc / s + b over [m_total][y_cstride] (8 channels per thread)
@@ -1948,11 +1949,7 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
     PCB_CHECK(P.stages >= 2, "TMA-fed conv: stage of %zu bytes does not fit twice", stage);
     const size_t smem = 1024 + P.stages * stage + 32 * MAX_RING + 64;
     auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE, HALO, PAIR>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_done = true;
-    }
+    PCB_SMEM_OPT_IN(kern, 224 * 1024);
     if (P.ksplit < 1) P.ksplit = 1;
     const int m_tiles = (P.m_total + BLOCK_M - 1) / BLOCK_M;
     P.dbg = debug_buffer();
@@ -2259,15 +2256,22 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
         // inside a stream capture: the internal streams join the capture and leave it again).
         const long long class_tiles = ((m_class + BLOCK_M - 1) / BLOCK_M) * (L.ktap / bn);
         const bool fork = class_tiles < pcb_num_sms() && !getenv("PCB_DISABLE_CLASS_STREAMS");
-        static cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-        static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-        if (fork && aux[0] == nullptr) {
+        // internal streams / events: one set per device AND per host thread (two host threads driving dgrads on two streams
+        // must not share the fork / join events)
+        struct ClassStreams { cudaStream_t aux[3]; cudaEvent_t ev_fork, ev_join[3]; bool ready; };
+        static thread_local ClassStreams cs_all[PCB_MAX_DEVICES] = {};
+        ClassStreams &CS = cs_all[pcb_cur_device()];
+        cudaStream_t *aux = CS.aux;
+        cudaEvent_t *ev_join = CS.ev_join;
+        if (fork && !CS.ready) {
             for (int i = 0; i < 3; ++i) {
                 PCB_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
                 PCB_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
             }
-            PCB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            PCB_CUDA(cudaEventCreateWithFlags(&CS.ev_fork, cudaEventDisableTiming));
+            CS.ready = true;
         }
+        cudaEvent_t ev_fork = CS.ev_fork;
         if (fork) PCB_CUDA(cudaEventRecord(ev_fork, st));
         for (int cls = 0; cls < 4; ++cls) {
             TcParams Q = P;
@@ -2330,11 +2334,7 @@ int launch_wgrad_tma(WgParams &P, const CUtensorMap &tdc, const CUtensorMap &ta0
     PCB_CHECK(P.stages >= 2, "TMA-fed wgrad: stage of %zu bytes does not fit twice", stage);
     const size_t smem = 1024 + P.stages * stage + 24 * MAX_RING + 64;
     auto kern = pconv_tc_wgrad_tma_kernel<BLOCK_N, T, HALO>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
-    }
+    PCB_SMEM_OPT_IN(kern, 220 * 1024);
     P.tap_groups = HALO ? P.kh : (P.kh * P.kw + T - 1) / T;
     P.ci_tiles = (P.ktap + 127) / 128;
     const int co_tiles = (P.cout + BLOCK_N - 1) / BLOCK_N;
@@ -2355,11 +2355,7 @@ template <int BLOCK_N, int T, int STAGES>
 static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream_t st) {
     constexpr size_t smem = 1024 + STAGES * (T * 16384 + BLOCK_N * 128) + 24 * STAGES + 16 + 16;
     auto kern = pconv_tc_wgrad_kernel<BLOCK_N, T, STAGES>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    PCB_SMEM_OPT_IN(kern, (int)smem);
     P.tap_groups = (P.ntaps + T - 1) / T;
     P.ci_tiles = (P.ktap + 127) / 128;
     const int co_tiles = (cout + BLOCK_N - 1) / BLOCK_N;

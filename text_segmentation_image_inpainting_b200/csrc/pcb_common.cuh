@@ -33,16 +33,39 @@ void pcb_count_launch(int n = 1);
         pcb_count_launch();                                                                      \
     } while (0)
 
-static inline int pcb_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
+// Per-device host state.  One process may drive several GPUs (a second device in the same process, or host threads each
+// bound to their own device): everything cached on the host side -- SM counts, the >48 KB dynamic shared-memory opt-in of
+// each kernel instantiation, abort flags, scratch buffers, internal streams -- is keyed by the CURRENT device.
+constexpr int PCB_MAX_DEVICES = 64;
+
+static inline int pcb_cur_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < PCB_MAX_DEVICES) ? dev : 0;
 }
+
+static inline int pcb_num_sms() {
+    static int sms[PCB_MAX_DEVICES] = {0};
+    const int dev = pcb_cur_device();
+    if (!sms[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
+    }
+    return sms[dev];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): function attributes live in the
+// device's context, so a flag per process would leave every device but the first without the opt-in.
+#define PCB_SMEM_OPT_IN(kern, bytes)                                                                          \
+    do {                                                                                                      \
+        static bool pcb_done_[PCB_MAX_DEVICES] = {};                                                          \
+        const int pcb_dev_ = pcb_cur_device();                                                                \
+        if (!pcb_done_[pcb_dev_]) {                                                                           \
+            PCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            pcb_done_[pcb_dev_] = true;                                                                       \
+        }                                                                                                     \
+    } while (0)
 
 static inline size_t pcb_dtype_size(int dtype) { return dtype == PCB_BF16 ? 2 : 4; }
 

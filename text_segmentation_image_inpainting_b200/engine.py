@@ -76,6 +76,21 @@ class TrainStep:
         self.bucket_elems = bucket_mb * (1 << 20) // 4
         self.launches_per_step = 0
         self.graph_update = None
+        self._captured_operands = None
+        if self.pg is not None:
+            self._sync_replicas()
+
+    def _sync_replicas(self):
+        """Data parallel start-up: every rank adopts rank 0's parameters and module buffers (BatchNorm running statistics,
+        `num_batches_tracked`), like torch DDP does, so replicas built from different seeds or checkpoints cannot silently
+        diverge.  BatchNorm batch statistics stay rank-local afterwards (the reference has no SyncBN); running statistics
+        therefore drift per rank during training and rank 0's are the ones to checkpoint."""
+        dist = torch.distributed
+        dist.broadcast(self.flat.flat_p, src=dist.get_global_rank(self.pg, 0), group=self.pg)
+        for b in self.net.buffers():
+            if b.is_floating_point() or b.dtype in (torch.int64, torch.int32):
+                dist.broadcast(b, src=dist.get_global_rank(self.pg, 0), group=self.pg)
+        ops.bump_weight_epoch()
 
     # -- one eager step ----------------------------------------------------------------------------
     def _prepare(self, x: torch.Tensor, mask: torch.Tensor):
@@ -160,6 +175,11 @@ class TrainStep:
             with torch.cuda.graph(self.graph_update):
                 self._update(False)
         self.graph = graph
+        # The captured kernels hold raw pointers to the per-layer operand buffers (the `_wcache` entries): keep them alive for as
+        # long as the graph exists.  An eager forward after capture (validation) misses the cache -- the optimiser bumps the
+        # weight epoch -- and, with the in-place refresh off, replaces `cache["val"]` with new buffers; without this list the
+        # old ones would be freed under the graph.  (Each replay refreshes the captured buffers itself.)
+        self._captured_operands = [c.get("val") for c in self._wcaches]
         torch.cuda.synchronize()
 
     def step(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:

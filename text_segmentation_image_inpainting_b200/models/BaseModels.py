@@ -11,6 +11,12 @@ import torch
 from torch import nn
 
 
+def _weights_changed():
+    """`.data` mutations do not bump tensor version counters: invalidate the cached compute-dtype weight operands."""
+    from .. import ops
+    ops.bump_weight_epoch()
+
+
 class BaseModule(nn.Module):
     def __init__(self):
         self.act_fn = None
@@ -28,6 +34,7 @@ class BaseModule(nn.Module):
         for m in self._trainable(nn.BatchNorm2d):
             m.weight.data.fill_(1)
             m.bias.data.zero_()
+        _weights_changed()
 
     def initialize_weights(self):
         for m in self._trainable(nn.Conv2d):
@@ -37,6 +44,7 @@ class BaseModule(nn.Module):
         for m in self._trainable(nn.BatchNorm2d):
             m.weight.data.fill_(1)
             m.bias.data.zero_()
+        _weights_changed()
 
     # -- checkpoints ------------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, self_state=False):
@@ -52,6 +60,7 @@ class BaseModule(nn.Module):
                 print("Parameter {} fails to load.".format(name))
                 print("-----------------------------------------")
                 print(exc)
+        _weights_changed()
 
     @contextmanager
     def set_activation_inplace(self):

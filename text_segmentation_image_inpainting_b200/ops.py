@@ -80,7 +80,21 @@ def as_feature_padded(x: torch.Tensor) -> torch.Tensor:
     if x.dim() != 4:
         raise _lib.PcbError(f"expected a 4-D NCHW activation, got shape {tuple(x.shape)}")
     _dtype_code(x)
-    return x if nhwc_layout(x) is not None else x.contiguous(memory_format=CL)
+    # Kernel family and weight layout are chosen from the problem geometry alone (ConvGeom.signature); the families test
+    # 16/32-byte alignment of the source pointers, so a channel-sliced view with a misaligned first element is copied to an
+    # aligned buffer here instead of silently changing family after the weights were laid out.
+    if nhwc_layout(x) is None:
+        return x.contiguous(memory_format=CL)
+    if x.data_ptr() % 32:
+        return _aligned_copy(x)
+    return x
+
+
+def _aligned_copy(x: torch.Tensor) -> torch.Tensor:
+    """Copy of an NHWC (possibly channel-padded) view into a fresh, allocator-aligned buffer with the same logical shape."""
+    buf = padded_empty(*x.shape, x.dtype, x.device)
+    buf.copy_(x)
+    return buf
 
 
 def padded_empty(n, c, h, w, dtype, device):
@@ -154,7 +168,8 @@ class ConvGeom:
                     self.parts.append((xi, a - lo, b_ - a, plane, mup))
         if len(self.parts) > _lib.MAX_PARTS:
             raise NotImplementedError(f"more than {_lib.MAX_PARTS} (source, mask-plane) parts in one convolution")
-        self.signature = (self.dtype, cin, cout, kh, kw, groups, tuple(p[2] for p in self.parts), tuple(self.x_cstrides))
+        self.signature = (self.dtype, cin, cout, kh, kw, groups, tuple(p[2] for p in self.parts), tuple(self.x_cstrides),
+                          tuple(self.x_ups), s, d)
 
     def struct(self, xs: Optional[Sequence[torch.Tensor]], force_generic=False) -> Conv:
         c = Conv()
