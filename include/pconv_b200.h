@@ -202,6 +202,10 @@ int pcb_l1_mean_backward(const void *x, int dtype, long long numel, float gscale
 /* fused SGD + momentum + Nesterov + weight decay over one flat fp32 tensor (checkpoints/ReadME.md:4 recipe). */
 int pcb_sgd_step(float *param, const float *grad, float *momentum_buf, long long numel, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, pcb_stream_t stream);
+/* same, with the gradient multiplied by `grad_scale` first: data-parallel training all-reduces the SUM of the per-rank gradient
+   arenas and folds the 1/world of the mean in here instead of a separate pass over the arena. */
+int pcb_sgd_step_scaled(float *param, const float *grad, float *momentum_buf, long long numel, float lr, float momentum,
+                        float weight_decay, int nesterov, int first_step, float grad_scale, pcb_stream_t stream);
 
 #ifdef __cplusplus
 }

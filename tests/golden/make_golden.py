@@ -135,7 +135,7 @@ def sub(t, step=8):
     return t[..., ::step, ::step].contiguous()
 
 
-def gen_network(cls_name, n, hw, grad_keys, step=8):
+def gen_network(cls_name, n, hw, grad_keys, step=8, tag=""):
     """End-to-end U-Net: det-filled weights (regenerable from names), seeded blob/line masks,
     train-mode fwd + bwd of loss = out.abs().mean()."""
     net = getattr(rii, cls_name)()
@@ -149,7 +149,7 @@ def gen_network(cls_name, n, hw, grad_keys, step=8):
     params = dict(net.named_parameters())
     sd = net.state_dict()
     bn_keys = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
-    save("net_" + cls_name,
+    save("net_" + cls_name + tag,
          mask_bits=np.packbits(mask[:, 0].numpy().astype(np.uint8)), n=n, hw=hw, step=step,
          out_sub=sub(out, step), out_sum=out.double().sum(), out_abs_sum=out.double().abs().sum(),
          loss=loss, out_row=out[0, :, hw // 2, :],
@@ -168,6 +168,11 @@ if __name__ == "__main__":
                  "decoder.6.0.1.bn_act.0.bias", "encoder.7.0.1.bn_act.0.weight"])
     gen_network("ImageFillOriginV2", 2, 256, ["decoder.7.0.feature_conv.weight"])
     gen_network("ImageFill", 2, 128, ["decoder.3.0.feature_conv.weight"])
+    # the BENCHMARKED resolution (BASELINE.json configs[2]: 512x512): selects the N = 256 tiles, row-halo tiles on every
+    # full-resolution decoder layer and the concurrent parity-class data gradients that 256x256 never reaches
+    gen_network("ImageFillOrigin", 2, 512,
+                ["encoder.0.0.feature_conv.weight", "decoder.7.0.feature_conv.weight", "decoder.6.0.0.feature_conv.weight",
+                 "decoder.6.0.1.bn_act.0.weight", "decoder.4.0.1.bn_act.0.bias", "encoder.2.0.1.bn_act.0.weight"], step=16, tag="_512")
 
 
 def gen_state_dict_keys():

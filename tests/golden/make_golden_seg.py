@@ -73,7 +73,7 @@ def gen_blocks():
     save("seg_pool_bilinear", xp=xp.detach(), yp=yp, gyp=gyp, gxp=xp.grad, xb=xb.detach(), **outs)
 
 
-def gen_network(cls_name, n, hw, grad_keys, step=4):
+def gen_network(cls_name, n, hw, grad_keys, step=4, tag=""):
     net = getattr(rts, cls_name)()
     net.load_state_dict(det_fill_state_dict(net.state_dict()))
     net.train()
@@ -84,7 +84,7 @@ def gen_network(cls_name, n, hw, grad_keys, step=4):
     params = dict(net.named_parameters())
     sd = net.state_dict()
     bn_keys = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
-    save("segnet_" + cls_name, n=n, hw=hw, step=step, out_sub=out[..., ::step, ::step].contiguous(), loss=loss,
+    save("segnet_" + cls_name + tag, n=n, hw=hw, step=step, out_sub=out[..., ::step, ::step].contiguous(), loss=loss,
          out_row=out[0, :, hw // 2, :], **{"g." + k: params[k].grad for k in grad_keys},
          **{"bn." + k: sd[k] for k in bn_keys[:4] + bn_keys[-2:]})
     keys = [[k, list(v.shape)] for k, v in sd.items()]
@@ -98,6 +98,13 @@ if __name__ == "__main__":
                                                                "encoder.features.0.0.weight", "smooth_feature_4x_conv.1.conv.2.weight"])
     keys["XceptionTextSegment"] = gen_network("XceptionTextSegment", 2, 64, ["out_conv.2.weight", "feature_pooling.out_conv.0.weight",
                                                                              "encoder.entry_flow_1.0.weight", "encoder.exit_flow.3.conv.2.depth_wise_conv.0.weight"])
+    # 256x256: the 1/8-resolution maps are 32x32, so RFB's dilation-17/29 branches and the d = 8/16 stages see real taps
+    # (at 64x64 input they only ever see padding)
+    gen_network("TextSegament", 2, 256, ["out_conv.0.weight", "feature_pooling.rfb_linear_conv.0.weight",
+                                         "encoder.features.0.0.weight", "smooth_feature_4x_conv.1.conv.2.weight"], step=8, tag="_256")
+    gen_network("XceptionTextSegment", 2, 256, ["out_conv.2.weight", "feature_pooling.out_conv.0.weight",
+                                                "encoder.entry_flow_1.0.weight", "encoder.exit_flow.3.conv.2.depth_wise_conv.0.weight"],
+                step=8, tag="_256")
     path = os.path.join(HERE, "state_dict_keys.json")
     allk = json.load(open(path))
     allk.update(keys)

@@ -286,10 +286,10 @@ def _lazycat_case(tag, dev, dtype=BF):
 
 # well-conditioned quantities only in bf16: the count-2/8 BatchNorm layers at the bottom of ImageFillOrigin make the
 # deep-layer gradients numerically ill-posed (x_hat = +-1), so bf16 compares outputs, loss and decoder-side grads.
-def run_net(cls_name, dev, dtype):
+def run_net(cls_name, dev, dtype, tag=""):
     from text_segmentation_image_inpainting_b200 import ops
     from text_segmentation_image_inpainting_b200.models import image_inpainting as PII
-    g = np.load(os.path.join(ROOT, "tests", "golden", f"net_{cls_name}.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"net_{cls_name}{tag}.npz"))
     n, hw, step = int(g["n"]), int(g["hw"]), int(g["step"])
     net = getattr(PII, cls_name)()
     net.load_state_dict(det_fill_state_dict(net.state_dict()))
@@ -374,10 +374,10 @@ def pool_bilinear_case(dev, dtype):
     return errs
 
 
-def run_segnet(cls_name, dev, dtype):
+def run_segnet(cls_name, dev, dtype, tag=""):
     from text_segmentation_image_inpainting_b200 import ops
     from text_segmentation_image_inpainting_b200.models import text_segmentation as MT
-    g = np.load(os.path.join(ROOT, "tests", "golden", f"segnet_{cls_name}.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"segnet_{cls_name}{tag}.npz"))
     n, hw, step = int(g["n"]), int(g["hw"]), int(g["step"])
     net = getattr(MT, cls_name)()
     net.load_state_dict(det_fill_state_dict(net.state_dict()))

@@ -47,14 +47,20 @@ def _free_port():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(0)
+    torch.manual_seed(rank)                                        # replicas built from DIFFERENT seeds ...
     net = Tiny()
+    net.bn.running_mean.fill_(float(rank + 1))
     ts = TrainStep(net, process_group=dist.group.WORLD, use_graph=False, bucket_mb=1)
+    # ... must adopt rank 0's parameters and buffers at start-up (TrainStep._sync_replicas)
+    gathered = [torch.empty_like(ts.flat.flat_p) for _ in range(world)]
+    dist.all_gather(gathered, ts.flat.flat_p)
+    same = all(torch.equal(gathered[0], g) for g in gathered) and float(net.bn.running_mean[0]) == 1.0
     ts.bucket_elems = 64                                           # force several buckets
     ts.flat.flat_g.copy_(torch.arange(ts.flat.numel, dtype=torch.float32) * (rank + 1))
     ts._allreduce()
+    # ranks exchange the SUM; the 1/world of the mean is folded into the optimiser kernel (TrainStep.grad_scale)
     expect = torch.arange(ts.flat.numel, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
-    out[rank] = bool(torch.allclose(ts.flat.flat_g, expect))
+    out[rank] = bool(torch.allclose(ts.flat.flat_g * ts.grad_scale, expect)) and ts.grad_scale == 1.0 / world and same
     dist.destroy_process_group()
 
 
@@ -64,3 +70,27 @@ def test_gradient_allreduce_averages_over_ranks_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_gradient_buckets_partition_the_arena_at_parameter_boundaries():
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Conv2d(8, 8, 3) for _ in range(6)])
+    for m in net:
+        m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+    ts = TrainStep(net, use_graph=False)
+    ts.bucket_elems = 1000
+    ts._make_buckets()
+    assert ts.buckets[0][0] == 0 and ts.buckets[-1][1] == ts.flat.numel
+    assert all(a[1] == b[0] for a, b in zip(ts.buckets, ts.buckets[1:]))
+    assert sorted(i for _, _, mem in ts.buckets for i in mem) == list(range(len(ts.flat.params)))
+    assert all(s in ts.flat.offsets for s, _, _ in ts.buckets) and len(ts.buckets) > 1
+    # every parameter reports exactly once; a bucket is exchanged when its last member reports
+    launched = []
+    ts._comm_stream = None
+    ts._launch_bucket = lambda b: launched.append(b)
+    ts._hooks_installed = True
+    ts._arm_overlap(True)
+    for i in reversed(range(len(ts.flat.params))):
+        ts._param_ready(i)
+        ts._param_ready(i)
+    assert launched == list(reversed(range(len(ts.buckets))))

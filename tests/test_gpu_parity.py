@@ -54,21 +54,25 @@ def test_partial_conv_over_lazy_upsample_concat(tag, dev):
         assert res[k] <= res["tol"], (k, res)
 
 
-@pytest.mark.parametrize("cls_name", ["ImageFillOrigin", "ImageFillOriginV2", "ImageFill"])
-def test_network_fp32_matches_reference_golden(cls_name, dev):
+NET_GOLDENS = [("ImageFillOrigin", ""), ("ImageFillOriginV2", ""), ("ImageFill", ""), ("ImageFillOrigin", "_512")]     # "_512": the benchmarked resolution (BASELINE.json configs[2])
+SEG_GOLDENS = [("TextSegament", ""), ("XceptionTextSegment", ""), ("TextSegament", "_256"), ("XceptionTextSegment", "_256")]
+
+
+@pytest.mark.parametrize("cls_name,tag", NET_GOLDENS)
+def test_network_fp32_matches_reference_golden(cls_name, tag, dev):
     """exact mode end to end: forward within 1e-3 relative of the reference's CPU forward (north_star bar);
     gradients within 2e-3 (fp32 re-association noise amplified by the tiny-batch BatchNorms at the bottom)."""
-    errs = run_net(cls_name, dev, F32)
+    errs = run_net(cls_name, dev, F32, tag)
     assert errs["out"] <= 1e-3 and errs["out_row"] <= 1e-3 and errs["loss"] <= 1e-5, errs
     assert max(errs.values()) <= 2e-3, errs
 
 
-@pytest.mark.parametrize("cls_name", ["ImageFillOrigin", "ImageFillOriginV2", "ImageFill"])
-def test_network_bf16_tensor_core_mode(cls_name, dev):
+@pytest.mark.parametrize("cls_name,tag", NET_GOLDENS)
+def test_network_bf16_tensor_core_mode(cls_name, tag, dev):
     """bf16 storage + tcgen05: 16+ layers of bf16 rounding -> a few 1e-3 on the output and loss.  Gradients of the
     BatchNorm scales see LeakyReLU sign flips of pre-activations within one bf16 ulp of zero (a systematic, not a
     random, perturbation): a few percent of max|grad|; convolution weight grads stay at the 1e-3 level."""
-    errs = run_net(cls_name, dev, BF)
+    errs = run_net(cls_name, dev, BF, tag)
     assert _pipeline_clean()
     assert errs["out"] <= 2e-2 and errs["loss"] <= 2e-3, errs
     assert all(v <= 1e-2 for k, v in errs.items() if k.endswith("feature_conv.weight")), errs
@@ -228,19 +232,19 @@ def test_avgpool_and_bilinear_vs_reference_golden(dtype, dev):
     assert max(errs.values()) <= (1e-5 if dtype == F32 else 2e-2), errs
 
 
-@pytest.mark.parametrize("cls_name", ["TextSegament", "XceptionTextSegment"])
-def test_segmentation_network_fp32_matches_reference_golden(cls_name, dev):
+@pytest.mark.parametrize("cls_name,tag", SEG_GOLDENS)
+def test_segmentation_network_fp32_matches_reference_golden(cls_name, tag, dev):
     from gpu_cases import run_segnet
-    errs = run_segnet(cls_name, dev, F32)
+    errs = run_segnet(cls_name, dev, F32, tag)
     assert errs["out"] <= 1e-3 and errs["out_row"] <= 1e-3 and errs["loss"] <= 1e-4, errs      # north_star bar on the forward
     # gradients: fp32 re-association noise is amplified through ~70 BatchNorm'd layers of a randomly initialised net
     # (the late layers agree to 1e-6, the first conv to ~5e-3)
     assert max(errs.values()) <= 2e-2, errs
 
 
-@pytest.mark.parametrize("cls_name", ["TextSegament", "XceptionTextSegment"])
-def test_segmentation_network_bf16(cls_name, dev):
+@pytest.mark.parametrize("cls_name,tag", SEG_GOLDENS)
+def test_segmentation_network_bf16(cls_name, tag, dev):
     from gpu_cases import run_segnet
-    errs = run_segnet(cls_name, dev, BF)
+    errs = run_segnet(cls_name, dev, BF, tag)
     assert _pipeline_clean()
     assert errs["out"] <= 0.15 and errs["loss"] <= 2e-2, errs          # relative L2 of the logit map after ~70 bf16 layers

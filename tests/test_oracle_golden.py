@@ -129,9 +129,10 @@ def _net_state_dict(cls_name):
     return det_fill_state_dict(net.state_dict())
 
 
-@pytest.mark.parametrize("cls_name", ["ImageFillOrigin", "ImageFillOriginV2", "ImageFill"])
-def test_network_forward_backward(cls_name):
-    g = _load("net_" + cls_name)
+@pytest.mark.parametrize("cls_name,tag", [("ImageFillOrigin", ""), ("ImageFillOriginV2", ""), ("ImageFill", ""),
+                                          ("ImageFillOrigin", "_512")])      # _512: the benchmarked resolution
+def test_network_forward_backward(cls_name, tag):
+    g = _load("net_" + cls_name + tag)
     n, hw, step = int(g["n"]), int(g["hw"]), int(g["step"])
     sd = O.clone_state_dict(_net_state_dict(cls_name), requires_grad=True)
     plane = np.unpackbits(g["mask_bits"])[: n * hw * hw].reshape(n, 1, hw, hw).astype(np.float32)

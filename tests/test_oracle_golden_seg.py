@@ -66,9 +66,10 @@ def test_rfb_and_asp():
     _check("asp", _sd(MC.ASP(24, 16, act, asp_rate=(3, 5, 9))), lambda sd, x: O.asp(sd, "", x, ACT, (3, 5, 9)))
 
 
-@pytest.mark.parametrize("cls_name", ["TextSegament", "XceptionTextSegment"])
-def test_segmentation_network_forward_backward(cls_name, capsys):
-    g = _load("segnet_" + cls_name)
+@pytest.mark.parametrize("cls_name,tag", [("TextSegament", ""), ("XceptionTextSegment", ""),
+                                          ("TextSegament", "_256"), ("XceptionTextSegment", "_256")])
+def test_segmentation_network_forward_backward(cls_name, tag, capsys):
+    g = _load("segnet_" + cls_name + tag)
     n, hw, step = int(g["n"]), int(g["hw"]), int(g["step"])
     sd = _sd(getattr(MT, cls_name)())
     x = det_tensor(cls_name + ".x", (n, 3, hw, hw))

@@ -523,9 +523,9 @@ __global__ void l1_bwd_kernel(const T *__restrict__ x, long long numel, float gs
 }
 
 __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, long long numel, float lr, float mom,
-                           float wd, int nesterov, int first) {
+                           float wd, int nesterov, int first, float gscale) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float d = g[i] + wd * p[i];
+        float d = g[i] * gscale + wd * p[i];
         if (mom != 0.f) {
             const float b = first ? d : mom * buf[i] + d;
             buf[i] = b;
@@ -791,10 +791,15 @@ extern "C" __attribute__((visibility("default"))) int pcb_l1_mean_backward(const
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int pcb_sgd_step(float *param, const float *grad, float *momentum_buf, long long numel, float lr, float momentum,
-                            float weight_decay, int nesterov, int first_step, pcb_stream_t stream) {
+extern "C" __attribute__((visibility("default"))) int pcb_sgd_step_scaled(float *param, const float *grad, float *momentum_buf, long long numel, float lr, float momentum,
+                            float weight_decay, int nesterov, int first_step, float grad_scale, pcb_stream_t stream) {
     PCB_CHECK(param && grad && numel > 0 && (momentum == 0.f || momentum_buf), "pcb_sgd_step: bad arguments");
-    sgd_kernel<<<ew_grid(numel, EW_THREADS * 8), EW_THREADS, 0, ST>>>(param, grad, momentum_buf, numel, lr, momentum, weight_decay, nesterov, first_step);
+    sgd_kernel<<<ew_grid(numel, EW_THREADS * 8), EW_THREADS, 0, ST>>>(param, grad, momentum_buf, numel, lr, momentum, weight_decay, nesterov, first_step, grad_scale);
     PCB_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcb_sgd_step(float *param, const float *grad, float *momentum_buf, long long numel, float lr, float momentum,
+                            float weight_decay, int nesterov, int first_step, pcb_stream_t stream) {
+    return pcb_sgd_step_scaled(param, grad, momentum_buf, numel, lr, momentum, weight_decay, nesterov, first_step, 1.0f, stream);
 }

@@ -7,6 +7,7 @@ the unit BASELINE.json's images/sec is quoted on.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -51,17 +52,22 @@ class FlatParams:
                 p.data = v
                 p.grad = _flat_view(self.flat_g, o, p.data)
         self.true_numel = total
-        # convolution weights: the weight-gradient kernels write straight into the arena (ops.GradSink)
+        # Gradient sinks (ops.GradSink): the weight-gradient kernels (4-D convolution weights) and the BatchNorm backward
+        # (1-D scale / shift) write straight into the arena -- no gradient tensor, no autograd accumulation kernel.
         self.sinks = []
-        for p in self.params:
-            if p.dim() == 4 and p.grad.is_contiguous(memory_format=CL) and (p.grad.data_ptr() % 16) == 0:
+        self.sink_of = {}
+        for i, p in enumerate(self.params):
+            ok4 = p.dim() == 4 and p.grad.is_contiguous(memory_format=CL) and (p.grad.data_ptr() % 16) == 0
+            ok1 = p.dim() == 1
+            if ok4 or ok1:
                 p._pcb_grad_sink = ops.GradSink(p.grad)
                 self.sinks.append(p._pcb_grad_sink)
+                self.sink_of[i] = p._pcb_grad_sink
 
 
 class TrainStep:
     def __init__(self, net: torch.nn.Module, compute_dtype=torch.bfloat16, lr=2e-4, momentum=0.9, weight_decay=1e-4,
-                 nesterov=True, process_group=None, use_graph=True, bucket_mb=32):
+                 nesterov=True, process_group=None, use_graph=True, bucket_mb=32, overlap_allreduce=None):
         self.net = net.train()
         self.dtype = compute_dtype
         self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
@@ -69,6 +75,9 @@ class TrainStep:
         self._wcaches = [m._wcache for m in net.modules() if isinstance(getattr(m, "_wcache", None), dict)]
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        # data parallel: ranks exchange the SUM of their gradient arenas; the 1/world of the mean is folded into the optimiser
+        # kernel (no scaling pass over the 131 MB arena)
+        self.grad_scale = 1.0 / self.world
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_x = self.static_m = self.static_loss = None
@@ -77,6 +86,14 @@ class TrainStep:
         self.launches_per_step = 0
         self.graph_update = None
         self._captured_operands = None
+        is_cuda = self.flat.flat_p.is_cuda
+        if overlap_allreduce is None:
+            overlap_allreduce = os.environ.get("PCB_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap_allreduce) and self.world > 1 and is_cuda
+        self.overlap_active = False
+        self._comm_stream = torch.cuda.Stream(device=self.flat.flat_p.device) if (self.world > 1 and is_cuda) else None
+        self._hooks_installed = False
+        self._make_buckets()
         if self.pg is not None:
             self._sync_replicas()
 
@@ -86,11 +103,89 @@ class TrainStep:
         diverge.  BatchNorm batch statistics stay rank-local afterwards (the reference has no SyncBN); running statistics
         therefore drift per rank during training and rank 0's are the ones to checkpoint."""
         dist = torch.distributed
-        dist.broadcast(self.flat.flat_p, src=dist.get_global_rank(self.pg, 0), group=self.pg)
+        src = dist.get_global_rank(self.pg, 0)
+        dist.broadcast(self.flat.flat_p, src=src, group=self.pg)
         for b in self.net.buffers():
-            if b.is_floating_point() or b.dtype in (torch.int64, torch.int32):
-                dist.broadcast(b, src=dist.get_global_rank(self.pg, 0), group=self.pg)
+            dist.broadcast(b, src=src, group=self.pg)
         ops.bump_weight_epoch()
+
+    # -- gradient exchange ---------------------------------------------------------------------------
+    def _make_buckets(self):
+        """Buckets of ~bucket_elems consecutive arena elements, cut at parameter boundaries.  Backward produces gradients
+        roughly from the END of the arena (decoder) to its start (encoder), so buckets complete tail first."""
+        fp = self.flat
+        self.buckets = []               # [start, end, [param indices]]
+        start, members = 0, []
+        for i, off in enumerate(fp.offsets):
+            end = fp.offsets[i + 1] if i + 1 < len(fp.offsets) else fp.numel
+            members.append(i)
+            if end - start >= self.bucket_elems or i + 1 == len(fp.offsets):
+                self.buckets.append([start, end, members])
+                start, members = end, []
+        self._bucket_of = {}
+        for b, (_, _, mem) in enumerate(self.buckets):
+            for i in mem:
+                self._bucket_of[i] = b
+
+    def _install_hooks(self):
+        if self._hooks_installed:
+            return
+        self._hooks_installed = True
+        for i, p in enumerate(self.flat.params):
+            sink = self.flat.sink_of.get(i)
+            if sink is not None:
+                sink.on_written = (lambda idx: (lambda: self._param_ready(idx)))(i)
+            # parameters whose gradient still arrives through autograd (or a sink that was refused and fell back to it)
+            p.register_post_accumulate_grad_hook((lambda idx: (lambda _p: self._param_ready(idx)))(i))
+
+    def _param_ready(self, idx):
+        if not self._overlap_armed:
+            return
+        b = self._bucket_of[idx]
+        if idx in self._pending[b]:
+            self._pending[b].discard(idx)
+            if not self._pending[b]:
+                self._launch_bucket(b)
+
+    def _launch_bucket(self, b):
+        """All-reduce (sum) of bucket b on the communication stream, ordered after everything issued so far on the compute
+        stream (BatchNorm / bias gradients, autograd accumulations) and on the weight-gradient side stream."""
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        s, e, _ = self.buckets[b]
+        comm = self._comm_stream
+        comm.wait_stream(torch.cuda.current_stream())
+        for st in ops.side_streams():
+            comm.wait_stream(st)
+        with torch.cuda.stream(comm):
+            torch.distributed.all_reduce(self.flat.flat_g[s:e], group=self.pg)
+
+    def _arm_overlap(self, on: bool):
+        self._overlap_armed = bool(on)
+        if on:
+            self._install_hooks()
+            self._pending = [set(mem) for _, _, mem in self.buckets]
+            self._launched = [False] * len(self.buckets)
+
+    _overlap_armed = False
+
+    def _finish_overlap(self):
+        """Buckets whose parameters did not all report (an unused parameter) are exchanged now; then the compute stream waits
+        for the communication stream."""
+        for b in range(len(self.buckets) - 1, -1, -1):
+            if not self._launched[b]:
+                self._launch_bucket(b)
+        self._overlap_armed = False
+        torch.cuda.current_stream().wait_stream(self._comm_stream)
+
+    def _allreduce(self):
+        """Un-overlapped exchange (fallback, and the CPU/gloo path): bucketed SUM all-reduce of the whole arena."""
+        if self.world == 1:
+            return
+        g = self.flat.flat_g
+        for s in range(0, g.numel(), self.bucket_elems):
+            torch.distributed.all_reduce(g[s:s + self.bucket_elems], group=self.pg)
 
     # -- one eager step ----------------------------------------------------------------------------
     def _prepare(self, x: torch.Tensor, mask: torch.Tensor):
@@ -101,18 +196,14 @@ class TrainStep:
         buf = torch.empty((n, (c + 7) // 8 * 8, h, w), dtype=self.dtype, device=x.device, memory_format=CL).zero_()
         xin = buf[:, :c]
         xin.copy_(x * mask.to(x.dtype))                                                # Dataloader.py:131
-        # masks of the reference's data path are one plane repeated over RGB (Dataloader.py:128-129)
+        # masks of the reference's data path are one plane repeated over RGB (Dataloader.py:128-129); outside a graph capture
+        # that promise is checked (one device sync), inside a capture it was checked by the eager warm-up steps
+        if not torch.cuda.is_current_stream_capturing() and mask.shape[1] > 1:
+            if not bool((mask == mask[:, :1]).all()):
+                raise ValueError("TrainStep expects a channel-uniform hole mask (one plane repeated over the input channels)")
         return xin, HoleMask.from_dense(mask, channel_uniform=True)
 
-    def _allreduce(self):
-        if self.world == 1:
-            return
-        g = self.flat.flat_g
-        g.mul_(1.0 / self.world)
-        for s in range(0, g.numel(), self.bucket_elems):
-            torch.distributed.all_reduce(g[s:s + self.bucket_elems], group=self.pg)
-
-    def _fwd_bwd(self, x, mask):
+    def _fwd_bwd(self, x, mask, overlap=False):
         self.flat.flat_g.zero_()
         for sk in self.flat.sinks:
             sk.used = False
@@ -121,6 +212,7 @@ class TrainStep:
         # operand buffers refreshed in place, mask passes running ahead on their own stream
         ops.set_inplace_weight_refresh(True)
         ops.set_mask_chain_stream(True)
+        self._arm_overlap(overlap)
         try:
             ops.prefetch_weights(self._wcaches)        # operand re-layout of all layers runs ahead on its own stream
             xin, hm = self._prepare(x, mask)
@@ -131,15 +223,19 @@ class TrainStep:
             ops.set_mask_chain_stream(False)
             ops.set_inplace_weight_refresh(False)
             ops.join_side_streams()
+            if overlap:
+                self._finish_overlap()
         return loss.detach()
 
     def _update(self, first_step: bool):
         ops.sgd_step(self.flat.flat_p, self.flat.flat_g, self.flat.flat_m, self.lr, self.momentum, self.wd, self.nesterov,
-                     first_step)
+                     first_step, grad_scale=self.grad_scale)
 
-    def _step(self, x, mask, first_step: bool):
-        loss = self._fwd_bwd(x, mask)
-        self._allreduce()
+    def _step(self, x, mask, first_step: bool, overlap=None):
+        overlap = self.overlap if overlap is None else overlap
+        loss = self._fwd_bwd(x, mask, overlap=overlap)
+        if self.world > 1 and not overlap:
+            self._allreduce()
         self._update(first_step)
         return loss
 
@@ -152,6 +248,7 @@ class TrainStep:
             self.first = False
             self.launches_per_step = _lib.launch_count() - before
         torch.cuda.synchronize()
+        self.overlap_active = self.overlap
         if not self.use_graph:
             return
         self.static_x = x.clone()
@@ -162,13 +259,27 @@ class TrainStep:
             self._step(self.static_x, self.static_m, False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        if self.world == 1:
-            with torch.cuda.graph(graph):
-                self.static_loss = self._step(self.static_x, self.static_m, False)
-        else:
-            # data parallel: the NCCL all-reduce stays OUTSIDE the captured graphs (graph A = forward+backward,
-            # eager bucketed all-reduce of the gradient arena, graph B = fused SGD): no collective is ever captured
+        graph = None
+        if self.world == 1 or self.overlap:
+            # one graph for the whole step.  Data parallel: the bucketed NCCL all-reduces are captured with it, on the
+            # communication stream, each ordered after the kernels that complete its bucket -- they overlap the rest of backward
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.static_loss = self._step(self.static_x, self.static_m, False)
+            except Exception as exc:  # noqa: BLE001 -- a collective that cannot be captured: fall back to the split scheme
+                if self.world == 1:
+                    raise
+                print(f"[engine] capturing the overlapped all-reduce failed ({type(exc).__name__}: {exc}); "
+                      "falling back to graph(forward+backward) | eager all-reduce | graph(SGD)", flush=True)
+                graph = None
+                self.overlap = self.overlap_active = False
+                self._overlap_armed = False
+                torch.cuda.synchronize()
+        if graph is None:
+            # data parallel fallback: the NCCL all-reduce stays OUTSIDE the captured graphs (graph A = forward+backward,
+            # eager bucketed all-reduce of the gradient arena, graph B = fused SGD): no collective is captured
+            graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.static_loss = self._fwd_bwd(self.static_x, self.static_m)
             self.graph_update = torch.cuda.CUDAGraph()
@@ -190,7 +301,7 @@ class TrainStep:
             if mask.data_ptr() != self.static_m.data_ptr():
                 self.static_m.copy_(mask, non_blocking=True)
             self.graph.replay()
-            if self.world > 1:
+            if self.graph_update is not None:
                 self._allreduce()
                 self.graph_update.replay()
             return self.static_loss

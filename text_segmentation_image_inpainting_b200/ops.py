@@ -326,9 +326,13 @@ class PartialConvFn(torch.autograd.Function):
                 if sink is not None:
                     deferred = True
                     _DEFERRED.append((dc, ws, xs))            # keep the side stream's operands alive until the join
+                    if sink.on_written is not None:
+                        sink.on_written()
             else:
                 with _Timed("wgrad", geom):
                     _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
+                if sink is not None and sink.on_written is not None:
+                    sink.on_written()
         gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
         if any(need):
             # full-resolution gradient buffer per source tensor; parts write their channel slices
@@ -486,6 +490,12 @@ class GradSink:
 
     def __init__(self, view: torch.Tensor):
         self.view, self.used = view, False
+        self.on_written = None        # optional callback: the kernel that writes `view` has just been launched
+
+
+def side_streams():
+    """The weight-gradient side streams created so far (a training engine orders its gradient exchange after them)."""
+    return list(_SIDE_STREAMS.values())
 
 
 def join_side_streams():
@@ -745,12 +755,14 @@ def l1_mean(x):
     return L1MeanFn.apply(as_feature(x) if x.dim() == 4 else x)
 
 
-def sgd_step(param, grad, buf, lr, momentum=0.0, weight_decay=0.0, nesterov=False, first_step=False):
+def sgd_step(param, grad, buf, lr, momentum=0.0, weight_decay=0.0, nesterov=False, first_step=False, grad_scale=1.0):
+    """torch.optim.SGD semantics on flat buffers; `grad_scale` multiplies the gradient first (data parallel: 1 / world on the
+    all-reduced SUM, so no separate scaling pass)."""
     lib = _lib.load()
     if not (param.is_contiguous() or param.is_contiguous(memory_format=CL)) or param.stride() != grad.stride():
         raise _lib.PcbError("sgd_step: param and grad must be dense with identical strides")
-    _lib.check(lib.pcb_sgd_step(param.data_ptr(), grad.data_ptr(), _ptr(buf), param.numel(), float(lr), float(momentum),
-                                float(weight_decay), int(nesterov), int(first_step), _stream()))
+    _lib.check(lib.pcb_sgd_step_scaled(param.data_ptr(), grad.data_ptr(), _ptr(buf), param.numel(), float(lr), float(momentum),
+                                       float(weight_decay), int(nesterov), int(first_step), float(grad_scale), _stream()))
     bump_weight_epoch()
 
 
