@@ -100,6 +100,14 @@ int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, v
 int pcb_pconv_mask_pass(const pcb_conv *c, float *msum, uint8_t *newmask, void *workspace, pcb_stream_t stream);
 int pcb_pconv_forward_premasked(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
                       uint8_t *newmask, void *workspace, pcb_stream_t stream);
+/* Forward with the STATISTICS PASS of the BatchNorm that follows the convolution (partial_convolution.py:193-197,
+ * BaseModels.py:95-99) fused into the convolution epilogue: bn_sums[co] += sum over pixels of y[.., co], bn_sums[cout + co] +=
+ * sum of y^2 (of the values as stored, holes contribute their zeros).  bn_sums = [2][cout] doubles, ZERO on entry; only for
+ * problems with pcb_conv_fuses_bn_stats(c) == 1 (the tcgen05 kernels); bn_sums NULL = plain forward.
+ * mask_pass_done != 0: pcb_pconv_mask_pass already ran (see pcb_pconv_forward_premasked).                                    */
+int pcb_conv_fuses_bn_stats(const pcb_conv *c);
+int pcb_pconv_forward_bn(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                         uint8_t *newmask, void *workspace, int mask_pass_done, double *bn_sums, pcb_stream_t stream);
 
 /* Backward of the renormalisation (autograd of partial_convolution.py:71-72):
  *   dc = dy * [s>0] / s          (NHWC [n,ho,wo,dc_cstride]; channels [cout, dc_cstride) zeroed)
@@ -117,6 +125,9 @@ int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, c
 /* dw[co][r][s][ci] = sum_pixels dc[p][co] * (x*m)[p@tap][ci]   (fp32 KRSC, logical/unpadded, overwritten).
  * workspace: pcb_pconv_workspace(c) bytes (may be NULL when that is 0).                         */
 int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream);
+/* same, ACCUMULATING into dw (dw is not zeroed first): for a gradient buffer the caller already zeroed -- e.g. a flat gradient arena
+ * cleared once per step -- or for gradient accumulation over micro-batches. */
+int pcb_pconv_backward_weight_acc(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream);
 
 /* Debug aid: after a device synchronise, returns the (sticky) pipeline-timeout code set by a tensor-core
  * kernel whose mbarrier wait expired (0 = none) and clears it. */
@@ -133,6 +144,17 @@ int pcb_mask_plane_to_dense(const uint8_t *plane, int n, int h, int w, int up, f
 /* nn.BatchNorm2d + act as built by PartialActivatedBN (partial_convolution.py:193-201) and
  * Conv_block (BaseModels.py:95-99).  x/y NHWC [count, c].                                     */
 int pcb_bn_stats(const void *x, int dtype, long long count, int c, double *sum, double *sqsum, pcb_stream_t stream);
+/* accumulate-only statistics: sums = [2][c] doubles (sum | sum of squares) that the CALLER zeroed -- e.g. a slice of a per-step
+ * zero arena, so a training step issues one memset instead of one per BatchNorm.                                              */
+int pcb_bn_stats_acc(const void *x, int dtype, long long count, int c, double *sums, pcb_stream_t stream);
+/* Training-mode forward of nn.BatchNorm2d (+act, +residual) from COMPLETE sums in one launch: mean / biased var / invstd,
+ * running-statistics + num_batches_tracked update (unbiased var, momentum), y = act(x*scale+shift) [+ residual].
+ * The sums come from pcb_bn_stats_acc or from the producing convolution's epilogue (pcb_pconv_forward_bn).
+ * coef: [4][c] floats written for the backward: scale | shift | mean | invstd.  c % 8 == 0, c <= 2048.                      */
+int pcb_bn_forward_fused(const void *x, int dtype, long long count, int c, const double *sums, const float *gamma,
+                         const float *beta, float *running_mean, float *running_var, long long *num_batches_tracked,
+                         float momentum, float eps, int act, float slope, const void *residual, void *y, float *coef,
+                         pcb_stream_t stream);
 /* training: mean/var from (sum,sqsum); updates running stats (unbiased var, momentum) and
  * num_batches_tracked; writes scale = gamma*invstd, shift = beta - mean*scale, save_mean, save_invstd.
  * eval (training==0): scale/shift from the running stats; sum/sqsum ignored.                  */
@@ -150,6 +172,10 @@ int pcb_bn_act_forward(const void *x, int dtype, long long count, int c, const f
 int pcb_bn_act_backward_reduce(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
                                const float *shift, const float *mean, const float *invstd, int act, float slope,
                                double *sum_g, double *sum_gx, pcb_stream_t stream);
+/* same without the memset: sums = [2][c] doubles (sum gz | sum gz*xhat) zeroed by the caller; c % 8 == 0, c <= 2048 */
+int pcb_bn_act_backward_reduce_acc(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                   const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                   double *sums, pcb_stream_t stream);
 /* dx = scale * (gz - sum_g/count - xhat * sum_gx/count)  (training) or scale * gz (eval / no BN: scale NULL => gz).
  * dgamma = sum_gx, dbeta = sum_g (fp32, optional).                                             */
 int pcb_bn_act_backward_apply(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from gpu_cases import BF, CONV_CASES, F32, LAZYCAT_CASES, conv_case, lazycat_case, relerr, run_net
+from oracle import pconv_torch as O
 
 pytestmark = pytest.mark.gpu
 
@@ -101,6 +102,54 @@ def test_bn_act_and_running_stats(dev):
             assert int(bn.num_batches_tracked) == 1
             bn.eval(); ref.eval()
             assert relerr(ops.bn_act(xd.detach(), bn, act), act(ref(xq)) if act else ref(xq)) <= tol
+
+
+@pytest.mark.parametrize("shape", [(64, 128, 3, 1, 1, (2, 24, 20)), (64, 64, 3, 1, 1, (2, 8, 128)), (128, 256, 3, 2, 1, (2, 32, 32)),
+                                   (192, 320, 1, 1, 0, (1, 16, 16))])
+def test_bn_statistics_fused_into_conv_epilogue(shape, dev):
+    """PartialConv -> BatchNorm(train) -> LeakyReLU block: the per-channel sums accumulated in the tcgen05 epilogue
+    (pcb_pconv_forward_bn) against the separate statistics pass (ops.set_fused_bn_stats(False)) and against the oracle."""
+    from gpu_cases import blob
+    from oracle.detfill import det_fill_state_dict, det_tensor
+    from text_segmentation_image_inpainting_b200 import ops
+    from text_segmentation_image_inpainting_b200.models import partial_convolution as PC
+    cin, cout, k, s, p, (n, h, w) = shape
+    blk = PC.partial_convolution_block(cin, cout, k, s, p, 1, bias=False, BN=True, activation=torch.nn.LeakyReLU(0.2), same_holes=True)
+    sd = det_fill_state_dict(blk.state_dict())
+    x = det_tensor("fbn.x", (n, cin, h, w)).to(BF)
+    mask = blob(n, cin, h, w, 3)
+    gy = None
+    res = {}
+    for fused in (True, False):
+        ops.set_fused_bn_stats(fused)
+        try:
+            blk.load_state_dict(sd)
+            m = blk.to(dev).train()
+            xd = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            y, _ = m((xd, mask.to(dev)))
+            if gy is None:
+                gy = det_tensor("fbn.gy", tuple(y.shape)).to(BF)
+            y.backward(gy.to(dev))
+            torch.cuda.synchronize()
+            res[fused] = (y.detach().float().cpu(), xd.grad.float().cpu(), m[1].bn_act[0].running_mean.cpu().clone(),
+                          m[1].bn_act[0].running_var.cpu().clone(), m[1].bn_act[0].weight.grad.cpu().clone(), m[0].feature_conv.weight.grad.cpu().clone())
+        finally:
+            ops.set_fused_bn_stats(True)
+    assert _pipeline_clean()
+    for a, b in zip(res[True], res[False]):
+        assert relerr(a, b) <= 2e-2, relerr(a, b)
+    # the statistics themselves are sums of the same bf16-rounded values: only the summation order differs
+    assert relerr(res[True][2], res[False][2]) <= 1e-5 and relerr(res[True][3], res[False][3]) <= 1e-4
+    # oracle on the same bf16-rounded operands
+    wq = sd["0.feature_conv.weight"].to(BF).float()
+    xo, wo = x.float().clone().requires_grad_(True), wq.clone().requires_grad_(True)
+    yo, _ = O.partial_conv(xo, mask, wo, None, s, p, 1, 1, True)
+    bn = torch.nn.BatchNorm2d(cout)
+    bn.load_state_dict({kk[len("1.bn_act.0."):]: v for kk, v in sd.items() if kk.startswith("1.bn_act.0.")})
+    zo = torch.nn.functional.leaky_relu(bn(yo), 0.2)
+    (zo * gy.float()).sum().backward()
+    assert relerr(res[True][0], zo) <= 3e-2 and relerr(res[True][2], bn.running_mean) <= 1e-2 and relerr(res[True][3], bn.running_var) <= 1e-2
+    assert relerr(res[True][5], wo.grad) <= 3e-2
 
 
 def test_concat_upsample_and_masks(dev):

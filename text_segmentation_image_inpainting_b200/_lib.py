@@ -37,15 +37,23 @@ _SIGS = {
     "pcb_conv_weight_refresh": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_pconv_forward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_pconv_forward_premasked": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_conv_fuses_bn_stats": (c_int, [ctypes.POINTER(Conv)]),
+    "pcb_pconv_forward_bn": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pcb_pconv_mask_pass": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_pconv_renorm_backward": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pcb_pconv_backward_data": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p),
                                         ctypes.POINTER(ctypes.c_int32), c_void_p]),
     "pcb_pconv_backward_weight": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "pcb_pconv_backward_weight_acc": (c_int, [ctypes.POINTER(Conv), c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pcb_debug_pipeline_status": (c_int, [ctypes.POINTER(c_int)]),
     "pcb_mask_planes_from_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pcb_mask_plane_to_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pcb_bn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p]),
+    "pcb_bn_stats_acc": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
+    "pcb_bn_forward_fused": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcb_bn_act_backward_reduce_acc": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_int, c_float, c_void_p, c_void_p]),
     "pcb_bn_finalize": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_bn_act_forward": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),

@@ -81,13 +81,17 @@ PCB_API int pcb_conv_weight_refresh(const pcb_conv *c, const float *w_master_krs
     return weight_prepare(c, w_master_krsc, w_fwd, w_dgrad, false, stream);
 }
 
+// 1 when the forward kernel this problem dispatches to can accumulate the per-channel BatchNorm statistics of its output itself
+PCB_API int pcb_conv_fuses_bn_stats(const pcb_conv *c) { return (c && use_tc(c) && pcb_tc_fuses_bn_stats(c)) ? 1 : 0; }
+
 static int pconv_forward_impl(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
-                              uint8_t *newmask, void *workspace, bool mask_pass_done, pcb_stream_t stream) {
+                              uint8_t *newmask, void *workspace, bool mask_pass_done, double *bn_sums, pcb_stream_t stream) {
     if (int rc = validate(c, true)) return rc;
     PCB_CHECK(w_fwd && y && msum && newmask && y_cstride >= c->cout, "pcb_pconv_forward: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!mask_pass_done)
         if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
+    PCB_CHECK(bn_sums == nullptr || pcb_conv_fuses_bn_stats(c), "pcb_pconv_forward_bn: this problem's kernel does not fuse the BatchNorm statistics (ask pcb_conv_fuses_bn_stats first)");
     if (use_dw(c)) {
         PCB_CHECK(y_cstride % 8 == 0, "depthwise forward: y channel stride must be a multiple of 8");
         return pcb_dw_forward(c, w_fwd, bias, y, y_cstride, msum, st);
@@ -95,14 +99,22 @@ static int pconv_forward_impl(const pcb_conv *c, const void *w_fwd, const float 
     if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr, "pcb_pconv_forward: workspace required for the tensor-core path");
         PCB_CHECK((reinterpret_cast<uintptr_t>(w_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "w / y must be 16-byte aligned");
-        return pcb_tc_forward_ws(c, w_fwd, bias, y, y_cstride, msum, static_cast<uint64_t *>(workspace), mask_pass_done, st);
+        return pcb_tc_forward_ws(c, w_fwd, bias, y, y_cstride, msum, static_cast<uint64_t *>(workspace), mask_pass_done, bn_sums, st);
     }
     return pcb_generic_forward(c, w_fwd, bias, y, y_cstride, msum, st);
 }
 
 PCB_API int pcb_pconv_forward(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
                               uint8_t *newmask, void *workspace, pcb_stream_t stream) {
-    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, false, stream);
+    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, false, nullptr, stream);
+}
+
+// Forward with the statistics pass of the BatchNorm that follows (partial_convolution.py:193-197, BaseModels.py:95-99) fused into
+// the convolution epilogue: bn_sums[0..cout) += sum over pixels of y, bn_sums[cout..2cout) += sum of y^2 (of the values as stored).
+// `bn_sums` must be zero on entry and the problem must satisfy pcb_conv_fuses_bn_stats.  mask_pass_done: see pcb_pconv_forward_premasked.
+PCB_API int pcb_pconv_forward_bn(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
+                                 uint8_t *newmask, void *workspace, int mask_pass_done, double *bn_sums, pcb_stream_t stream) {
+    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, mask_pass_done != 0, bn_sums, stream);
 }
 
 // The forward in two calls, for callers that run the mask chain of a network ahead of the feature path on another stream:
@@ -122,7 +134,7 @@ PCB_API int pcb_pconv_mask_pass(const pcb_conv *c, float *msum, uint8_t *newmask
 
 PCB_API int pcb_pconv_forward_premasked(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
                                         uint8_t *newmask, void *workspace, pcb_stream_t stream) {
-    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, true, stream);
+    return pconv_forward_impl(c, w_fwd, bias, y, y_cstride, msum, newmask, workspace, true, nullptr, stream);
 }
 
 PCB_API int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_fwd, const void *w_dgrad,
@@ -143,19 +155,29 @@ PCB_API int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cs
     return pcb_generic_dgrad(c, dc, dc_cstride, w_fwd, dx, dx_cstride, st);
 }
 
-PCB_API int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream) {
+static int backward_weight_impl(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, pcb_stream_t stream) {
     if (int rc = validate(c, true)) return rc;
     PCB_CHECK(dc && dw && dc_cstride >= c->cout, "pcb_pconv_backward_weight: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (use_dw(c)) {
         PCB_CHECK(dc_cstride % 8 == 0, "depthwise wgrad: dc channel stride must be a multiple of 8");
-        return pcb_dw_wgrad(c, dc, dc_cstride, dw, st);
+        return pcb_dw_wgrad(c, dc, dc_cstride, dw, zero_dw, st);
     }
     if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr && (reinterpret_cast<uintptr_t>(dc) & 15) == 0, "pcb_pconv_backward_weight: workspace required / dc misaligned");
-        return pcb_tc_wgrad(c, dc, dc_cstride, dw, workspace, st);
+        return pcb_tc_wgrad(c, dc, dc_cstride, dw, workspace, zero_dw, st);
     }
-    return pcb_generic_wgrad(c, dc, dc_cstride, dw, st);
+    return pcb_generic_wgrad(c, dc, dc_cstride, dw, zero_dw, st);
+}
+
+PCB_API int pcb_pconv_backward_weight(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream) {
+    return backward_weight_impl(c, dc, dc_cstride, dw, workspace, true, stream);
+}
+
+// same, ACCUMULATING into dw (no memset): for callers whose gradient buffer is already zero -- a training engine that zeroes its
+// flat gradient arena once per step (one memset instead of one per layer), or genuine gradient accumulation
+PCB_API int pcb_pconv_backward_weight_acc(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, pcb_stream_t stream) {
+    return backward_weight_impl(c, dc, dc_cstride, dw, workspace, false, stream);
 }
 
 PCB_API int pcb_debug_pipeline_status(int *code) {

@@ -368,11 +368,11 @@ int pcb_generic_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const v
     return launch_dgrad<float>(G, dc, dc_cstride, w_krsc, O, st);
 }
 
-int pcb_generic_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, cudaStream_t st) {
+int pcb_generic_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st) {
     GParams G;
     fill(G, c);
     const size_t bytes = sizeof(float) * c->cout * c->kh * c->kw * (c->cin / c->groups);
-    PCB_CUDA(cudaMemsetAsync(dw, 0, bytes, st));
+    if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, bytes, st));
     if (c->dtype == PCB_BF16) return launch_wgrad<bf16>(G, dc, dc_cstride, dw, st);
     return launch_wgrad<float>(G, dc, dc_cstride, dw, st);
 }

@@ -466,9 +466,9 @@ int pcb_smallco_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void
     return launch(smallco_dgrad_kernel<0>, attr[2], P, smem, 2, st);
 }
 
-int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, float *dw, cudaStream_t st) {
+int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st) {
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= 8, "small-cout wgrad: dc channel stride must be a multiple of 8");
-    PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cout * c->kh * c->kw * c->cin, st));
+    if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cout * c->kh * c->kw * c->cin, st));
     ScParams P;
     fill(P, c, L, false);
     P.dc = static_cast<const bf16 *>(dc); P.dc_cstride = dc_cstride; P.dw = dw;

@@ -89,7 +89,32 @@ struct TcParams {
     // the epilogue.  ksplit = 1: `partial` is null and the epilogue runs in the kernel.
     int ksplit;
     float *partial;
+    // fused BatchNorm statistics (forward, MODE 0): per-channel sum / sum of squares of the bf16-ROUNDED outputs are accumulated
+    // into bn_sums[0][co] / bn_sums[1][co] (doubles, pre-zeroed by the caller, row pitch bn_c = cout) -- the separate statistics
+    // pass over y (nn.BatchNorm2d in training mode, partial_convolution.py:193-197) disappears.  null: off.
+    double *bn_sums;
+    int bn_c;
 };
+
+constexpr int STAT_FLOATS_PER_WARP = 2 * 256;              // [sum | sum of squares] x up to 256 tile columns
+constexpr int STAT_SMEM_BYTES = 4 * STAT_FLOATS_PER_WARP * 4 + 16;
+
+// 32 values per lane, 32 lanes: returns in lane l the sum over all lanes of v[l] (a transposing butterfly: 31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < (n >> 1)) {
+                const float send = upper ? v[i] : v[i + (n >> 1)];
+                const float keep = upper ? v[i + (n >> 1)] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    return v[0];
+}
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
 
@@ -97,7 +122,7 @@ __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) &
 // epilogue shared by the forward / dgrad kernels: TMEM -> registers -> renormalise / mask -> bf16 NHWC
 // -------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int MODE>
-__device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_base, int warp, int lane, int m0, int n0) {
+__device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_base, int warp, int lane, int m0, int n0, float *s_stat) {
                 ptx::tc_fence_after();
                 const int row = warp * 32 + lane;
                 const int m = m0 + row;
@@ -154,7 +179,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                             }
                         }
                     }
-                    if (nstore > 0) {
+                    const bool stats = (MODE == 0) && (s_stat != nullptr);
+                    if (nstore > 0 || stats) {
                         uint4 o[4];
                         __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(o);
     #pragma unroll
@@ -171,12 +197,43 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                             }
                             ob[j] = __floats2bfloat162_rn(a, b);
                         }
-                        uint4 *dst = reinterpret_cast<uint4 *>(orow);
+                        if (nstore > 0) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(orow);
     #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j * 8 < nstore) dst[j] = o[j];
+                            for (int j = 0; j < 4; ++j)
+                                if (j * 8 < nstore) dst[j] = o[j];
+                        }
+                        if (stats) {
+                            // per-channel sum and sum of squares of what was just stored (rows past the tensor contribute 0)
+                            float v[32], q[32];
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 f = __bfloat1622float2(ob[j]);
+                                v[2 * j] = rvalid ? f.x : 0.f; v[2 * j + 1] = rvalid ? f.y : 0.f;
+                                q[2 * j] = v[2 * j] * v[2 * j]; q[2 * j + 1] = v[2 * j + 1] * v[2 * j + 1];
+                            }
+                            const float cs = warp_transpose_sum(v, lane), cq = warp_transpose_sum(q, lane);
+                            s_stat[c0 + lane] += cs;                          // this warp's private accumulators: no atomics needed
+                            s_stat[256 + c0 + lane] += cq;
+                        }
                     }
                 }
+}
+
+// flush one warp's per-column statistics of the N tile starting at n0 into the global fp64 sums, and clear them
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_stats_flush(const TcParams &P, float *s_stat, int lane, int n0) {
+    __syncwarp();
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int co = n0 + c0 + lane;
+        if (co < P.bn_c) {
+            atomicAdd(P.bn_sums + co, static_cast<double>(s_stat[c0 + lane]));
+            atomicAdd(P.bn_sums + P.bn_c + co, static_cast<double>(s_stat[256 + c0 + lane]));
+        }
+        s_stat[c0 + lane] = 0.f; s_stat[256 + c0 + lane] = 0.f;
+    }
+    __syncwarp();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -582,16 +639,30 @@ pconv_tc_persistent_kernel(const __grid_constant__ TcParams P, const __grid_cons
     } else {
         // ================================ epilogue warps (6-9) ================================
         int tile_iter = 0;
+        // fused BatchNorm statistics: this warp's private per-column accumulators in shared memory, flushed to the global fp64
+        // sums whenever the CTA moves to another N tile, and at the end
+        float *s_stat = (MODE == 0 && P.bn_sums != nullptr && P.partial == nullptr)
+                            ? reinterpret_cast<float *>(smem_raw + (((s_tmem_ptr + 32u) & ~15u) - ptx::smem_u32(smem_raw))) + (warp & 3) * STAT_FLOATS_PER_WARP : nullptr;
+        int stat_n0 = -1;
+        if (s_stat) {
+            for (int i = lane; i < STAT_FLOATS_PER_WARP; i += 32) s_stat[i] = 0.f;
+            __syncwarp();
+        }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int acc = tile_iter & 1;
-            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 102)) break;
-            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0);
+            if (s_stat && n0 != stat_n0) {
+                if (stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
+                stat_n0 = n0;
+            }
+            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 102)) { stat_n0 = -1; break; }
+            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0, s_stat);
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
             ++tile_iter;
         }
+        if (s_stat && stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
     }
 
     ptx::tc_fence_before();
@@ -999,18 +1070,31 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     } else {
         // ================================ epilogue warps (6-9) ================================
         int tile_iter = 0;
+        // fused BatchNorm statistics (see pconv_tc_persistent_kernel)
+        float *s_stat = (MODE == 0 && P.bn_sums != nullptr && P.partial == nullptr)
+                            ? reinterpret_cast<float *>(smem_gen + (((s_tmem_ptr + 32u) & ~15u) - smem_base)) + (warp & 3) * STAT_FLOATS_PER_WARP : nullptr;
+        int stat_n0 = -1;
+        if (s_stat) {
+            for (int i = lane; i < STAT_FLOATS_PER_WARP; i += 32) s_stat[i] = 0.f;
+            __syncwarp();
+        }
         for (int tile = tile0; tile < num_tiles; tile += tstep) {
             const int mn = tile / KS;
             const int m0 = m0_of(mn / n_tiles), n0 = (mn % n_tiles) * BLOCK_N;
             if (!tile_active(n0)) continue;
             const int acc = tile_iter & 1;
-            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 123)) break;
-            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0);
+            if (s_stat && n0 != stat_n0) {
+                if (stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
+                stat_n0 = n0;
+            }
+            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 123)) { stat_n0 = -1; break; }
+            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0, s_stat);
             ptx::tc_fence_before();
             if (PAIR && rank == 1) ptx::mbar_arrive_cluster(ptx::mapa(bar_tmem_empty + 8 * acc, 0));   // the leader waits for both epilogues
             else ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
             ++tile_iter;
         }
+        if (s_stat && stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
     }
 
     ptx::tc_fence_before();
@@ -1793,7 +1877,7 @@ int launch_persistent(TcParams &P, const CUtensorMap &tm, cudaStream_t st) {
     P.ring_a = HALO ? 3 : 6;
     while (P.ring_a * a_stage + P.ring_b * b_stage > budget && P.ring_b > 3) --P.ring_b;
     while (P.ring_a * a_stage + P.ring_b * b_stage > budget && P.ring_a > 2) --P.ring_a;
-    const size_t smem = 1024 + P.ring_a * a_stage + P.ring_b * b_stage + 40 * MAX_RING + 64;
+    const size_t smem = 1024 + P.ring_a * a_stage + P.ring_b * b_stage + 40 * MAX_RING + 64 + STAT_SMEM_BYTES;
     auto kern = pconv_tc_persistent_kernel<BLOCK_N, MODE, HALO>;
     PCB_SMEM_OPT_IN(kern, 220 * 1024);
     const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
@@ -1947,7 +2031,7 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
     const size_t stage = a_room + static_cast<size_t>(nb) * (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;
     P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (208 * 1024) / stage));
     PCB_CHECK(P.stages >= 2, "TMA-fed conv: stage of %zu bytes does not fit twice", stage);
-    const size_t smem = 1024 + P.stages * stage + 32 * MAX_RING + 64;
+    const size_t smem = 1024 + P.stages * stage + 32 * MAX_RING + 64 + STAT_SMEM_BYTES;
     auto kern = pconv_tc_tma_kernel<BLOCK_N, MODE, HALO, PAIR>;
     PCB_SMEM_OPT_IN(kern, 224 * 1024);
     if (P.ksplit < 1) P.ksplit = 1;
@@ -2117,8 +2201,13 @@ int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t 
     return launch_tapmask(c, tapmask, st);
 }
 
+// true when pcb_tc_forward_ws accumulates the BatchNorm statistics of its output itself (tcgen05 kernels, no split-K)
+bool pcb_tc_fuses_bn_stats(const pcb_conv *c) {
+    return pcb_tc_eligible(c) && !smallco_ok(c) && !getenv("PCB_SPLITK") && !getenv("PCB_DISABLE_FUSED_BN_STATS");
+}
+
 int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
-                      uint64_t *tapmask, bool mask_pass_done, cudaStream_t st) {
+                      uint64_t *tapmask, bool mask_pass_done, double *bn_sums, cudaStream_t st) {
     int *flag = abort_flag_ptr();
     PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
@@ -2133,6 +2222,8 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     P.m_total = static_cast<int>(m_total);
     fill_parts(c, L, P.parts, tapmask, m_total);
     P.bias = bias; P.msum = msum; P.y = static_cast<bf16 *>(y); P.y_cstride = y_cstride; P.abort_flag = flag;
+    PCB_CHECK(bn_sums == nullptr || pcb_tc_fuses_bn_stats(c), "fused BatchNorm statistics requested from a kernel that does not produce them");
+    P.bn_sums = bn_sums; P.bn_c = c->cout;
     P.ncols = L.rows_f;
     CUtensorMap tm;
     if (tma_fwd_ok(c)) {
@@ -2372,18 +2463,18 @@ static int launch_wgrad(WgParams &P, const CUtensorMap &tm, int cout, cudaStream
     return 0;
 }
 
-int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, cudaStream_t st) {
+int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, cudaStream_t st) {
     int *flag = abort_flag_ptr();
     PCB_CHECK(flag != nullptr, "cudaMalloc(abort flag) failed");
     PCB_CHECK(workspace != nullptr, "pcb_tc_wgrad: workspace required");
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= c->cout, "tensor-core wgrad: dc channel stride must be a multiple of 8");
-    if (smallco_ok(c)) return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, st);
+    if (smallco_ok(c)) return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, zero_dw, st);
     uint64_t *tapmask = static_cast<uint64_t *>(workspace);
     if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     const size_t dw_bytes = sizeof(float) * c->cout * c->kh * c->kw * c->cin;
-    PCB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, st));
+    if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, st));
     const Layout L = layout_of(c);
     WgParams P;
     memset(&P, 0, sizeof(P));

@@ -234,11 +234,11 @@ int pcb_dw_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     return 0;
 }
 
-int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, cudaStream_t st) {
+int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st) {
     DwParams P;
     fill(P, c);
     const int taps = c->kh * c->kw;
-    PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cin * taps, st));
+    if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cin * taps, st));
     const long long total = static_cast<long long>(c->n) * c->ho * c->wo;
     const int rpb = 256 / (c->cin / 8);
     long long blocks = (total + rpb * 16 - 1) / (rpb * 16);

@@ -17,7 +17,7 @@ inline int ew_grid(long long work_items, int per_block) {
 // blocks would serialise thousands of atomics on the same c addresses
 inline int ew_grid_red(long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
-    const long long cap = 4ll * pcb_num_sms();
+    const long long cap = 8ll * pcb_num_sms();
     return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -150,6 +150,59 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const T *__restr
     }
 }
 
+// BatchNorm (training mode) finalisation + apply + activation in ONE launch: every thread derives the scale / shift of its
+// 8 channels from the complete fp64 sums (produced by the convolution epilogue or pcb_bn_stats_acc), block 0 additionally
+// updates the running statistics and writes the per-channel coefficients the backward needs.
+//   coef: [4][c] floats = scale (gamma * invstd) | shift (beta - mean * scale) | mean | invstd
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_fwd_fused_kernel(const T *__restrict__ x, long long count, int c, const double *__restrict__ sums,
+                                                                  const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                  float *running_mean, float *running_var, long long *nbt, float momentum, float eps,
+                                                                  int act, float slope, const T *__restrict__ residual, T *__restrict__ y,
+                                                                  float *__restrict__ coef) {
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    if (r >= rpb) return;
+    float sc[8], sh[8];
+    const double inv_n = 1.0 / static_cast<double>(count);
+    const bool writer = blockIdx.x == 0 && r == 0;
+    if (writer && v == 0 && nbt) *nbt += 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = v * 8 + j;
+        const double m = sums[ch] * inv_n;
+        double var = sums[c + ch] * inv_n - m * m;                    // biased (normalisation)
+        if (var < 0) var = 0;
+        const float mean = static_cast<float>(m);
+        const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);      // fp32 like torch's batch_norm kernels
+        const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+        sc[j] = g * invstd;
+        sh[j] = b - mean * g * invstd;
+        if (writer) {
+            coef[ch] = sc[j]; coef[c + ch] = sh[j]; coef[2 * c + ch] = mean; coef[3 * c + ch] = invstd;
+            if (running_mean) {
+                const double unbiased = count > 1 ? var * static_cast<double>(count) / static_cast<double>(count - 1) : var;
+                running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+                running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+            }
+        }
+    }
+    const long long step = static_cast<long long>(gridDim.x) * rpb;
+#pragma unroll 4
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
+        float f[8], rres[8];
+        Vec8<T>::load(x + row * c + v * 8, f);
+        if (residual) Vec8<T>::load(residual + row * c + v * 8, rres);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float z = apply_act(f[j] * sc[j] + sh[j], act, slope);
+            if (residual) z += rres[j];
+            f[j] = z;
+        }
+        Vec8<T>::store(y + row * c + v * 8, f);
+    }
+}
+
 template <typename T>
 __global__ void bn_act_fwd_scalar_kernel(const T *x, long long numel, int c, const float *scale, const float *shift, int act,
                                          float slope, const T *residual, T *y) {
@@ -202,20 +255,27 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__res
                                                                   const float *__restrict__ scale, const float *__restrict__ shift,
                                                                   const float *__restrict__ mean, const float *__restrict__ invstd, int act,
                                                                   float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
-                                                                  int training, const float *__restrict__ msum, T *__restrict__ dx) {
+                                                                  int training, const float *__restrict__ msum, T *__restrict__ dx,
+                                                                  float *__restrict__ dgamma, float *__restrict__ dbeta) {
     const int cv = c >> 3, rpb = EW_THREADS / cv;
     const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
     if (r >= rpb) return;
     const float inv_count = 1.0f / static_cast<float>(count);
     const bool full = scale && training;
+    const bool writer = full && blockIdx.x == 0 && r == 0;            // parameter gradients: dgamma = sum gz*xhat, dbeta = sum gz
     float sc[8], sh[8], mu[8], is[8], mg[8], mgx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int ch = v * 8 + j;
         sc[j] = scale ? scale[ch] : 1.f; sh[j] = scale ? shift[ch] : 0.f;
         mu[j] = full ? mean[ch] : 0.f; is[j] = full ? invstd[ch] : 0.f;
-        mg[j] = full ? static_cast<float>(sum_g[ch]) * inv_count : 0.f;
-        mgx[j] = full ? static_cast<float>(sum_gx[ch]) * inv_count : 0.f;
+        const float sg = full ? static_cast<float>(sum_g[ch]) : 0.f, sgx = full ? static_cast<float>(sum_gx[ch]) : 0.f;
+        mg[j] = sg * inv_count;
+        mgx[j] = sgx * inv_count;
+        if (writer) {
+            if (dgamma) dgamma[ch] = sgx;
+            if (dbeta) dbeta[ch] = sg;
+        }
     }
     const long long step = static_cast<long long>(gridDim.x) * rpb;
     const bool renorm = msum != nullptr;
@@ -562,6 +622,37 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_stats(const void *x
     return 0;
 }
 
+// statistics WITHOUT the memset: `sums` = [2][c] doubles that the caller zeroed (e.g. a slice of a per-step zero arena)
+extern "C" __attribute__((visibility("default"))) int pcb_bn_stats_acc(const void *x, int dtype, long long count, int c, double *sums, pcb_stream_t stream) {
+    PCB_CHECK(x && sums && count > 0 && c > 0, "pcb_bn_stats_acc: bad arguments");
+    if (c % 8 == 0 && c <= 2048) {
+        const int rpb = EW_THREADS / (c / 8);
+        const int grid = ew_grid_red(count, rpb * 8);
+        if (dtype == PCB_BF16) bn_stats_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sums, sums + c);
+        else bn_stats_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sums, sums + c);
+    } else {
+        if (dtype == PCB_BF16) bn_stats_scalar_kernel<bf16><<<min(c, 1024), 256, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sums, sums + c);
+        else bn_stats_scalar_kernel<float><<<min(c, 1024), 256, 0, ST>>>(static_cast<const float *>(x), count, c, sums, sums + c);
+    }
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+// training-mode BatchNorm forward from COMPLETE sums: finalise (mean / invstd / running statistics) + apply + activation
+// (+ residual) in one launch; `coef` receives [4][c] floats scale | shift | mean | invstd for the backward.
+extern "C" __attribute__((visibility("default"))) int pcb_bn_forward_fused(const void *x, int dtype, long long count, int c, const double *sums, const float *gamma,
+                                    const float *beta, float *running_mean, float *running_var, long long *num_batches_tracked,
+                                    float momentum, float eps, int act, float slope, const void *residual, void *y, float *coef,
+                                    pcb_stream_t stream) {
+    PCB_CHECK(x && y && sums && coef && count > 0 && c > 0 && c % 8 == 0 && c <= 2048, "pcb_bn_forward_fused: bad arguments (c must be a multiple of 8, <= 2048)");
+    PCB_CHECK((running_mean == nullptr) == (running_var == nullptr), "pcb_bn_forward_fused: running statistics come in pairs");
+    const int grid = ew_grid(count, (EW_THREADS / (c / 8)) * 4);
+    if (dtype == PCB_BF16) bn_fwd_fused_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y), coef);
+    else bn_fwd_fused_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const float *>(residual), static_cast<float *>(y), coef);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int pcb_bn_finalize(const double *sum, const double *sqsum, long long count, int c, const float *gamma, const float *beta,
                                float *running_mean, float *running_var, long long *num_batches_tracked, float momentum, float eps,
                                int training, float *scale, float *shift, float *save_mean, float *save_invstd, pcb_stream_t stream) {
@@ -613,6 +704,19 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
     return 0;
 }
 
+// backward reduction WITHOUT the memset: `sums` = [2][c] doubles zeroed by the caller (sum gz | sum gz * xhat)
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce_acc(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
+                                          const float *shift, const float *mean, const float *invstd, int act, float slope,
+                                          double *sums, pcb_stream_t stream) {
+    PCB_CHECK(gy && x && sums && count > 0 && c % 8 == 0 && c <= 2048, "pcb_bn_act_backward_reduce_acc: bad arguments (c must be a multiple of 8, <= 2048)");
+    const int rpb = EW_THREADS / (c / 8);
+    const int grid = ew_grid_red(count, rpb * 8);
+    if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
+    else bn_bwd_reduce_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
 static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
                                       const float *shift, const float *mean, const float *invstd, int act, float slope,
                                       const double *sum_g, const double *sum_gx, int training, const float *msum, void *dx, float *dgamma,
@@ -625,13 +729,17 @@ static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, 
     if (!vec) {
         if (dtype == PCB_BF16) bn_bwd_apply_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
         else bn_bwd_apply_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
-    } else if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx));
-    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx));
-    PCB_LAUNCH_CHECK();
-    if ((dgamma || dbeta) && sum_g && sum_gx) {
-        bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sum_g, sum_gx, c, dgamma, dbeta);
         PCB_LAUNCH_CHECK();
+        if ((dgamma || dbeta) && sum_g && sum_gx) {
+            bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, ST>>>(sum_g, sum_gx, c, dgamma, dbeta);
+            PCB_LAUNCH_CHECK();
+        }
+        return 0;
     }
+    // vector path: block 0 also writes the parameter gradients (dgamma = sum gz*xhat, dbeta = sum gz) -- no extra launch
+    if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
+    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx), dgamma, dbeta);
+    PCB_LAUNCH_CHECK();
     return 0;
 }
 

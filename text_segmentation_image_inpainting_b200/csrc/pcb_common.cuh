@@ -139,7 +139,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 int pcb_generic_forward(const pcb_conv *c, const void *w, const float *bias, void *y, int y_cstride, const float *msum, cudaStream_t st);
 int pcb_generic_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_krsc, void *const *dx, const int *dx_cstride,
                       cudaStream_t st);
-int pcb_generic_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, cudaStream_t st);
+int pcb_generic_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st);
 // mask box sums (all paths): msum fp32 [mg][n,ho,wo] (0 at holes), newmask u8 [mg][n,ho,wo]
 int pcb_mask_sums(const pcb_conv *c, float *msum, uint8_t *newmask, cudaStream_t st);
 bool pcb_tc_eligible(const pcb_conv *c);
@@ -149,10 +149,11 @@ void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_el
 int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st);
 int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t st);
 int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
-                      uint64_t *tapmask, bool mask_pass_done, cudaStream_t st);
+                      uint64_t *tapmask, bool mask_pass_done, double *bn_sums, cudaStream_t st);
+bool pcb_tc_fuses_bn_stats(const pcb_conv *c);
 int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
                  cudaStream_t st);
-int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, cudaStream_t st);
+int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, cudaStream_t st);
 int pcb_tc_read_abort_flag(int *value);
 // layers with <= 8 output channels (conv_smallco.cu); weights are read from the tensor-core operand layouts
 struct pcb_smallco_layout { int ktap, koff[2], cout64; long long kf, kd; };
@@ -161,10 +162,10 @@ int pcb_smallco_forward(const pcb_conv *c, const pcb_smallco_layout &L, const vo
                         cudaStream_t st);
 int pcb_smallco_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
                       cudaStream_t st);
-int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, float *dw, cudaStream_t st);
+int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st);
 // depthwise fast path (dwconv.cu)
 bool pcb_dw_eligible(const pcb_conv *c);
 int pcb_dw_weight_prepare(const pcb_conv *c, const float *w_master, void *w_t, cudaStream_t st);
 int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *y, int y_cstride, const float *msum, cudaStream_t st);
 int pcb_dw_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_t, void *dx, int dx_cstride, cudaStream_t st);
-int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, cudaStream_t st);
+int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st);

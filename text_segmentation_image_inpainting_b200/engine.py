@@ -61,6 +61,7 @@ class FlatParams:
             ok1 = p.dim() == 1
             if ok4 or ok1:
                 p._pcb_grad_sink = ops.GradSink(p.grad)
+                p._pcb_grad_sink.prezeroed = True        # TrainStep zeroes the whole gradient arena at the start of every step
                 self.sinks.append(p._pcb_grad_sink)
                 self.sink_of[i] = p._pcb_grad_sink
 
@@ -207,6 +208,7 @@ class TrainStep:
         self.flat.flat_g.zero_()
         for sk in self.flat.sinks:
             sk.used = False
+        ops.begin_step_arena(self.flat.flat_g.device)      # one zero fill for every reduction target of the step
         ops.bump_weight_epoch()
         # scheduling switches that are only safe inside a loop that joins once per step (scoped to this call):
         # operand buffers refreshed in place, mask passes running ahead on their own stream
@@ -222,6 +224,7 @@ class TrainStep:
         finally:
             ops.set_mask_chain_stream(False)
             ops.set_inplace_weight_refresh(False)
+            ops.end_step_arena(self.flat.flat_g.device)
             ops.join_side_streams()
             if overlap:
                 self._finish_overlap()

@@ -106,7 +106,8 @@ class PartialBlock(nn.Sequential):
 
     def forward(self, args):
         if len(self) == 2 and type(self[0]) is PartialConv and isinstance(self[1], PartialActivatedBN):
-            h = ops.RenormHandoff()
+            bn = self[1].bn_act[0]
+            h = ops.RenormHandoff(want_stats=bn.training and bn.weight is not None)
             return self[1](self[0](args, handoff=h), handoff=h)
         return super().forward(args)
 

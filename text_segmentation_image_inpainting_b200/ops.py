@@ -184,6 +184,46 @@ class ConvGeom:
         return c
 
 
+# ------------------------------------------------------------------------------------------------
+# per-step zero arena: reduction targets (BatchNorm sums) are slices of ONE buffer that the training engine zeroes once per
+# step, instead of one cudaMemsetAsync per reduction (the step had 106 of them)
+# ------------------------------------------------------------------------------------------------
+class _ZeroArena:
+    def __init__(self):
+        self.buf, self.off, self.active = None, 0, False
+
+
+_ARENAS = {}
+
+
+def begin_step_arena(device, nbytes=1 << 20):
+    """Zero the arena of `device` on the current stream and hand out slices of it until end_step_arena()."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    a = _ARENAS.setdefault(key, _ZeroArena())
+    if a.buf is None or a.buf.numel() < nbytes:
+        a.buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+    a.buf.zero_()
+    a.off, a.active = 0, True
+
+
+def end_step_arena(device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key in _ARENAS:
+        _ARENAS[key].active = False
+
+
+def zeros_f64(n, device):
+    """n zeroed doubles: a slice of the step arena when one is active (and has room), else a fresh zero tensor."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    a = _ARENAS.get(key)
+    nbytes = (n * 8 + 255) // 256 * 256
+    if a is not None and a.active and a.off + nbytes <= a.buf.numel():
+        view = a.buf[a.off:a.off + n * 8].view(torch.float64)
+        a.off += nbytes
+        return view
+    return torch.zeros((n,), dtype=torch.float64, device=device)
+
+
 _PROFILE = None     # optional list: (kind, geom, start_event, end_event) appended per conv kernel call
 
 
@@ -230,6 +270,12 @@ class PartialConvFn(torch.autograd.Function):
         else:
             y = torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=xs[0].dtype, device=dev, memory_format=CL)
         b32 = bias.detach().float().contiguous() if bias is not None else None
+        # BatchNorm statistics of y in the convolution epilogue when the consumer announced itself (RenormHandoff.want_stats)
+        bn_sums = None
+        if handoff is not None and handoff.want_stats and _FUSED_BN_STATS and lib.pcb_conv_fuses_bn_stats(ctypes.byref(c)) \
+                and nhwc_layout(y) == geom.cout:
+            bn_sums = zeros_f64(2 * geom.cout, dev)
+            handoff.bn_sums = bn_sums
         global _LAST_MASK_EVENT
         _LAST_MASK_EVENT = None
         if _MASK_CHAIN_STREAM and _PROFILE is None and not geom.plain:
@@ -256,15 +302,15 @@ class PartialConvFn(torch.autograd.Function):
             main.wait_event(ev)
             _DEFERRED.append((msum, newmask, ws))
             _LAST_MASK_EVENT = ev
-            _lib.check(lib.pcb_pconv_forward_premasked(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y),
-                                                       msum.data_ptr(), newmask.data_ptr(), ws.data_ptr(), _stream()))
+            _lib.check(lib.pcb_pconv_forward_bn(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y),
+                                                msum.data_ptr(), newmask.data_ptr(), ws.data_ptr(), 1, _ptr(bn_sums), _stream()))
         else:
             msum = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.float32, device=dev)
             newmask = torch.empty((geom.mg, geom.n, geom.ho, geom.wo), dtype=torch.uint8, device=dev)
             ws = _workspace(lib, c, dev)
             with _Timed("fwd", geom):
-                _lib.check(lib.pcb_pconv_forward(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
-                                                 newmask.data_ptr(), ws.data_ptr(), _stream()))
+                _lib.check(lib.pcb_pconv_forward_bn(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
+                                                    newmask.data_ptr(), ws.data_ptr(), 0, _ptr(bn_sums), _stream()))
         ctx.geom, ctx.wprep, ctx.has_bias, ctx.weight_ref = geom, wprep, bias is not None, weight
         ctx.handoff = handoff
         if handoff is not None:
@@ -307,10 +353,13 @@ class PartialConvFn(torch.autograd.Function):
             # the engine calls join_side_streams(), so the weight gradient also overlaps the element-wise backward kernels
             # of the layers that follow.  A second use of the same weight in one pass falls back to autograd accumulation.
             sink = getattr(ctx.weight_ref, "_pcb_grad_sink", None)
+            wgrad_fn = lib.pcb_pconv_backward_weight
             shape = (geom.cout, geom.cin // geom.groups, geom.kh, geom.kw)
             if sink is not None and not sink.used and tuple(sink.view.shape) == shape and sink.view.dtype == torch.float32 \
                     and sink.view.is_contiguous(memory_format=CL):
                 dw_buf, sink.used = sink.view, True
+                if sink.prezeroed:           # the owner zeroed the whole arena at the start of the step: accumulate, no memset
+                    wgrad_fn = lib.pcb_pconv_backward_weight_acc
             else:
                 sink = None
                 dw_buf = dw = torch.empty(shape, dtype=torch.float32, device=dev, memory_format=CL)
@@ -322,7 +371,7 @@ class PartialConvFn(torch.autograd.Function):
                 side = _side_stream(dev)
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
+                    _lib.check(wgrad_fn(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
                 if sink is not None:
                     deferred = True
                     _DEFERRED.append((dc, ws, xs))            # keep the side stream's operands alive until the join
@@ -330,7 +379,7 @@ class PartialConvFn(torch.autograd.Function):
                         sink.on_written()
             else:
                 with _Timed("wgrad", geom):
-                    _lib.check(lib.pcb_pconv_backward_weight(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
+                    _lib.check(wgrad_fn(ctypes.byref(c), dc.data_ptr(), dcs, dw_buf.data_ptr(), ws.data_ptr(), _stream()))
                 if sink is not None and sink.on_written is not None:
                     sink.on_written()
         gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
@@ -490,6 +539,7 @@ class GradSink:
 
     def __init__(self, view: torch.Tensor):
         self.view, self.used = view, False
+        self.prezeroed = False        # the owner guarantees `view` is zero when the backward pass starts (skip the kernel's memset)
         self.on_written = None        # optional callback: the kernel that writes `view` has just been launched
 
 
@@ -522,8 +572,19 @@ class RenormHandoff:
     models/partial_convolution.py): the BN backward then writes dc = dy / mask_sum directly (one pass less over every conv
     output) and the convolution's backward skips its renormalisation step.  Never use it when y has another consumer."""
 
-    def __init__(self):
+    def __init__(self, want_stats=False):
         self.msum, self.eligible, self.fused = None, False, False
+        # want_stats: the consumer is a training-mode BatchNorm -> the convolution accumulates the per-channel sum / sum of
+        # squares of its output in its epilogue (`bn_sums`, [2][cout] doubles) and the statistics pass over y disappears
+        self.want_stats, self.bn_sums = bool(want_stats), None
+
+
+_FUSED_BN_STATS = True
+
+
+def set_fused_bn_stats(enabled: bool):
+    global _FUSED_BN_STATS
+    _FUSED_BN_STATS = bool(enabled)
 
 
 def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_holes=False, no_guard=False, cache=None,
@@ -569,11 +630,21 @@ def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_
 # ------------------------------------------------------------------------------------------------
 # BatchNorm2d (+ activation, + residual)
 # ------------------------------------------------------------------------------------------------
+def _vec_bn(c):
+    return c % 8 == 0 and c <= 2048
+
+
 class BNActFn(torch.autograd.Function):
-    """y = act(BN(x)) [+ residual]; BN optional (gamma None => plain activation)."""
+    """y = act(BN(x)) [+ residual]; BN optional (gamma None => plain activation).
+
+    Training mode, channel count a multiple of 8: the statistics come either from the producing convolution's epilogue
+    (`pre_sums`) or from one accumulate-only pass into a slice of the step's zero arena; finalisation (mean / invstd / running
+    statistics), normalisation and activation are ONE launch (pcb_bn_forward_fused).  Backward = one reduction + one apply
+    launch that also writes dgamma / dbeta -- straight into the training engine's gradient arena when the parameters carry
+    gradient sinks (no autograd accumulation kernels)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope, msum=None):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope, msum=None, pre_sums=None):
         lib = _lib.load()
         n, c, h, w = x.shape
         count = n * h * w
@@ -581,29 +652,42 @@ class BNActFn(torch.autograd.Function):
         dev = x.device
         has_bn = gamma is not None
         scale = shift = mean = invstd = None
-        if has_bn:
-            scale = torch.empty((c,), dtype=torch.float32, device=dev)
-            shift = torch.empty_like(scale)
-            use_batch = training or running_mean is None
-            if use_batch:
-                if count <= 1 and training:
-                    raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
-                sums = torch.empty((2, c), dtype=torch.float64, device=dev)
-                _lib.check(lib.pcb_bn_stats(x.data_ptr(), code, count, c, sums[0].data_ptr(), sums[1].data_ptr(), _stream()))
-                mean = torch.empty_like(scale)
-                invstd = torch.empty_like(scale)
-                _lib.check(lib.pcb_bn_finalize(sums[0].data_ptr(), sums[1].data_ptr(), count, c, gamma.data_ptr(), beta.data_ptr(),
-                                               _ptr(running_mean) if training else None, _ptr(running_var) if training else None,
-                                               _ptr(nbt) if training else None, float(momentum), float(eps), 1,
-                                               scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), _stream()))
-            else:
-                _lib.check(lib.pcb_bn_finalize(None, None, count, c, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
-                                               running_var.data_ptr(), None, float(momentum), float(eps), 0,
-                                               scale.data_ptr(), shift.data_ptr(), None, None, _stream()))
         y = torch.empty_like(x, memory_format=CL)
-        _lib.check(lib.pcb_bn_act_forward(x.data_ptr(), code, count, c, _ptr(scale), _ptr(shift), act, float(slope),
-                                          _ptr(residual), y.data_ptr(), _stream()))
+        use_batch = has_bn and (training or running_mean is None)
+        if use_batch and count <= 1 and training:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
+        if use_batch and _vec_bn(c):
+            sums = pre_sums
+            if sums is None:
+                sums = zeros_f64(2 * c, dev)
+                _lib.check(lib.pcb_bn_stats_acc(x.data_ptr(), code, count, c, sums.data_ptr(), _stream()))
+            coef = torch.empty((4, c), dtype=torch.float32, device=dev)
+            _lib.check(lib.pcb_bn_forward_fused(x.data_ptr(), code, count, c, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                _ptr(running_mean) if training else None, _ptr(running_var) if training else None,
+                                                _ptr(nbt) if training else None, float(momentum), float(eps), act, float(slope),
+                                                _ptr(residual), y.data_ptr(), coef.data_ptr(), _stream()))
+            scale, shift, mean, invstd = coef[0], coef[1], coef[2], coef[3]
+        else:
+            if has_bn:
+                scale = torch.empty((c,), dtype=torch.float32, device=dev)
+                shift = torch.empty_like(scale)
+                if use_batch:
+                    sums = torch.empty((2, c), dtype=torch.float64, device=dev)
+                    _lib.check(lib.pcb_bn_stats(x.data_ptr(), code, count, c, sums[0].data_ptr(), sums[1].data_ptr(), _stream()))
+                    mean = torch.empty_like(scale)
+                    invstd = torch.empty_like(scale)
+                    _lib.check(lib.pcb_bn_finalize(sums[0].data_ptr(), sums[1].data_ptr(), count, c, gamma.data_ptr(), beta.data_ptr(),
+                                                   _ptr(running_mean) if training else None, _ptr(running_var) if training else None,
+                                                   _ptr(nbt) if training else None, float(momentum), float(eps), 1,
+                                                   scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), _stream()))
+                else:
+                    _lib.check(lib.pcb_bn_finalize(None, None, count, c, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                                   running_var.data_ptr(), None, float(momentum), float(eps), 0,
+                                                   scale.data_ptr(), shift.data_ptr(), None, None, _stream()))
+            _lib.check(lib.pcb_bn_act_forward(x.data_ptr(), code, count, c, _ptr(scale), _ptr(shift), act, float(slope),
+                                              _ptr(residual), y.data_ptr(), _stream()))
         ctx.cfg = (count, c, code, act, float(slope), has_bn, mean is not None, residual is not None)
+        ctx.params = (gamma, beta)
         ctx.save_for_backward(x, scale, shift, mean, invstd, msum)
         return y
 
@@ -618,28 +702,50 @@ class BNActFn(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=CL)
         dgamma = dbeta = None
         if has_bn and batch_stats:
-            sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
-            _lib.check(lib.pcb_bn_act_backward_reduce(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
-                                                      mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
-                                                      sums[1].data_ptr(), _stream()))
-            dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
-            dbeta = torch.empty_like(dgamma)
+            dev = x.device
+            # parameter gradients: written in place into the engine's gradient arena when the parameters carry sinks
+            gamma, beta = ctx.params
+            sinks = []
+            outs = []
+            for p in (gamma, beta):
+                sk = getattr(p, "_pcb_grad_sink", None)
+                if sk is not None and not sk.used and sk.view.dtype == torch.float32 and sk.view.numel() == c and sk.view.is_contiguous() \
+                        and p.requires_grad:
+                    sk.used = True
+                    sinks.append(sk); outs.append(sk.view)
+                else:
+                    sinks.append(None); outs.append(torch.empty((c,), dtype=torch.float32, device=dev))
+            if _vec_bn(c):
+                sums = zeros_f64(2 * c, dev)
+                _lib.check(lib.pcb_bn_act_backward_reduce_acc(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
+                                                              mean.data_ptr(), invstd.data_ptr(), act, slope, sums.data_ptr(), _stream()))
+                s0, s1 = sums.data_ptr(), sums.data_ptr() + 8 * c
+            else:
+                sums = torch.empty((2, c), dtype=torch.float64, device=dev)
+                _lib.check(lib.pcb_bn_act_backward_reduce(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
+                                                          mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
+                                                          sums[1].data_ptr(), _stream()))
+                s0, s1 = sums[0].data_ptr(), sums[1].data_ptr()
             if msum is not None:
                 _lib.check(lib.pcb_bn_act_backward_apply_renorm(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
-                                                                mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
-                                                                sums[1].data_ptr(), 1, msum.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
-                                                                dbeta.data_ptr(), _stream()))
+                                                                mean.data_ptr(), invstd.data_ptr(), act, slope, s0, s1, 1, msum.data_ptr(),
+                                                                dx.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), _stream()))
             else:
                 _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
-                                                         mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
-                                                         sums[1].data_ptr(), 1, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream()))
+                                                         mean.data_ptr(), invstd.data_ptr(), act, slope, s0, s1, 1, dx.data_ptr(),
+                                                         outs[0].data_ptr(), outs[1].data_ptr(), _stream()))
+            dgamma = None if sinks[0] is not None else outs[0]
+            dbeta = None if sinks[1] is not None else outs[1]
+            for sk in sinks:
+                if sk is not None and sk.on_written is not None:
+                    sk.on_written()
         elif has_bn:   # eval-mode BN: a fixed affine map (parameter grads not produced in eval)
             _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
                                                      None, None, act, slope, None, None, 0, dx.data_ptr(), None, None, _stream()))
         else:
             _lib.check(lib.pcb_bn_act_backward_apply(gy.data_ptr(), x.data_ptr(), code, count, c, None, None, None, None, act, slope,
                                                      None, None, 0, dx.data_ptr(), None, None, _stream()))
-        return dx, dgamma, dbeta, (gy if has_res else None), None, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, (gy if has_res else None), None, None, None, None, None, None, None, None, None, None
 
 
 def bn_act(x, bn, act, residual=None, handoff=None):
@@ -656,8 +762,9 @@ def bn_act(x, bn, act, residual=None, handoff=None):
     if handoff is not None and handoff.eligible and bn.training and x.requires_grad and x.shape[1] % 8 == 0 and x.shape[1] <= 2048 \
             and x.is_contiguous(memory_format=CL):
         msum, handoff.fused = handoff.msum, True
+    pre_sums = handoff.bn_sums if (handoff is not None and bn.training and bn.weight is not None) else None
     return BNActFn.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                         bn.training, momentum, bn.eps, code, slope, msum)
+                         bn.training, momentum, bn.eps, code, slope, msum, pre_sums)
 
 
 def activation_only(x, act, residual=None):
