@@ -14,6 +14,65 @@ import torch
 import torch.nn.functional as F
 
 # ----------------------------------------------------------------------------
+# storage-precision emulation (bf16 mode of the CUDA path)
+# ----------------------------------------------------------------------------
+# The CUDA path's tensor-core mode keeps activations and activation gradients in bf16 between kernels (fp32 accumulation
+# inside them).  With `storage(torch.bfloat16)` active the oracle rounds at exactly those hand-over points -- and nowhere
+# else -- so that a bf16 GPU result can be compared with "the reference algorithm under the same storage precision" at a tight
+# tolerance instead of with the fp32 reference at a loose one:
+#   forward : conv operands w, x*mask ; conv output y (after renormalisation) ; BN+activation output z ; network output
+#   backward: gradient of every conv INPUT use (the data-gradient kernel's output, before the 2x2 sum of an upsampled source),
+#             gradient of every block output (sum of its consumers' gradients = a bf16 add / the 2x2 reduction),
+#             gradient of the conv's raw accumulator dc = dy / mask_sum (BatchNorm-backward / renorm-backward output)
+_STORAGE = None
+
+
+class storage:
+    """Context manager: `with storage(torch.bfloat16): ...` (None = exact fp32, the default)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _STORAGE
+        self.prev, _STORAGE = _STORAGE, self.dtype
+
+    def __exit__(self, *exc):
+        global _STORAGE
+        _STORAGE = self.prev
+        return False
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).to(g.dtype), None
+
+
+def _rf(x):
+    return x if _STORAGE is None else _RoundFwd.apply(x, _STORAGE)
+
+
+def _rb(x):
+    return x if (_STORAGE is None or not x.requires_grad) else _RoundBwd.apply(x, _STORAGE)
+
+
+# ----------------------------------------------------------------------------
 # L1: the three partial convolutions               models/partial_convolution.py
 # ----------------------------------------------------------------------------
 
@@ -32,7 +91,12 @@ def partial_conv(x, mask, weight, bias=None, stride=1, padding=0, dilation=1, gr
     Returns (output, new_mask).  `new_mask` is a stride-0 expand when
     same_holes (partial_convolution.py:76-77).
     """
-    out = F.conv2d(x * mask, weight, bias, stride, padding, dilation, groups)          # :51
+    x, weight = _rb(x), _rf(weight)                                                     # (storage emulation: no-ops in fp32 mode)
+    out = F.conv2d(x * mask, weight, None if _STORAGE is not None else bias, stride, padding, dilation, groups)   # :51
+    if _STORAGE is not None:
+        out = _rb(out)                                                                  # dc = dy / mask_sum is stored rounded
+        if bias is not None:
+            out = out + bias.view(1, -1, 1, 1)
     if bias is not None:
         out_bias = bias.view(1, -1, 1, 1).expand_as(out)                                # :52-53
     else:
@@ -47,7 +111,7 @@ def partial_conv(x, mask, weight, bias=None, stride=1, padding=0, dilation=1, gr
             msum = F.conv2d(mask, ones_w, None, stride, padding, dilation, groups)      # :63
             holes = msum == 0                                                           # :64
     msum = msum.masked_fill(holes, 1.0)                                                 # :66
-    out = ((out - out_bias) / msum + out_bias).masked_fill(holes, 0.0)                  # :71-72
+    out = _rf(((out - out_bias) / msum + out_bias).masked_fill(holes, 0.0))             # :71-72
     new_mask = torch.ones_like(msum).masked_fill(holes, 0.0)                            # :74-75
     if same_holes:
         new_mask = new_mask.expand_as(out)                                              # :77
@@ -56,21 +120,26 @@ def partial_conv(x, mask, weight, bias=None, stride=1, padding=0, dilation=1, gr
 
 def partial_conv_1x1(x, mask, weight, bias=None, groups=1):
     """PartialConv1x1.forward, partial_convolution.py:101-105 (x is NOT masked)."""
-    out = F.conv2d(x, weight, bias, 1, 0, 1, groups)
+    out = _rf(_rb(F.conv2d(_rb(x), _rf(weight), bias, 1, 0, 1, groups)))
     return out, mask[:, :1, :, :].expand_as(out)
 
 
 def partial_conv_no_holes(x, mask, weight, bias=None, stride=1, padding=0, dilation=1):
     """PartialConvNoHoles.forward, partial_convolution.py:121-137 (no zero guard: NaN on an
     all-hole window, by design of the reference)."""
-    out = F.conv2d(x * mask, weight, bias, stride, padding, dilation, 1)
+    x, weight = _rb(x), _rf(weight)
+    out = F.conv2d(x * mask, weight, None if _STORAGE is not None else bias, stride, padding, dilation, 1)
+    if _STORAGE is not None:
+        out = _rb(out)
+        if bias is not None:
+            out = out + bias.view(1, -1, 1, 1)
     if bias is not None:
         out_bias = bias.view(1, -1, 1, 1).expand_as(out)
     else:
         out_bias = torch.zeros_like(out)
     with torch.no_grad():
         msum = F.conv2d(mask, torch.ones_like(weight), None, stride, padding, dilation, 1)
-    out = (out - out_bias) / msum + out_bias
+    out = _rf((out - out_bias) / msum + out_bias)
     return out, torch.ones_like(out)
 
 
@@ -109,7 +178,7 @@ def double_upsample(x, mask, scale=2):
 
 
 def pconv_block(sd, prefix, x, mask, *, k, s=1, p=0, d=1, groups=1, bn=True, act=None,
-                use_1_conv=False, no_holes_1_conv=False, same_holes=False, training=True):
+                use_1_conv=False, no_holes_1_conv=False, same_holes=False, training=True, residual=None):
     """partial_convolution_block (+ its BN/act tail), partial_convolution.py:163-180.
 
     `prefix` addresses the nn.Sequential the factory returns: `<prefix>0.` is the conv,
@@ -124,11 +193,18 @@ def pconv_block(sd, prefix, x, mask, *, k, s=1, p=0, d=1, groups=1, bn=True, act
         x, mask = partial_conv_no_holes(x, mask, w, b, s, p, d)
     else:
         x, mask = partial_conv(x, mask, w, b, s, p, d, groups, same_holes)
+    # `residual`: the identity shortcut some callers add to the block output (image_inpainting.py:216, MobileNetV2.py:187).
+    # Mathematically the caller's `out + residual`; taken here so that storage emulation rounds the SUM once, like the
+    # CUDA path's fused BN + activation + residual pass does.
     if bn:
         x = activation(act, batchnorm(x, sd, prefix + "1.bn_act.0.", training))         # :195-201
     elif act:
         x = activation(act, x)                                                          # :177-178
-    return x, mask
+    if residual is not None:
+        x = x + residual
+    if bn or act or residual is not None:
+        x = _rf(x)
+    return _rb(x), mask
 
 
 # ----------------------------------------------------------------------------
@@ -182,9 +258,9 @@ def _double_partial_residual(sd, prefix, x, mask, k, stride, rates, act, same_ho
     (the ctor's own `padding`/`dilation` args are ignored, :201-202,206-207)."""
     x1, m1 = pconv_block(sd, prefix + "conv1.", x, mask, k=k, s=stride, p=rates[0], d=rates[0], bn=True,
                          act=act, same_holes=same_holes, training=training)
-    x2, m2 = pconv_block(sd, prefix + "conv2.", x1, m1, k=k, s=1, p=rates[1], d=rates[1], bn=True,
-                         act=act, same_holes=same_holes, training=training)
-    return x2 + x1, m2                                                                  # :216
+    y, m2 = pconv_block(sd, prefix + "conv2.", x1, m1, k=k, s=1, p=rates[1], d=rates[1], bn=True,
+                        act=act, same_holes=same_holes, training=training, residual=x1)   # x2 + x1, :216
+    return y, m2
 
 
 def image_fill_origin_v2(sd, x, mask, training=True):
@@ -217,9 +293,8 @@ def _partial_inverted_residual(sd, prefix, x, mask, cin, cout, k, s, p, d, t, ac
     y, m = pconv_block(sd, prefix + "conv.1.", y, m, k=k, s=s, p=p, d=d, groups=mid, bn=True, act=act,
                        same_holes=same_holes, training=training)                       # :174-176
     y, m = pconv_block(sd, prefix + "conv.2.", y, m, k=1, bn=True, act=None, use_1_conv=use_1,
-                       no_holes_1_conv=no_holes, training=training)                    # :178-180
-    if s == 1 and cin == cout:                                                          # :158,186-187
-        y = x + y
+                       no_holes_1_conv=no_holes, training=training,
+                       residual=x if (s == 1 and cin == cout) else None)               # :178-180, shortcut :158,186-187
     return y, m
 
 

@@ -3,9 +3,9 @@
 prefetch, everything bench.py times -- against the ORACLE (oracle/pconv_torch.py, pinned bit-for-bit to the reference by
 tests/golden/net_ImageFillOrigin_512.npz), not against the engine's own eager mode.
 
-Tolerances (bf16 storage + tcgen05, compared with the fp32 CPU oracle on the same fp32 weights; same bars as
-tests/test_gpu_parity.py::test_network_bf16_tensor_core_mode): loss 2e-3 relative; convolution weight gradients 1e-2 of
-max|ref|; BatchNorm scale/shift gradients 1e-1 of max|ref| (LeakyReLU sign flips within one bf16 ulp of 0).
+Tolerances: the loss within 2e-3 of the fp32 oracle; every checked gradient within 3e-2 of max|ref| of the oracle run under
+the SAME storage precision (oracle.pconv_torch.storage(bfloat16): activations / activation gradients rounded to bf16 at the
+kernel hand-over points, fp32 everywhere else) -- the comparison that isolates the kernels from the precision policy.
 """
 import os
 import socket
@@ -39,12 +39,12 @@ def _inputs(batch, hw, seed=21):
 
 
 def _oracle_step(sd0, x, mask):
-    """fwd + bwd of the reference algorithm on the host cores (fp32): loss and gradients by parameter name."""
-    sd = O.clone_state_dict(sd0, requires_grad=True)
-    out = O.image_fill_origin(sd, x * mask, mask, training=True)
-    loss = out.abs().mean()
-    loss.backward()
-    return float(loss), {k: sd[k].grad for k in GRAD_KEYS}
+    """fwd (fp32) and fwd + bwd (bf16 storage emulation) of the reference algorithm on the host cores."""
+    from gpu_cases import oracle_bf16_step
+    with torch.no_grad():
+        loss32 = float(O.image_fill_origin(O.clone_state_dict(sd0), x * mask, mask, training=True).abs().mean())
+    loss16, grads = oracle_bf16_step("ImageFillOrigin", x, mask, sd0)
+    return loss32, loss16, grads
 
 
 def test_train_step_graph_512_batch8_matches_oracle(dev):
@@ -57,7 +57,7 @@ def test_train_step_graph_512_batch8_matches_oracle(dev):
     sd0 = det_fill_state_dict(net.state_dict())
     net.load_state_dict(sd0)
     x, mask = _inputs(8, 512)
-    ref_loss, ref_grads = _oracle_step(sd0, x, mask)
+    ref_loss, ref_loss16, ref_grads = _oracle_step(sd0, x, mask)
 
     net = net.to(dev)
     # lr = 0: the eager warm-up steps and the capture run leave the weights where the oracle has them
@@ -70,11 +70,13 @@ def test_train_step_graph_512_batch8_matches_oracle(dev):
     code = _lib.ctypes.c_int(0)
     _lib.check(_lib.load().pcb_debug_pipeline_status(_lib.ctypes.byref(code)))
     assert code.value == 0, f"a tensor-core pipeline wait timed out (code {code.value})"
-    assert abs(loss - ref_loss) <= 2e-3 * abs(ref_loss), (loss, ref_loss)
+    assert abs(loss - ref_loss) <= 2e-3 * abs(ref_loss) and abs(loss - ref_loss16) <= 1e-3 * abs(ref_loss16), (loss, ref_loss, ref_loss16)
     params = dict(net.named_parameters())
-    errs = {k: relerr(params[k].grad, ref_grads[k]) for k in GRAD_KEYS}
-    assert all(v <= 1e-2 for k, v in errs.items() if k.endswith("feature_conv.weight")), errs
-    assert max(errs.values()) <= 1e-1, errs
+    errs = {k: relerr(params[k].grad, ref_grads[k]) for k in ref_grads}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    assert all(errs[k] <= 3e-2 for k in GRAD_KEYS), worst
+    # the count-8 BatchNorms at the bottom of the U (2x2 maps) make the deepest gradients ill-conditioned: looser there
+    assert max(errs.values()) <= 1e-1, worst
 
     # graph -> eager evaluation -> graph.  The eager pass re-lays-out the weights into NEW buffers (the optimiser
     # bumped the weight epoch); the graph must keep replaying on its own (pinned) operand buffers.

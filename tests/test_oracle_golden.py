@@ -151,3 +151,37 @@ def test_network_forward_backward(cls_name, tag):
         assert abs(got - float(g[k])) <= 1e-9 * max(1.0, abs(float(g[k]))), k
     for k in [k for k in g if k.startswith("bn.")]:
         assert np.array_equal(sd[k[3:]].numpy(), g[k]), k
+
+
+def test_bf16_storage_emulation_is_off_by_default_and_documents_the_precision_gap():
+    """oracle.pconv_torch.storage(bfloat16) rounds activations / activation gradients where the CUDA path's tensor-core mode
+    stores them in bf16.  (a) Outside the context manager the oracle is untouched (the golden tests above pin that bit for bit);
+    (b) under it the forward stays within bf16 rounding of the fp32 reference while gradients that pass through a BatchNorm move
+    by far more than bf16 epsilon on ill-conditioned channels -- the reason the GPU parity tests compare bf16 gradients with the
+    emulated oracle and only the forward / loss / tail layer with the fp32 reference."""
+    cls_name, n, hw = "ImageFillOrigin", 2, 256
+    sd0 = _net_state_dict(cls_name)
+    x = det_tensor("emu.x", (n, 3, hw, hw))
+    from text_segmentation_image_inpainting_b200.synthetic import random_hole_masks
+    mask = torch.from_numpy(random_hole_masks(n, hw, hw, seed=3))
+
+    def run(st):
+        sd = O.clone_state_dict(sd0, requires_grad=True)
+        with O.storage(st):
+            xin = x * mask if st is None else (x * mask).to(st).float()
+            out = O.NETWORKS[cls_name](sd, xin, mask, training=True)
+            if st is not None:
+                out = O._rb(O._rf(out))
+            loss = out.abs().mean()
+            loss.backward()
+        return out.detach(), float(loss.detach()), {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+    assert O._STORAGE is None
+    o32, l32, g32 = run(None)
+    o16, l16, g16 = run(torch.bfloat16)
+    assert O._STORAGE is None
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())  # noqa: E731
+    assert rel(o16, o32) <= 2e-2 and abs(l16 - l32) <= 2e-3 * l32
+    assert rel(g16["decoder.7.0.feature_conv.weight"], g32["decoder.7.0.feature_conv.weight"]) <= 1e-2      # no BatchNorm behind it
+    gap = max(rel(g16[k], g32[k]) for k in g32 if ".bn_act." in k or k.startswith("decoder.6.0.0"))
+    assert gap > 2e-2, gap            # the gap this emulation exists to account for

@@ -311,7 +311,7 @@ class PartialConvFn(torch.autograd.Function):
             with _Timed("fwd", geom):
                 _lib.check(lib.pcb_pconv_forward_bn(ctypes.byref(c), w_fwd.data_ptr(), _ptr(b32), y.data_ptr(), nhwc_layout(y), msum.data_ptr(),
                                                     newmask.data_ptr(), ws.data_ptr(), 0, _ptr(bn_sums), _stream()))
-        ctx.geom, ctx.wprep, ctx.has_bias, ctx.weight_ref = geom, wprep, bias is not None, weight
+        ctx.geom, ctx.wprep, ctx.has_bias, ctx.weight_ref, ctx.bias_ref = geom, wprep, bias is not None, weight, bias
         ctx.handoff = handoff
         if handoff is not None:
             handoff.msum = msum
@@ -339,9 +339,19 @@ class PartialConvFn(torch.autograd.Function):
             dc = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, tdtype, dev) if geom.dtype == PCB_BF16 else \
                 torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=tdtype, device=dev, memory_format=CL)
             dcs = nhwc_layout(dc)
-            dbias = torch.empty((geom.cout,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+            dbias = bsink = None
+            if ctx.has_bias:
+                bsink = getattr(ctx.bias_ref, "_pcb_grad_sink", None)
+                if bsink is not None and not bsink.used and bsink.view.dtype == torch.float32 and bsink.view.numel() == geom.cout \
+                        and bsink.view.is_contiguous():
+                    bsink.used = True                     # the kernel overwrites the arena slice: no gradient tensor for autograd
+                else:
+                    bsink = None
+                    dbias = torch.empty((geom.cout,), dtype=torch.float32, device=dev)
             _lib.check(lib.pcb_pconv_renorm_backward(ctypes.byref(c), gy.data_ptr(), nhwc_layout(gy), msum.data_ptr(), dc.data_ptr(), dcs,
-                                                     _ptr(dbias), _stream()))
+                                                     _ptr(bsink.view if bsink is not None else dbias), _stream()))
+            if bsink is not None and bsink.on_written is not None:
+                bsink.on_written()
         dw = None
         need = [ctx.needs_input_grad[5 + i] for i in range(len(xs))]
         side = None
