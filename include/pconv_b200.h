@@ -176,6 +176,11 @@ int pcb_bn_act_backward_reduce(const void *gy, const void *x, int dtype, long lo
 int pcb_bn_act_backward_reduce_acc(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,
                                    const float *shift, const float *mean, const float *invstd, int act, float slope,
                                    double *sums, pcb_stream_t stream);
+/* Whole training-mode backward of a SMALL tensor (count <= ~16 K rows) in ONE launch: reduction + apply + dgamma/dbeta
+ * [+ division by the producing partial convolution's mask sums when msum != NULL].  coef = the [4][c] block of
+ * pcb_bn_forward_fused (scale | shift | mean | invstd).  c % 8 == 0. */
+int pcb_bn_act_backward_small(const void *gy, const void *x, int dtype, long long count, int c, const float *coef, int act,
+                              float slope, const float *msum, void *dx, float *dgamma, float *dbeta, pcb_stream_t stream);
 /* dx = scale * (gz - sum_g/count - xhat * sum_gx/count)  (training) or scale * gz (eval / no BN: scale NULL => gz).
  * dgamma = sum_gx, dbeta = sum_g (fp32, optional).                                             */
 int pcb_bn_act_backward_apply(const void *gy, const void *x, int dtype, long long count, int c, const float *scale,

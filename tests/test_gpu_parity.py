@@ -87,14 +87,15 @@ def test_network_bf16_tensor_core_mode(cls_name, tag, dev):
     assert all(v <= 3e-2 for k, v in errs.items() if k.startswith("g.")), worst
 
 
-def test_bn_act_and_running_stats(dev):
+@pytest.mark.parametrize("c", [24, 256])       # 256 channels x 297 rows: the one-launch small-tensor backward (pcb_bn_act_backward_small)
+def test_bn_act_and_running_stats(c, dev):
     from oracle.detfill import det_fill_state_dict, det_tensor
     from text_segmentation_image_inpainting_b200 import ops
     for dtype, tol in ((F32, 2e-5), (BF, 2e-2)):
         for act in (torch.nn.ReLU(), torch.nn.LeakyReLU(0.2), None, torch.nn.ReLU6()):
-            bn = torch.nn.BatchNorm2d(24); sd = det_fill_state_dict(bn.state_dict()); bn.load_state_dict(sd)
-            ref = torch.nn.BatchNorm2d(24); ref.load_state_dict(sd)
-            xq = (det_tensor("bn.x", (3, 24, 9, 11)) * 2 + 0.3).to(dtype).float()
+            bn = torch.nn.BatchNorm2d(c); sd = det_fill_state_dict(bn.state_dict()); bn.load_state_dict(sd)
+            ref = torch.nn.BatchNorm2d(c); ref.load_state_dict(sd)
+            xq = (det_tensor("bn.x", (3, c, 9, 11)) * 2 + 0.3).to(dtype).float()
             xr = xq.clone().requires_grad_(True)
             yr = ref(xr); yr = act(yr) if act else yr
             gy = det_tensor("bn.gy", tuple(yr.shape)).to(dtype).float()
@@ -107,6 +108,15 @@ def test_bn_act_and_running_stats(dev):
                          (bn.running_mean, ref.running_mean), (bn.running_var, ref.running_var)):
                 assert relerr(a, b) <= tol
             assert int(bn.num_batches_tracked) == 1
+            if c >= 256:                  # the two-launch path must agree with the one-launch path
+                ops.set_bn_small_kernel(False)
+                try:
+                    bn.zero_grad(set_to_none=True)
+                    x2 = xd.detach().clone().requires_grad_(True)
+                    ops.bn_act(x2, bn, act).backward(gy.to(dev).to(dtype))
+                    assert relerr(x2.grad, xd.grad) <= (1e-5 if dtype == F32 else 1e-2) and relerr(bn.weight.grad, ref.weight.grad) <= tol
+                finally:
+                    ops.set_bn_small_kernel(True)
             bn.eval(); ref.eval()
             assert relerr(ops.bn_act(xd.detach(), bn, act), act(ref(xq)) if act else ref(xq)) <= tol
 

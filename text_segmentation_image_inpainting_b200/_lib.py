@@ -54,6 +54,7 @@ _SIGS = {
                                      c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_bn_act_backward_reduce_acc": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_int, c_float, c_void_p, c_void_p]),
+    "pcb_bn_act_backward_small": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_bn_finalize": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcb_bn_act_forward": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),

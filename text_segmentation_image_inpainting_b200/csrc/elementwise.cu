@@ -216,90 +216,171 @@ __global__ void bn_act_fwd_scalar_kernel(const T *x, long long numel, int c, con
     }
 }
 
+// sum_g = sum gz, sum_gx = sum gz * xhat with gz = gy * act'(BN(x)), xhat = (x - mean) * invstd.  The loop accumulates
+// gz * (x - mean) and multiplies by invstd once at the end: three coefficient vectors live in registers instead of four.
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
-                                                                   const float *__restrict__ scale, const float *__restrict__ shift,
-                                                                   const float *__restrict__ mean, const float *__restrict__ invstd,
-                                                                   int act, float slope, double *sum_g, double *sum_gx) {
+__global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_reduce_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
+                                                                      const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                      const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                                      int act, float slope, double *sum_g, double *sum_gx) {
     const int cv = c >> 3, rpb = EW_THREADS / cv;
     const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
     if (r < rpb) {
-        float sc[8], sh[8], mu[8], is[8];
+        float sc[8], sh[8], mu[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             sc[j] = scale ? scale[v * 8 + j] : 1.f; sh[j] = shift ? shift[v * 8 + j] : 0.f;
-            mu[j] = mean ? mean[v * 8 + j] : 0.f; is[j] = invstd ? invstd[v * 8 + j] : 1.f;
+            mu[j] = mean ? mean[v * 8 + j] : 0.f;
         }
+        const long long step = static_cast<long long>(gridDim.x) * rpb;
+        const T *pg = gy + v * 8, *px = x + v * 8;
 #pragma unroll 4
-        for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
+        for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
             float g[8], f[8];
-            Vec8<T>::load(gy + row * c + v * 8, g);
-            Vec8<T>::load(x + row * c + v * 8, f);
+            Vec8<T>::load(pg + row * c, g);
+            Vec8<T>::load(px + row * c, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
                 acc[0][j] += gz;
-                acc[1][j] += gz * (f[j] - mu[j]) * is[j];
+                acc[1][j] += gz * (f[j] - mu[j]);
             }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[1][j] *= invstd ? invstd[v * 8 + j] : 1.f;
     }
     double *const outs[2] = {sum_g, sum_gx};
     block_flush<2>(acc, cv, rpb, r, v, outs);
 }
 
+// dx = scale * (gz - sum_g/count - xhat * sum_gx/count) [* 1/mask_sum] written as  A*gz + B*(x - mean) + C  with per-channel
+// A = scale, B = -scale*invstd*sum_gx/count, C = -scale*sum_g/count: five coefficient vectors in registers.
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
-                                                                  const float *__restrict__ scale, const float *__restrict__ shift,
-                                                                  const float *__restrict__ mean, const float *__restrict__ invstd, int act,
-                                                                  float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
-                                                                  int training, const float *__restrict__ msum, T *__restrict__ dx,
-                                                                  float *__restrict__ dgamma, float *__restrict__ dbeta) {
+__global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_apply_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
+                                                                     const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                     const float *__restrict__ mean, const float *__restrict__ invstd, int act,
+                                                                     float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
+                                                                     int training, const float *__restrict__ msum, T *__restrict__ dx,
+                                                                     float *__restrict__ dgamma, float *__restrict__ dbeta) {
     const int cv = c >> 3, rpb = EW_THREADS / cv;
     const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
     if (r >= rpb) return;
     const float inv_count = 1.0f / static_cast<float>(count);
     const bool full = scale && training;
     const bool writer = full && blockIdx.x == 0 && r == 0;            // parameter gradients: dgamma = sum gz*xhat, dbeta = sum gz
-    float sc[8], sh[8], mu[8], is[8], mg[8], mgx[8];
+    float sc[8], sh[8], mu[8], cb[8], cc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int ch = v * 8 + j;
         sc[j] = scale ? scale[ch] : 1.f; sh[j] = scale ? shift[ch] : 0.f;
-        mu[j] = full ? mean[ch] : 0.f; is[j] = full ? invstd[ch] : 0.f;
+        mu[j] = full ? mean[ch] : 0.f;
         const float sg = full ? static_cast<float>(sum_g[ch]) : 0.f, sgx = full ? static_cast<float>(sum_gx[ch]) : 0.f;
-        mg[j] = sg * inv_count;
-        mgx[j] = sgx * inv_count;
+        cb[j] = full ? -sc[j] * invstd[ch] * sgx * inv_count : 0.f;
+        cc[j] = full ? -sc[j] * sg * inv_count : 0.f;
         if (writer) {
             if (dgamma) dgamma[ch] = sgx;
             if (dbeta) dbeta[ch] = sg;
         }
     }
+    const float ca = (scale != nullptr) ? 1.f : 0.f;                  // no BN at all: d = gz
     const long long step = static_cast<long long>(gridDim.x) * rpb;
     const bool renorm = msum != nullptr;
+    const T *pg = gy + v * 8, *px = x + v * 8;
+    T *pd = dx + v * 8;
 #pragma unroll 4
     for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
         float g[8], f[8];
         // optional fused renormalisation backward of the producing partial convolution: dc = d / s, 0 at holes
         const float s = renorm ? __ldg(msum + row) : 1.f;
-        Vec8<T>::load(gy + row * c + v * 8, g);
-        Vec8<T>::load(x + row * c + v * 8, f);
+        Vec8<T>::load(pg + row * c, g);
+        Vec8<T>::load(px + row * c, f);
         const float rs = (s == 0.f) ? 0.f : __frcp_rn(s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
-            float d;
-            if (!scale) d = gz;
-            else if (!training) d = sc[j] * gz;
-            else {
-                const float xhat = (f[j] - mu[j]) * is[j];
-                d = sc[j] * (gz - mg[j] - xhat * mgx[j]);
-            }
+            const float d = (ca != 0.f) ? fmaf(sc[j], gz, fmaf(cb[j], f[j] - mu[j], cc[j])) : gz;
             f[j] = renorm ? d * rs : d;
         }
-        Vec8<T>::store(dx + row * c + v * 8, f);
+        Vec8<T>::store(pd + row * c, f);
+    }
+}
+
+// Small tensors (the bottom of the U: <= 16 K rows): reduction AND apply in one launch.  One CTA per 8-channel vector walks all
+// rows twice (the second pass hits L2), so no grid-wide dependency exists: the whole BatchNorm backward of such a layer is one
+// kernel instead of memset + reduce + apply + parameter-gradient.
+constexpr int BN_SMALL_THREADS = 1024;
+template <typename T>
+__global__ void __launch_bounds__(BN_SMALL_THREADS) bn_bwd_small_kernel(const T *__restrict__ gy, const T *__restrict__ x, int count, int c,
+                                                                        const float *__restrict__ coef /* [4][c] scale|shift|mean|invstd */,
+                                                                        int act, float slope, const float *__restrict__ msum, T *__restrict__ dx,
+                                                                        float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    __shared__ float s_part[BN_SMALL_THREADS / 32][16];
+    __shared__ float s_tot[16];
+    const int v = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = v * 8 + j;
+        sc[j] = coef[ch]; sh[j] = coef[c + ch]; mu[j] = coef[2 * c + ch]; is[j] = coef[3 * c + ch];
+    }
+    const T *pg = gy + v * 8, *px = x + v * 8;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (int row = t; row < count; row += BN_SMALL_THREADS) {
+        float g[8], f[8];
+        Vec8<T>::load(pg + static_cast<long long>(row) * c, g);
+        Vec8<T>::load(px + static_cast<long long>(row) * c, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+            acc[j] += gz;
+            acc[8 + j] += gz * (f[j] - mu[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float w = warp_sum(acc[j]);
+        if (lane == 0) s_part[warp][j] = w;
+    }
+    __syncthreads();
+    if (t < 16) {
+        float tot = 0.f;
+        for (int w = 0; w < BN_SMALL_THREADS / 32; ++w) tot += s_part[w][t];
+        const int ch = v * 8 + (t & 7);
+        if (t >= 8) tot *= coef[3 * c + ch];                                  // invstd (read from memory: no dynamic register indexing)
+        s_tot[t] = tot;
+        if (t < 8 && dbeta) dbeta[ch] = tot;
+        if (t >= 8 && dgamma) dgamma[ch] = tot;
+    }
+    __syncthreads();
+    const float inv_count = 1.0f / static_cast<float>(count);
+    float cb[8], cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cb[j] = -sc[j] * is[j] * s_tot[8 + j] * inv_count;
+        cc[j] = -sc[j] * s_tot[j] * inv_count;
+    }
+    T *pd = dx + v * 8;
+    const bool renorm = msum != nullptr;
+#pragma unroll 4
+    for (int row = t; row < count; row += BN_SMALL_THREADS) {
+        float g[8], f[8];
+        const float s = renorm ? __ldg(msum + row) : 1.f;
+        Vec8<T>::load(pg + static_cast<long long>(row) * c, g);
+        Vec8<T>::load(px + static_cast<long long>(row) * c, f);
+        const float rs = (s == 0.f) ? 0.f : __frcp_rn(s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+            const float d = fmaf(sc[j], gz, fmaf(cb[j], f[j] - mu[j], cc[j]));
+            f[j] = renorm ? d * rs : d;
+        }
+        Vec8<T>::store(pd + static_cast<long long>(row) * c, f);
     }
 }
 
@@ -713,6 +794,18 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
     const int grid = ew_grid_red(count, rpb * 8);
     if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
     else bn_bwd_reduce_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Whole training-mode BatchNorm(+act) backward of a SMALL tensor in one launch (reduction + apply + parameter gradients [+ the
+// renormalisation backward of the producing partial convolution when msum != NULL]).  coef = the [4][c] block written by
+// pcb_bn_forward_fused.  Intended for count <= 16384 rows (one CTA per 8 channels walks every row twice); c % 8 == 0.
+extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_small(const void *gy, const void *x, int dtype, long long count, int c, const float *coef,
+                                         int act, float slope, const float *msum, void *dx, float *dgamma, float *dbeta, pcb_stream_t stream) {
+    PCB_CHECK(gy && x && dx && coef && count > 0 && count <= (1 << 20) && c % 8 == 0, "pcb_bn_act_backward_small: bad arguments");
+    if (dtype == PCB_BF16) bn_bwd_small_kernel<bf16><<<c / 8, BN_SMALL_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), static_cast<int>(count), c, coef, act, slope, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
+    else bn_bwd_small_kernel<float><<<c / 8, BN_SMALL_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), static_cast<int>(count), c, coef, act, slope, msum, static_cast<float *>(dx), dgamma, dbeta);
     PCB_LAUNCH_CHECK();
     return 0;
 }

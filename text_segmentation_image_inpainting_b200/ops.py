@@ -644,6 +644,14 @@ def _vec_bn(c):
     return c % 8 == 0 and c <= 2048
 
 
+_BN_SMALL = True
+
+
+def set_bn_small_kernel(enabled: bool):
+    global _BN_SMALL
+    _BN_SMALL = bool(enabled)
+
+
 class BNActFn(torch.autograd.Function):
     """y = act(BN(x)) [+ residual]; BN optional (gamma None => plain activation).
 
@@ -725,7 +733,15 @@ class BNActFn(torch.autograd.Function):
                     sinks.append(sk); outs.append(sk.view)
                 else:
                     sinks.append(None); outs.append(torch.empty((c,), dtype=torch.float32, device=dev))
-            if _vec_bn(c):
+            small = _vec_bn(c) and _BN_SMALL and count <= 16384 and c >= 256 and scale.data_ptr() + 4 * c == shift.data_ptr() \
+                and shift.data_ptr() + 4 * c == mean.data_ptr() and mean.data_ptr() + 4 * c == invstd.data_ptr()
+            if small:
+                # the bottom of the U: one launch does reduction + apply + parameter gradients (scale|shift|mean|invstd are the
+                # four rows of the [4][c] block pcb_bn_forward_fused wrote)
+                _lib.check(lib.pcb_bn_act_backward_small(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), act, slope,
+                                                         _ptr(msum), dx.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), _stream()))
+                s0 = s1 = None
+            elif _vec_bn(c):
                 sums = zeros_f64(2 * c, dev)
                 _lib.check(lib.pcb_bn_act_backward_reduce_acc(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
                                                               mean.data_ptr(), invstd.data_ptr(), act, slope, sums.data_ptr(), _stream()))
@@ -736,7 +752,9 @@ class BNActFn(torch.autograd.Function):
                                                           mean.data_ptr(), invstd.data_ptr(), act, slope, sums[0].data_ptr(),
                                                           sums[1].data_ptr(), _stream()))
                 s0, s1 = sums[0].data_ptr(), sums[1].data_ptr()
-            if msum is not None:
+            if small:
+                pass
+            elif msum is not None:
                 _lib.check(lib.pcb_bn_act_backward_apply_renorm(gy.data_ptr(), x.data_ptr(), code, count, c, scale.data_ptr(), shift.data_ptr(),
                                                                 mean.data_ptr(), invstd.data_ptr(), act, slope, s0, s1, 1, msum.data_ptr(),
                                                                 dx.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), _stream()))
