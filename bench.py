@@ -125,53 +125,90 @@ def pick_threads():
     return best, cores
 
 
+_REF_CACHE = {}
+
+
+def _reference_module():
+    """The UNMODIFIED reference's models.image_inpainting (from /root/reference in the build container, from the staging copy
+    baseline/_ref on the GPU box -- tools/stage_reference.py), or None when neither exists."""
+    if "mod" in _REF_CACHE:
+        return _REF_CACHE["mod"]
+    _REF_CACHE["mod"] = None
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from stage_reference import reference_dir
+        ref = reference_dir()
+    except Exception:  # noqa: BLE001
+        ref = None
+    if ref is None or "models" in sys.modules:
+        return None
+    sys.path.insert(0, ref)
+    try:
+        import importlib
+        _REF_CACHE["mod"] = importlib.import_module("models.image_inpainting")
+        return _REF_CACHE["mod"]
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] importing the staged reference failed ({type(exc).__name__}: {exc}); using the oracle port", file=sys.stderr)
+        return None
+    finally:
+        sys.path.remove(ref)
+
+
 def cpu_reference_steps(steps, warmup, batch=1, seed=0):
-    """fwd + bwd + SGD of ImageFillOrigin on CPU through the oracle's functional restatement of the
-    reference (same ATen ops in the same order; pinned bit-exactly by tests/golden).  Returns
-    (images_per_sec, ms_per_step, cores)."""
-    import numpy as np
+    """fwd + bwd + SGD of ImageFillOrigin on the host cores.  kind "reference": the reference's own nn.Modules
+    (models/image_inpainting.py + models/partial_convolution.py, stock torch CPU code path, nothing of this repo on the path);
+    kind "port": the oracle's functional restatement (same ATen ops in the same order; pinned bit-exactly by tests/golden) when the
+    reference is not staged.  Returns (images_per_sec, ms_per_step, cores, kind)."""
     import torch
 
-    from oracle import pconv_torch as O                       # cpu_baseline leg: allowed importer of oracle/
-    from text_segmentation_image_inpainting_b200.models.image_inpainting import ImageFillOrigin
     from text_segmentation_image_inpainting_b200.synthetic import random_hole_masks
 
     cores, avail = pick_threads()
     torch.manual_seed(seed)
-    skeleton = ImageFillOrigin()                               # parameter names / shapes / default init only
-    sd = O.clone_state_dict(skeleton.state_dict(), requires_grad=True)
-    params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.SGD(params, lr=2e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
     x = torch.randn(batch, 3, HW, HW)
     mask = torch.from_numpy(random_hole_masks(batch, HW, HW, seed=seed))
     xin = x * mask
+    ref = _reference_module()
+    if ref is not None:
+        kind = "reference"
+        net = ref.ImageFillOrigin().train()
+        params = [p for p in net.parameters() if p.requires_grad]
+        fwd = lambda: net((xin, mask))                                 # noqa: E731
+    else:
+        kind = "port"
+        from oracle import pconv_torch as O                       # cpu_baseline leg: allowed importer of oracle/
+        from text_segmentation_image_inpainting_b200.models.image_inpainting import ImageFillOrigin
+        skeleton = ImageFillOrigin()                               # parameter names / shapes / default init only
+        sd = O.clone_state_dict(skeleton.state_dict(), requires_grad=True)
+        params = [v for v in sd.values() if v.requires_grad]
+        fwd = lambda: O.image_fill_origin(sd, xin, mask, training=True)   # noqa: E731
+    opt = torch.optim.SGD(params, lr=2e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        out = O.image_fill_origin(sd, xin, mask, training=True)
-        loss = out.abs().mean()
+        loss = fwd().abs().mean()
         loss.backward()
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return batch * len(times) / total, 1e3 * total / len(times), f"{cores} of {avail} usable"
+    return batch * len(times) / total, 1e3 * total / len(times), f"{cores} of {avail} usable", kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                               # other ranks exit 0 without work
-    ips, ms, cores = cpu_reference_steps(args.steps, args.warmup, batch=1)
+    ips, ms, cores, kind = cpu_reference_steps(args.steps, args.warmup, batch=1)
     cores_n = int(str(cores).split()[0])
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ImageFillOrigin 512x512 fwd+bwd+SGD, CPU (reference algorithm via oracle port)",
+        "config": {"workload": "ImageFillOrigin 512x512 fwd+bwd+SGD, CPU (" + ("the unmodified reference's own modules" if kind == "reference" else "reference algorithm via the oracle port") + ")",
                    "batch_per_step": 1, "note": "each step is a bounded sample (1 image) of the batch-8 workload"},
-        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores_n, "cores_note": cores, "kind": "port",
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores_n, "cores_note": cores, "kind": kind,
                          "sample": f"{args.steps} steps x 1 image @512x512 after {args.warmup} warm-up"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -367,8 +404,8 @@ def run_b200(args):
     # ---------------- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = cpu_reference_steps(steps=3, warmup=1, batch=1)
-        cpu = {"value": ips, "unit": "images/sec", "cores": int(str(cores).split()[0]), "cores_note": cores, "kind": "port",
+        ips, ms, cores, kind = cpu_reference_steps(steps=3, warmup=1, batch=1)
+        cpu = {"value": ips, "unit": "images/sec", "cores": int(str(cores).split()[0]), "cores_note": cores, "kind": kind,
                "sample": "3 steps x 1 image @512x512 (fwd+bwd+SGD) after 1 warm-up, all host threads"}
 
     if rank == 0:

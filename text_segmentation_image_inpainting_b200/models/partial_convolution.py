@@ -146,4 +146,6 @@ class DoubleUpSample(nn.Module):
 
     def forward(self, args):
         x, mask = args
-        return ops.upsample2x(x), as_hole_mask(mask).upsampled()
+        # both sides are lazy: the features become a LazyCat (a Tensor subclass the next partial convolution reads in place,
+        # also after the reference's own `torch.cat([x_up, skip], dim=1)`), the mask a HoleMask with `up` bumped
+        return ops.upsample2x_lazy(x), as_hole_mask(mask).upsampled()

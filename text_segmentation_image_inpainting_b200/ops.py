@@ -105,23 +105,86 @@ def padded_empty(n, c, h, w, dtype, device):
     return torch.empty((n, c8, h, w), dtype=dtype, device=device, memory_format=CL).zero_()[:, :c]
 
 
-class LazyCat:
-    """cat([up2x?(x_i)], dim=1) that is never materialised: a partial convolution consumes the parts directly
-    (image_inpainting.py:183-185 folded into the gather of the next layer)."""
+_LAZY_META = {"shape", "size", "dim", "ndim", "device", "dtype", "is_cuda", "requires_grad", "numel", "ndimension", "layout",
+              "is_floating_point", "__len__", "grad_fn", "is_leaf", "names", "grad", "_version", "is_sparse", "is_quantized", "is_meta",
+              "is_complex"}
+_LAZY_CAT_FUNCS = {torch.cat, getattr(torch, "concat", torch.cat), getattr(torch, "concatenate", torch.cat)}
+LAZYCAT_MATERIALIZED = 0          # how many times a LazyCat had to be turned into a dense tensor (tests assert the fast path)
 
-    def __init__(self, xs: Sequence[torch.Tensor], ups: Sequence[int]):
-        self.xs = [as_feature_padded(x) for x in xs]
-        self.ups = [int(u) for u in ups]
-        n = self.xs[0].shape[0]
-        h, w = self.xs[0].shape[2] << self.ups[0], self.xs[0].shape[3] << self.ups[0]
-        for x, u in zip(self.xs, self.ups):
-            if (x.shape[0], x.shape[2] << u, x.shape[3] << u) != (n, h, w) or x.dtype != self.xs[0].dtype:
+
+class LazyCat(torch.Tensor):
+    """cat([up2x?(x_i)], dim=1) that is never materialised: a partial convolution consumes the parts directly
+    (image_inpainting.py:183-185 folded into the operand loads of the next layer).
+
+    A ``torch.Tensor`` wrapper subclass with the logical shape / dtype / device of the concatenation, so that the REFERENCE's
+    own network files run unchanged on top of this layer library and still get the fast path:
+      * ``DoubleUpSample`` returns ``LazyCat([x], ups=(1,))`` -- a nearest-x2 view that moves no data,
+      * ``torch.cat([x_up, skip], dim=1)`` (image_inpainting.py:184) concatenates part lists,
+      * the next partial convolution reads ``.xs`` / ``.ups``,
+      * any other torch function first materialises the dense tensor (one fused upsample + concat pass, differentiable).
+    Autograd flows through the constituent tensors ``xs``; the wrapper itself is not part of the graph."""
+
+    @staticmethod
+    def __new__(cls, xs: Sequence[torch.Tensor], ups: Sequence[int]):
+        xs = [as_feature_padded(x) for x in xs]
+        ups = [int(u) for u in ups]
+        n = xs[0].shape[0]
+        h, w = xs[0].shape[2] << ups[0], xs[0].shape[3] << ups[0]
+        for x, u in zip(xs, ups):
+            if (x.shape[0], x.shape[2] << u, x.shape[3] << u) != (n, h, w) or x.dtype != xs[0].dtype:
                 raise _lib.PcbError("LazyCat: mismatched batch / spatial size / dtype")
-        self.shape = torch.Size((n, sum(x.shape[1] for x in self.xs), h, w))
-        self.dtype, self.device = self.xs[0].dtype, self.xs[0].device
+        r = torch.Tensor._make_wrapper_subclass(cls, (n, sum(x.shape[1] for x in xs), h, w), dtype=xs[0].dtype, device=xs[0].device,
+                                                requires_grad=False)
+        r.xs, r.ups = xs, ups
+        return r
 
     def materialize(self) -> torch.Tensor:
+        global LAZYCAT_MATERIALIZED
+        LAZYCAT_MATERIALIZED += 1
         return concat_features([x if nhwc_layout(x) == x.shape[1] else x.contiguous(memory_format=CL) for x in self.xs], self.ups)
+
+    def __repr__(self):  # noqa: D105
+        with torch._C.DisableTorchFunctionSubclass():
+            shp = tuple(self.shape)
+        return f"LazyCat(shape={shp}, parts={[(tuple(x.shape), u) for x, u in zip(self.xs, self.ups)]})"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, "__name__", "")
+        if name in _LAZY_META or (name == "__get__" and getattr(getattr(func, "__self__", None), "__name__", "") in _LAZY_META):
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+        if func in _LAZY_CAT_FUNCS:
+            tensors = args[0]
+            dim = kwargs.get("dim", args[1] if len(args) > 1 else 0)
+            if dim in (1, -3) and all(isinstance(t, torch.Tensor) and t.dim() == 4 for t in tensors):
+                xs, ups = [], []
+                for t in tensors:
+                    if isinstance(t, LazyCat):
+                        xs += t.xs; ups += t.ups
+                    else:
+                        xs.append(t); ups.append(0)
+                if len({x.dtype for x in xs}) == 1 and all(x.is_cuda for x in xs):
+                    return LazyCat(xs, ups)
+
+        def conv(a):
+            if isinstance(a, LazyCat):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(conv(b) for b in a)
+            return a
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*conv(args), **{k: conv(v) for k, v in kwargs.items()})
+
+    __torch_dispatch__ = None  # all handling happens at the torch-function level
+
+
+def upsample2x_lazy(x: torch.Tensor) -> "LazyCat":
+    """nearest x2 of a feature map as a LazyCat (no data movement); an already lazily-upsampled source is materialised first."""
+    if isinstance(x, LazyCat):
+        x = x.materialize()
+    return LazyCat([as_feature_padded(x)], [1])
 
 
 class ConvGeom:
