@@ -31,6 +31,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="unet", choices=["unet", "textseg", "xception"],
+                    help="unet = BASELINE configs[2]/[4] (the headline metric); textseg = configs[1]; xception = configs[3]")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="print a per-layer CUDA-event table to stderr")
@@ -154,7 +156,7 @@ def _reference_module():
         sys.path.remove(ref)
 
 
-def cpu_reference_steps(steps, warmup, batch=1, seed=0):
+def cpu_reference_steps(steps, warmup, batch=1, seed=0, workload="unet"):
     """fwd + bwd + SGD of ImageFillOrigin on the host cores.  kind "reference": the reference's own nn.Modules
     (models/image_inpainting.py + models/partial_convolution.py, stock torch CPU code path, nothing of this repo on the path);
     kind "port": the oracle's functional restatement (same ATen ops in the same order; pinned bit-exactly by tests/golden) when the
@@ -169,7 +171,26 @@ def cpu_reference_steps(steps, warmup, batch=1, seed=0):
     mask = torch.from_numpy(random_hole_masks(batch, HW, HW, seed=seed))
     xin = x * mask
     ref = _reference_module()
-    if ref is not None:
+    if workload != "unet":
+        import contextlib
+        import io
+        cls = {"textseg": "TextSegament", "xception": "XceptionTextSegment"}[workload]
+        with contextlib.redirect_stdout(io.StringIO()):
+            if ref is not None:
+                kind = "reference"
+                import importlib
+                net = getattr(importlib.import_module("models.text_segmentation"), cls)().train()
+                params = [p for p in net.parameters() if p.requires_grad]
+                fwd = lambda: net(x)                                       # noqa: E731
+            else:
+                kind = "port"
+                from oracle import seg_torch as OS                     # cpu_baseline leg: allowed importer of oracle/
+                from oracle.pconv_torch import clone_state_dict
+                from text_segmentation_image_inpainting_b200.models import text_segmentation as MT
+                sd = clone_state_dict(getattr(MT, cls)().state_dict(), requires_grad=True)
+                params = [v for v in sd.values() if v.requires_grad]
+                fwd = lambda: OS.NETWORKS[cls](sd, x)                      # noqa: E731
+    elif ref is not None:
         kind = "reference"
         net = ref.ImageFillOrigin().train()
         params = [p for p in net.parameters() if p.requires_grad]
@@ -200,14 +221,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                               # other ranks exit 0 without work
-    ips, ms, cores, kind = cpu_reference_steps(args.steps, args.warmup, batch=1)
+    ips, ms, cores, kind = cpu_reference_steps(args.steps, args.warmup, batch=1, workload=args.workload)
     cores_n = int(str(cores).split()[0])
+    W = WORKLOADS[args.workload]
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": W["metric"], "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ImageFillOrigin 512x512 fwd+bwd+SGD, CPU (" + ("the unmodified reference's own modules" if kind == "reference" else "reference algorithm via the oracle port") + ")",
-                   "batch_per_step": 1, "note": "each step is a bounded sample (1 image) of the batch-8 workload"},
+        "config": {"workload": W["label"] + " 512x512 fwd+bwd+SGD, CPU (" + ("the unmodified reference's own modules" if kind == "reference" else "reference algorithm via the oracle port") + ")",
+                   "batch_per_step": 1, "note": f"each step is a bounded sample (1 image) of the batch-{W['batch']} workload"},
         "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores_n, "cores_note": cores, "kind": kind,
                          "sample": f"{args.steps} steps x 1 image @512x512 after {args.warmup} warm-up"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,13 +241,37 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    # BASELINE.json configs[2] (and [4] under torchrun): the headline
+    "unet": {"metric": METRIC, "net": ("image_inpainting", "ImageFillOrigin"), "batch": 8, "fwd_gf": 75.94, "no_dgrad_gf": 1.23,
+             "masks": True, "label": "ImageFillOrigin (PartialConv U-Net)"},
+    # BASELINE.json configs[1]: text_segmentation.py MobileNetV2 encoder-decoder @512x512 batch 8
+    "textseg": {"metric": "TextSegament (MobileNetV2+RFB) 512x512 images/sec (fwd+bwd)", "net": ("text_segmentation", "TextSegament"),
+                "batch": 8, "fwd_gf": 90.67, "no_dgrad_gf": 0.0, "masks": False, "label": "TextSegament (DilatedMobileNetV2 x2 + RFB)"},
+    # BASELINE.json configs[3]: Xception + atrous / ASP segmentation @512x512 batch 16 bf16
+    "xception": {"metric": "XceptionTextSegment 512x512 images/sec (fwd+bwd)", "net": ("text_segmentation", "XceptionTextSegment"),
+                 "batch": 16, "fwd_gf": 148.70, "no_dgrad_gf": 0.0, "masks": False, "label": "XceptionTextSegment (Xception + ASP)"},
+}
+KERNEL_OF = {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ smallco_fwd / pconv_tc_persistent_kernel for tail / stem)",
+             "tc_dgrad": "pconv_tc_tma_kernel<MODE=1> (+ smallco_dgrad for the tail)",
+             "tc_wgrad": "pconv_tc_wgrad_tma_kernel (+ smallco_wgrad / pconv_tc_wgrad_kernel for tail / stem)",
+             "dw_fwd": "dw_fwd_kernel (dwconv.cu)", "dw_dgrad": "dw_dgrad_kernel (dwconv.cu)", "dw_wgrad": "dw_wgrad_kernel (dwconv.cu)"}
+
+
 def conv_flops(g):
     return 2.0 * g.n * g.ho * g.wo * g.cout * (g.cin // g.groups) * g.kh * g.kw
 
 
+def conv_bytes(kind, g):
+    """ALGORITHMIC HBM bytes of a depthwise launch: one read of each input + one write of each output at the
+    storage dtype; weights / the fp32 weight gradient are negligible."""
+    xin, yout = g.n * g.cin * g.h * g.w * g.esz, g.n * g.cout * g.ho * g.wo * g.esz
+    return float(xin + yout)          # fwd: read x, write y | dgrad: read dc, write dx | wgrad: read x, read dc
+
+
 def layer_profile(ts, x, mask, peaks, verbose):
     """One instrumented EAGER step: CUDA events around every conv launch on the launching stream.
-    Returns the roofline dict of the dominant kernel family."""
+    Returns (roofline dict of the dominant family, per-family [work, ms, launches], per-family rooflines)."""
     import torch
     from text_segmentation_image_inpainting_b200 import _lib, ops
 
@@ -239,48 +285,61 @@ def layer_profile(ts, x, mask, peaks, verbose):
     for kind, g, s, e in rec:
         ms = s.elapsed_time(e)
         c = g.struct(None)
+        dw = g.groups > 1 and g.groups == g.cin and g.cout == g.cin
         tc = bool(_lib.load().pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)))
-        key = ("tc_" if tc else "generic_") + kind
+        key = ("dw_" if dw else ("tc_" if tc else "generic_")) + kind
+        work = conv_bytes(kind, g) if dw else conv_flops(g)
         f = fam.setdefault(key, [0.0, 0.0, 0])
-        f[0] += conv_flops(g); f[1] += ms; f[2] += 1
-        rows.append((key, f"{g.cin}->{g.cout} k{g.kh} s{g.stride} @{g.h}x{g.w}", conv_flops(g) / 1e9, ms))
+        f[0] += work; f[1] += ms; f[2] += 1
+        rows.append((key, f"{g.cin}->{g.cout} k{g.kh} s{g.stride} d{g.dil} g{g.groups} @{g.h}x{g.w}", work / 1e9, ms))
     if verbose:
         for r in rows:
-            print(f"  {r[0]:14s} {r[1]:28s} {r[2]:8.1f} GF {r[3]:8.3f} ms {r[2] / max(r[3], 1e-9):8.1f} TF/s", file=sys.stderr)
+            unit = "GB" if r[0].startswith("dw_") else "GF"
+            print(f"  {r[0]:14s} {r[1]:36s} {r[2]:8.2f} {unit} {r[3]:8.3f} ms {r[2] / max(r[3], 1e-9):8.1f} T{unit[1]}/s", file=sys.stderr)
         for k, (fl, ms, n) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
-            print(f"  == {k:14s} launches={n:3d} {fl / 1e9:9.1f} GF {ms:8.3f} ms {fl / 1e9 / max(ms, 1e-9):8.1f} TF/s", file=sys.stderr)
-    tcf = {k: v for k, v in fam.items() if k.startswith("tc_")}
-    if not tcf:
-        return None, fam
-    dom = max(tcf.items(), key=lambda kv: kv[1][1])
-    fl, ms, n = dom[1]
-    achieved = fl / (ms * 1e-3) / 1e12
-    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+            print(f"  == {k:14s} launches={n:3d} {fl / 1e9:9.1f} G {ms:8.3f} ms {fl / 1e9 / max(ms, 1e-9):8.1f} T/s", file=sys.stderr)
+    peak_t = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_b = peaks.get("hbm_gbs") or 6500.0
+    roofs = {}
+    for k, (work, ms, n) in fam.items():
+        if k.startswith("tc_"):
+            ach = work / (ms * 1e-3) / 1e12
+            roofs[k] = {"bound": "tensor", "kernel": KERNEL_OF.get(k, k), "achieved": ach, "peak": peak_t, "unit": "TFLOP/s", "frac": ach / peak_t,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",
+                        "launches_per_step": n, "flops_per_step": work, "ms_per_step_in_kernel": ms}
+        elif k.startswith("dw_"):
+            ach = work / (ms * 1e-3) / 1e9
+            roofs[k] = {"bound": "hbm", "kernel": KERNEL_OF.get(k, k), "achieved": ach, "peak": peak_b, "unit": "GB/s", "frac": ach / peak_b,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
+                        "launches_per_step": n, "bytes_per_step": work, "ms_per_step_in_kernel": ms}
+    if not roofs:
+        return None, fam, roofs
+    dom = max(roofs.items(), key=lambda kv: kv[1]["ms_per_step_in_kernel"])
+    roof = dict(dom[1])
     # DRAM bytes per launch of that family from the committed `ncu --set full` capture of one step (profiles/README.md)
-    traffic = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic_final.json")))[dom[0]]
-        traffic = t["dram_bytes"] / max(t["launches"], 1)
-    except Exception:  # noqa: BLE001
-        pass
-    return {"bound": "tensor", "kernel": {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ smallco_fwd / pconv_tc_persistent_kernel for tail / stem)",
-                                          "tc_dgrad": "pconv_tc_tma_kernel<MODE=1> (+ smallco_dgrad for the tail)",
-                                          "tc_wgrad": "pconv_tc_wgrad_tma_kernel (+ smallco_wgrad / pconv_tc_wgrad_kernel for tail / stem)"}[dom[0]],
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",
-            "launches_per_step": n, "flops_per_step": fl, "ms_per_step_in_kernel": ms, "traffic": traffic,
-            "traffic_note": "mean dram__bytes_read+write per TMA-path launch of the family, ncu --set full of one step"}, fam
+    roof["traffic"] = None
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic_final.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))[dom[0]]
+            roof["traffic"] = t["dram_bytes"] / max(t["launches"], 1)
+            roof["traffic_note"] = f"mean dram__bytes_read+write per launch of the family, ncu --set full of one step (profiles/{name})"
+            break
+        except Exception:  # noqa: BLE001
+            pass
+    return roof, fam, roofs
 
 
 def run_b200(args):
+    import importlib
+
     import torch
     import torch.distributed as dist
 
     from text_segmentation_image_inpainting_b200 import _lib
-    from text_segmentation_image_inpainting_b200.engine import TrainStep
-    from text_segmentation_image_inpainting_b200.models.image_inpainting import ImageFillOrigin
+    from text_segmentation_image_inpainting_b200.engine import SegTrainStep, TrainStep
     from text_segmentation_image_inpainting_b200.synthetic import random_hole_masks
 
+    W = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -300,18 +359,23 @@ def run_b200(args):
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
     torch.manual_seed(0)                                        # identical initial weights on every rank
-    net = ImageFillOrigin().to(dev)
-    ts = TrainStep(net, compute_dtype=torch.bfloat16, process_group=pg, use_graph=not args.no_graph)
+    mod = importlib.import_module("text_segmentation_image_inpainting_b200.models." + W["net"][0])
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):             # the reference's constructors print ("No check point ...")
+        net = getattr(mod, W["net"][1])().to(dev)
+    Step = TrainStep if W["masks"] else SegTrainStep
+    ts = Step(net, compute_dtype=torch.bfloat16, process_group=pg, use_graph=not args.no_graph)
 
-    # synthetic inputs: x ~ N(0,1), free-form line/ellipse holes, one plane per image x3 channels
-    B = PER_GPU_BATCH
+    # synthetic inputs: x ~ N(0,1); inpainting: free-form line/ellipse holes, one plane per image x3 channels
+    B = W["batch"]
     g = torch.Generator().manual_seed(1234 + rank)
     NBUF = 2
     host_x = [torch.randn(B, 3, HW, HW, generator=g).pin_memory() for _ in range(NBUF)]
-    host_m = [torch.from_numpy(random_hole_masks(B, HW, HW, seed=100 * rank + i)).pin_memory() for i in range(NBUF)]
+    host_m = [torch.from_numpy(random_hole_masks(B, HW, HW, seed=100 * rank + i)).pin_memory() for i in range(NBUF)] if W["masks"] else None
     dev_x = [t.to(dev) for t in host_x]
-    dev_m = [t.to(dev) for t in host_m]
-    h2d_bytes = host_x[0].numel() * 4 + host_m[0].numel() * 4
+    dev_m = [t.to(dev) for t in host_m] if host_m else [None] * NBUF
+    h2d_bytes = host_x[0].numel() * 4 + (host_m[0].numel() * 4 if host_m else 0)
 
     note("inputs ready; eager warm-up + graph capture")
     ts.warmup_and_capture(dev_x[0], dev_m[0], eager_warmup=2)
@@ -334,8 +398,8 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident timing: inputs already in HBM (two 50 MB input sets alternate; the
-    # step's working set (~3 GB of activations) is far larger than L2, so no explicit flush is needed)
+    # ---------------- device-resident timing: inputs already in HBM (two input sets alternate; the step's working set
+    # (GBs of activations) is far larger than L2, so no explicit flush is needed)
     for i in range(args.warmup):
         ts.step(dev_x[i % NBUF], dev_m[i % NBUF])
     clocks = Clocks(local)
@@ -358,7 +422,7 @@ def run_b200(args):
     # compute -> step -> D2H of the loss, every step inside the timed region
     copy_stream = torch.cuda.Stream()
     stage_x = [torch.empty_like(dev_x[0]) for _ in range(2)]
-    stage_m = [torch.empty_like(dev_m[0]) for _ in range(2)]
+    stage_m = [torch.empty_like(dev_m[0]) if host_m else None for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -368,7 +432,8 @@ def run_b200(args):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[b])
             stage_x[b].copy_(host_x[i % NBUF], non_blocking=True)
-            stage_m[b].copy_(host_m[i % NBUF], non_blocking=True)
+            if host_m:
+                stage_m[b].copy_(host_m[i % NBUF], non_blocking=True)
             ready[b].record(copy_stream)
 
     def e2e_run(nsteps):
@@ -396,27 +461,28 @@ def run_b200(args):
     note("end-to-end done")
 
     # ---------------- per-kernel roofline (rank 0): eager instrumented step, events on the launching stream
-    roof, fam = (None, {})
+    roof, fam, roofs = (None, {}, {})
     if rank == 0:
-        roof, fam = layer_profile(ts, dev_x[0], dev_m[0], peaks, args.profile_layers)
+        roof, fam, roofs = layer_profile(ts, dev_x[0], dev_m[0], peaks, args.profile_layers)
     barrier()
 
     # ---------------- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores, kind = cpu_reference_steps(steps=3, warmup=1, batch=1)
+        ips, ms, cores, kind = cpu_reference_steps(steps=3, warmup=1, batch=1, workload=args.workload)
         cpu = {"value": ips, "unit": "images/sec", "cores": int(str(cores).split()[0]), "cores_note": cores, "kind": kind,
                "sample": "3 steps x 1 image @512x512 (fwd+bwd+SGD) after 1 warm-up, all host threads"}
 
     if rank == 0:
-        step_flop = (3 * FWD_GFLOP_PER_IMAGE - 1.23) * 1e9 * B          # fwd+bwd, minus the stem dgrad
+        step_flop = (3 * W["fwd_gf"] - W["no_dgrad_gf"]) * 1e9 * B          # fwd+bwd (minus the stem dgrad)
         line = {
-            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": W["metric"], "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ImageFillOrigin (PartialConv U-Net) 512x512, batch 8 per GPU, fwd+bwd+SGD(nesterov), train-mode BN",
+            "config": {"workload": f"{W['label']} 512x512, batch {B} per GPU, fwd+bwd+SGD(nesterov), train-mode BN",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": ts.graph is not None,
-                       "l2": "inputs+activations per step (~3 GB) exceed the 126 MB L2; no explicit flush",
+                       "allreduce": ("overlapped with backward (captured)" if ts.overlap_active else "after backward") if world > 1 else "none",
+                       "l2": "inputs+activations per step (GBs) exceed the 126 MB L2; no explicit flush",
                        "loss": "out.abs().mean()", "algorithmic_tflop_per_step_per_gpu": step_flop / 1e12},
             "step_tflops_per_gpu": step_flop / 1e12 / (ms_total / args.steps * 1e-3),
             "clocks": clk,
@@ -424,6 +490,9 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": ts.launches_per_step * args.steps,
             "roofline": roof,
+            # every conv family of the step (the dominant one above flips between tc_fwd and tc_wgrad run to run: report all)
+            "rooflines": {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "launches_per_step", "ms_per_step_in_kernel")}
+                          for k, v in sorted(roofs.items())},
             "kernel_families_ms": {k: round(v[1], 4) for k, v in fam.items()},
             "cpu_baseline": cpu,
         }

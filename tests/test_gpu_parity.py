@@ -159,16 +159,55 @@ def test_bn_statistics_fused_into_conv_epilogue(shape, dev):
         assert relerr(a, b) <= 2e-2, relerr(a, b)
     # the statistics themselves are sums of the same bf16-rounded values: only the summation order differs
     assert relerr(res[True][2], res[False][2]) <= 1e-5 and relerr(res[True][3], res[False][3]) <= 1e-4
-    # oracle on the same bf16-rounded operands
-    wq = sd["0.feature_conv.weight"].to(BF).float()
-    xo, wo = x.float().clone().requires_grad_(True), wq.clone().requires_grad_(True)
-    yo, _ = O.partial_conv(xo, mask, wo, None, s, p, 1, 1, True)
-    bn = torch.nn.BatchNorm2d(cout)
-    bn.load_state_dict({kk[len("1.bn_act.0."):]: v for kk, v in sd.items() if kk.startswith("1.bn_act.0.")})
-    zo = torch.nn.functional.leaky_relu(bn(yo), 0.2)
-    (zo * gy.float()).sum().backward()
-    assert relerr(res[True][0], zo) <= 3e-2 and relerr(res[True][2], bn.running_mean) <= 1e-2 and relerr(res[True][3], bn.running_var) <= 1e-2
-    assert relerr(res[True][5], wo.grad) <= 3e-2
+    # the oracle under the same storage precision (conv output and BN+activation output rounded to bf16, like the two kernels
+    # store them): reference semantics of the whole block, partial_convolution.py:49-80 + :193-201
+    sdo = O.clone_state_dict(sd, requires_grad=True)
+    xo = x.float().clone().requires_grad_(True)
+    with O.storage(BF):
+        zo, _ = O.pconv_block(sdo, "", xo, mask, k=k, s=s, p=p, bn=True, act=("leaky", 0.2), same_holes=True, training=True)
+        (zo * gy.float()).sum().backward()
+    assert relerr(res[True][0], zo) <= 2e-2, relerr(res[True][0], zo)
+    assert relerr(res[True][2], sdo["1.bn_act.0.running_mean"]) <= 1e-2 and relerr(res[True][3], sdo["1.bn_act.0.running_var"]) <= 1e-2
+    assert relerr(res[True][5], sdo["0.feature_conv.weight"].grad) <= 3e-2 and relerr(res[True][1], xo.grad) <= 3e-2
+
+
+@pytest.mark.parametrize("dtype", [F32, BF], ids=["f32", "bf16"])
+def test_general_per_channel_masks_beyond_part_table(dtype, dev):
+    """partial_convolution.py:62-64 accepts ANY [N,C,H,W] mask.  12 genuinely different mask planes (more than PCB_MAX_PARTS = 8)
+    into a dense PartialConv, then a 16-group non-same_holes conv whose 16-plane output mask feeds a third layer: the general
+    dense-mask route must reproduce the oracle (masks bit-exact)."""
+    from gpu_cases import blob
+    from oracle.detfill import det_fill_state_dict, det_tensor
+    from text_segmentation_image_inpainting_b200.models import partial_convolution as PC
+    n, h, w = 2, 20, 24
+    mods = [PC.PartialConv(12, 32, 3, 1, 1, 1, 1, True, False), PC.PartialConv(32, 32, 3, 1, 1, 1, 16, False, False),
+            PC.PartialConv(32, 8, 3, 2, 1, 1, 1, True, False)]
+    sds = [det_fill_state_dict(m.state_dict()) for m in mods]
+    x = det_tensor("pcm.x", (n, 12, h, w)).to(dtype).float()
+    mask = blob(n, 12, h, w, 17, per_channel=True)
+    assert len({mask[0, c].numpy().tobytes() for c in range(12)}) > 8
+    xo = x.clone().requires_grad_(True)
+    ws = [sd["feature_conv.weight"].to(dtype).float().requires_grad_(True) for sd in sds]
+    yo, mo = xo, mask
+    for sd, wq, (s_, g_) in zip(sds, ws, ((1, 1), (1, 16), (2, 1))):
+        yo, mo = O.partial_conv(yo, mo.contiguous(), wq, sd.get("feature_conv.bias"), s_, 1, 1, g_, False)
+    gy = det_tensor("pcm.gy", tuple(yo.shape)).to(dtype).float()
+    (yo * gy).sum().backward()
+    yd = x.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xd, md = yd, mask.to(dev)
+    for m, sd, wq in zip(mods, sds, ws):
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            m.feature_conv.weight.copy_(wq.detach())
+        m.to(dev)
+        yd, md = m((yd, md))
+    yd.backward(gy.to(dev).to(dtype))
+    torch.cuda.synchronize()
+    tol = 1e-4 if dtype == F32 else 3e-2
+    assert torch.equal(md.dense().cpu(), mo.contiguous())
+    assert relerr(yd, yo) <= tol and relerr(xd.grad, xo.grad) <= tol
+    for m, wq in zip(mods, ws):
+        assert relerr(m.feature_conv.weight.grad, wq.grad) <= tol
 
 
 def test_concat_upsample_and_masks(dev):

@@ -770,6 +770,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     // inside an elect.sync region.  Written as `if (lane == 0) { whole loop }` the compiler treats every such instruction as
     // possibly divergent, wraps each in an ELECT/branch loop and keeps its operands in vector registers (R2UR per use):
     // ~8 dependent uniform-datapath instructions = ~60 cycles per tcgen05.mma, more than the N<=128 MMA itself takes.
+    float *s_stat = nullptr;                                          // epilogue warps: private BatchNorm-statistics accumulators
+    int stat_n0 = -1;                                                  // N tile they currently belong to (-1: none / aborted)
     if (warp == 0) {
         // ================================ TMA producer ================================
         int s = 0;
@@ -1071,9 +1073,8 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         // ================================ epilogue warps (6-9) ================================
         int tile_iter = 0;
         // fused BatchNorm statistics (see pconv_tc_persistent_kernel)
-        float *s_stat = (MODE == 0 && P.bn_sums != nullptr && P.partial == nullptr)
-                            ? reinterpret_cast<float *>(smem_gen + (((s_tmem_ptr + 32u) & ~15u) - smem_base)) + (warp & 3) * STAT_FLOATS_PER_WARP : nullptr;
-        int stat_n0 = -1;
+        s_stat = (MODE == 0 && P.bn_sums != nullptr && P.partial == nullptr)
+                     ? reinterpret_cast<float *>(smem_gen + (((s_tmem_ptr + 32u) & ~15u) - smem_base)) + (warp & 3) * STAT_FLOATS_PER_WARP : nullptr;
         if (s_stat) {
             for (int i = lane; i < STAT_FLOATS_PER_WARP; i += 32) s_stat[i] = 0.f;
             __syncwarp();
@@ -1094,11 +1095,25 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             else ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
             ++tile_iter;
         }
-        if (s_stat && stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    // last N tile's BatchNorm statistics: the four epilogue warps' partials are summed here, after the CTA-wide barrier, so the
+    // global sums receive ONE atomic per channel per CTA (148 per address instead of 592)
+    if (s_stat != nullptr && stat_n0 >= 0) {
+        const float *base = s_stat - (warp & 3) * STAT_FLOATS_PER_WARP;
+        for (int col = (warp & 3) * 32 + lane; col < BLOCK_N; col += 128) {
+            const int co = stat_n0 + col;
+            if (co < P.bn_c) {
+                float a = 0.f, q = 0.f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) { a += base[w4 * STAT_FLOATS_PER_WARP + col]; q += base[w4 * STAT_FLOATS_PER_WARP + 256 + col]; }
+                atomicAdd(P.bn_sums + co, static_cast<double>(a));
+                atomicAdd(P.bn_sums + P.bn_c + co, static_cast<double>(q));
+            }
+        }
+    }
     if (PAIR) ptx::cluster_sync();                                     // no CTA leaves while its partner may still touch its smem / TMEM
     if (warp == 1) {
         ptx::tc_fence_after();

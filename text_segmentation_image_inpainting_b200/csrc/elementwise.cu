@@ -7,9 +7,19 @@ namespace {
 
 constexpr int EW_THREADS = 256;
 
-inline int ew_grid(long long work_items, int per_block) {
+// activation as a template parameter of the hot kernels: the per-element switch on a runtime code was a third of their
+// instruction count (they are issue-bound before they are bandwidth-bound)
+#define PCB_ACT_SWITCH(act_code, ...)                                                  \
+    switch (act_code) {                                                                \
+        case PCB_ACT_RELU: { constexpr int ACT = PCB_ACT_RELU; __VA_ARGS__; } break;   \
+        case PCB_ACT_LEAKY: { constexpr int ACT = PCB_ACT_LEAKY; __VA_ARGS__; } break; \
+        case PCB_ACT_RELU6: { constexpr int ACT = PCB_ACT_RELU6; __VA_ARGS__; } break; \
+        default: { constexpr int ACT = PCB_ACT_NONE; __VA_ARGS__; } break;             \
+    }
+
+inline int ew_grid(long long work_items, int per_block, int blocks_per_sm = 16) {
     long long b = (work_items + per_block - 1) / per_block;
-    const long long cap = 16ll * pcb_num_sms();
+    const long long cap = static_cast<long long>(blocks_per_sm) * pcb_num_sms();
     return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -17,7 +27,7 @@ inline int ew_grid(long long work_items, int per_block) {
 // blocks would serialise thousands of atomics on the same c addresses
 inline int ew_grid_red(long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
-    const long long cap = 8ll * pcb_num_sms();
+    const long long cap = 3ll * pcb_num_sms();                  // launch bounds (256, 3): exactly one resident wave
     return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -27,25 +37,27 @@ inline int ew_grid_red(long long work_items, int per_block) {
 // F(row, v, vals...) is evaluated per 8-vector; NRED fp32 partials per channel are block-reduced through
 // shared memory and flushed with fp64 atomics.
 // ---------------------------------------------------------------------------------------------
+// All NRED partial sets are staged in shared memory at once and the cv*8 channel columns are summed by cv*8 threads in
+// parallel (the first version let only the cv threads of row 0 walk all rows serially, twice: ~4 us of tail per block -- as
+// long as the block's whole streaming phase).
 template <int NRED>
 __device__ __forceinline__ void block_flush(float (&acc)[NRED][8], int cv, int rpb, int r, int v, double *const (&out)[NRED]) {
-    __shared__ float s_red[EW_THREADS][8];
-    for (int q = 0; q < NRED; ++q) {
-        __syncthreads();
-        if (r < rpb) {
+    __shared__ float s_red[NRED][EW_THREADS][8];
+    if (r < rpb) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s_red[threadIdx.x][j] = acc[q][j];
-        }
-        __syncthreads();
-        if (r == 0 && v < cv) {
-            float tot[8];
+        for (int q = 0; q < NRED; ++q)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tot[j] = 0.f;
-            for (int rr = 0; rr < rpb; ++rr)
+            for (int j = 0; j < 8; ++j) s_red[q][threadIdx.x][j] = acc[q][j];
+    }
+    __syncthreads();
+    const int ncol = cv * 8;                                     // = c, at most 2048
+    for (int col = threadIdx.x; col < ncol; col += EW_THREADS) {
+        const int vv = col >> 3, jj = col & 7;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tot[j] += s_red[rr * cv + v][j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(out[q] + v * 8 + j, static_cast<double>(tot[j]));
+        for (int q = 0; q < NRED; ++q) {
+            float tot = 0.f;
+            for (int rr = 0; rr < rpb; ++rr) tot += s_red[q][rr * cv + vv][jj];
+            atomicAdd(out[q] + col, static_cast<double>(tot));
         }
     }
 }
@@ -154,7 +166,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const T *__restr
 // 8 channels from the complete fp64 sums (produced by the convolution epilogue or pcb_bn_stats_acc), block 0 additionally
 // updates the running statistics and writes the per-channel coefficients the backward needs.
 //   coef: [4][c] floats = scale (gamma * invstd) | shift (beta - mean * scale) | mean | invstd
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(EW_THREADS) bn_fwd_fused_kernel(const T *__restrict__ x, long long count, int c, const double *__restrict__ sums,
                                                                   const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                   float *running_mean, float *running_var, long long *nbt, float momentum, float eps,
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_fwd_fused_kernel(const T *__res
         if (residual) Vec8<T>::load(residual + row * c + v * 8, rres);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float z = apply_act(f[j] * sc[j] + sh[j], act, slope);
+            float z = apply_act(f[j] * sc[j] + sh[j], ACT, slope);
             if (residual) z += rres[j];
             f[j] = z;
         }
@@ -218,7 +230,7 @@ __global__ void bn_act_fwd_scalar_kernel(const T *x, long long numel, int c, con
 
 // sum_g = sum gz, sum_gx = sum gz * xhat with gz = gy * act'(BN(x)), xhat = (x - mean) * invstd.  The loop accumulates
 // gz * (x - mean) and multiplies by invstd once at the end: three coefficient vectors live in registers instead of four.
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_reduce_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
                                                                       const float *__restrict__ scale, const float *__restrict__ shift,
                                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_reduce_kernel(const T *_
             Vec8<T>::load(px + row * c, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+                const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], ACT, slope);
                 acc[0][j] += gz;
                 acc[1][j] += gz * (f[j] - mu[j]);
             }
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_reduce_kernel(const T *_
 
 // dx = scale * (gz - sum_g/count - xhat * sum_gx/count) [* 1/mask_sum] written as  A*gz + B*(x - mean) + C  with per-channel
 // A = scale, B = -scale*invstd*sum_gx/count, C = -scale*sum_g/count: five coefficient vectors in registers.
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_apply_kernel(const T *__restrict__ gy, const T *__restrict__ x, long long count, int c,
                                                                      const float *__restrict__ scale, const float *__restrict__ shift,
                                                                      const float *__restrict__ mean, const float *__restrict__ invstd, int act,
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_apply_kernel(const T *__
         const float rs = (s == 0.f) ? 0.f : __frcp_rn(s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], ACT, slope);
             const float d = (ca != 0.f) ? fmaf(sc[j], gz, fmaf(cb[j], f[j] - mu[j], cc[j])) : gz;
             f[j] = renorm ? d * rs : d;
         }
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_apply_kernel(const T *__
 // rows twice (the second pass hits L2), so no grid-wide dependency exists: the whole BatchNorm backward of such a layer is one
 // kernel instead of memset + reduce + apply + parameter-gradient.
 constexpr int BN_SMALL_THREADS = 1024;
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(BN_SMALL_THREADS) bn_bwd_small_kernel(const T *__restrict__ gy, const T *__restrict__ x, int count, int c,
                                                                         const float *__restrict__ coef /* [4][c] scale|shift|mean|invstd */,
                                                                         int act, float slope, const float *__restrict__ msum, T *__restrict__ dx,
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(BN_SMALL_THREADS) bn_bwd_small_kernel(const T 
         Vec8<T>::load(px + static_cast<long long>(row) * c, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], ACT, slope);
             acc[j] += gz;
             acc[8 + j] += gz * (f[j] - mu[j]);
         }
@@ -376,7 +388,7 @@ __global__ void __launch_bounds__(BN_SMALL_THREADS) bn_bwd_small_kernel(const T 
         const float rs = (s == 0.f) ? 0.f : __frcp_rn(s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], act, slope);
+            const float gz = g[j] * act_grad(f[j] * sc[j] + sh[j], ACT, slope);
             const float d = fmaf(sc[j], gz, fmaf(cb[j], f[j] - mu[j], cc[j]));
             f[j] = renorm ? d * rs : d;
         }
@@ -727,9 +739,10 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_forward_fused(const
                                     pcb_stream_t stream) {
     PCB_CHECK(x && y && sums && coef && count > 0 && c > 0 && c % 8 == 0 && c <= 2048, "pcb_bn_forward_fused: bad arguments (c must be a multiple of 8, <= 2048)");
     PCB_CHECK((running_mean == nullptr) == (running_var == nullptr), "pcb_bn_forward_fused: running statistics come in pairs");
-    const int grid = ew_grid(count, (EW_THREADS / (c / 8)) * 4);
-    if (dtype == PCB_BF16) bn_fwd_fused_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y), coef);
-    else bn_fwd_fused_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const float *>(residual), static_cast<float *>(y), coef);
+    const int grid = ew_grid(count, (EW_THREADS / (c / 8)) * 4, 8);       // the per-thread coefficient prologue is amortised over >= 16 rows
+    PCB_ACT_SWITCH(act,
+        if (dtype == PCB_BF16) bn_fwd_fused_kernel<bf16, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y), coef);
+        else bn_fwd_fused_kernel<float, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const float *>(residual), static_cast<float *>(y), coef))
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -779,8 +792,9 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
     }
     const int rpb = EW_THREADS / (c / 8);
     const int grid = ew_grid_red(count, rpb * 16);
-    if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
-    else bn_bwd_reduce_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
+    PCB_ACT_SWITCH(act,
+        if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx);
+        else bn_bwd_reduce_kernel<float, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx))
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -792,8 +806,9 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
     PCB_CHECK(gy && x && sums && count > 0 && c % 8 == 0 && c <= 2048, "pcb_bn_act_backward_reduce_acc: bad arguments (c must be a multiple of 8, <= 2048)");
     const int rpb = EW_THREADS / (c / 8);
     const int grid = ew_grid_red(count, rpb * 8);
-    if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
-    else bn_bwd_reduce_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
+    PCB_ACT_SWITCH(act,
+        if (dtype == PCB_BF16) bn_bwd_reduce_kernel<bf16, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c);
+        else bn_bwd_reduce_kernel<float, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sums, sums + c))
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -804,8 +819,9 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_reduce
 extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_small(const void *gy, const void *x, int dtype, long long count, int c, const float *coef,
                                          int act, float slope, const float *msum, void *dx, float *dgamma, float *dbeta, pcb_stream_t stream) {
     PCB_CHECK(gy && x && dx && coef && count > 0 && count <= (1 << 20) && c % 8 == 0, "pcb_bn_act_backward_small: bad arguments");
-    if (dtype == PCB_BF16) bn_bwd_small_kernel<bf16><<<c / 8, BN_SMALL_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), static_cast<int>(count), c, coef, act, slope, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
-    else bn_bwd_small_kernel<float><<<c / 8, BN_SMALL_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), static_cast<int>(count), c, coef, act, slope, msum, static_cast<float *>(dx), dgamma, dbeta);
+    PCB_ACT_SWITCH(act,
+        if (dtype == PCB_BF16) bn_bwd_small_kernel<bf16, ACT><<<c / 8, BN_SMALL_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), static_cast<int>(count), c, coef, act, slope, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
+        else bn_bwd_small_kernel<float, ACT><<<c / 8, BN_SMALL_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), static_cast<int>(count), c, coef, act, slope, msum, static_cast<float *>(dx), dgamma, dbeta))
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -818,7 +834,7 @@ static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, 
     PCB_CHECK(!msum || (c % 8 == 0 && c <= 2048), "pcb_bn_act_backward_apply_renorm: channel count must be a multiple of 8 (<= 2048)");
     PCB_CHECK(!(scale && training) || (mean && invstd && sum_g && sum_gx), "pcb_bn_act_backward_apply: training needs statistics");
     const bool vec = c % 8 == 0 && c <= 2048;
-    const int grid = vec ? ew_grid(count, (EW_THREADS / (c / 8)) * 4) : ew_grid(count * c, EW_THREADS * 4);
+    const int grid = vec ? ew_grid(count, (EW_THREADS / (c / 8)) * 4, 6) : ew_grid(count * c, EW_THREADS * 4);
     if (!vec) {
         if (dtype == PCB_BF16) bn_bwd_apply_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
         else bn_bwd_apply_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
@@ -830,8 +846,9 @@ static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, 
         return 0;
     }
     // vector path: block 0 also writes the parameter gradients (dgamma = sum gz*xhat, dbeta = sum gz) -- no extra launch
-    if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
-    else bn_bwd_apply_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx), dgamma, dbeta);
+    PCB_ACT_SWITCH(act,
+        if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
+        else bn_bwd_apply_kernel<float, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx), dgamma, dbeta))
     PCB_LAUNCH_CHECK();
     return 0;
 }

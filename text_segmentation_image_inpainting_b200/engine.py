@@ -217,9 +217,7 @@ class TrainStep:
         self._arm_overlap(overlap)
         try:
             ops.prefetch_weights(self._wcaches)        # operand re-layout of all layers runs ahead on its own stream
-            xin, hm = self._prepare(x, mask)
-            out = self.net((xin, hm))
-            loss = ops.l1_mean(out)
+            loss = self._forward_loss(x, mask)
             loss.backward()
         finally:
             ops.set_mask_chain_stream(False)
@@ -229,6 +227,11 @@ class TrainStep:
             if overlap:
                 self._finish_overlap()
         return loss.detach()
+
+    def _forward_loss(self, x, mask):
+        """Forward + scalar loss of one step (SURVEY 8d benchmark loss: out.abs().mean())."""
+        xin, hm = self._prepare(x, mask)
+        return ops.l1_mean(self.net((xin, hm)))
 
     def _update(self, first_step: bool):
         ops.sgd_step(self.flat.flat_p, self.flat.flat_g, self.flat.flat_m, self.lr, self.momentum, self.wd, self.nesterov,
@@ -243,7 +246,7 @@ class TrainStep:
         return loss
 
     # -- public -------------------------------------------------------------------------------------
-    def warmup_and_capture(self, x: torch.Tensor, mask: torch.Tensor, eager_warmup=2):
+    def warmup_and_capture(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, eager_warmup=2):
         """Run eager warm-up steps (also counts this library's launches per step), then capture the step."""
         for _ in range(eager_warmup):
             before = _lib.launch_count()
@@ -255,7 +258,7 @@ class TrainStep:
         if not self.use_graph:
             return
         self.static_x = x.clone()
-        self.static_m = mask.clone()
+        self.static_m = mask.clone() if mask is not None else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -296,12 +299,12 @@ class TrainStep:
         self._captured_operands = [c.get("val") for c in self._wcaches]
         torch.cuda.synchronize()
 
-    def step(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    def step(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x, mask already on the device.  Returns the (device) loss of this step."""
         if self.graph is not None:
             if x.data_ptr() != self.static_x.data_ptr():
                 self.static_x.copy_(x, non_blocking=True)
-            if mask.data_ptr() != self.static_m.data_ptr():
+            if mask is not None and mask.data_ptr() != self.static_m.data_ptr():
                 self.static_m.copy_(mask, non_blocking=True)
             self.graph.replay()
             if self.graph_update is not None:
@@ -311,3 +314,15 @@ class TrainStep:
         loss = self._step(x, mask, self.first)
         self.first = False
         return loss
+
+
+class SegTrainStep(TrainStep):
+    """The same step for the dense segmentation networks (models/text_segmentation.py: `net(x)`, no masks): BASELINE.json
+    configs[1] (TextSegament, batch 8) and configs[3] (XceptionTextSegment, batch 16, bf16).  `mask` is ignored."""
+
+    def _forward_loss(self, x, mask=None):
+        n, c, h, w = x.shape
+        buf = torch.empty((n, (c + 7) // 8 * 8, h, w), dtype=self.dtype, device=x.device, memory_format=CL).zero_()
+        xin = buf[:, :c]
+        xin.copy_(x)
+        return ops.l1_mean(self.net(xin))

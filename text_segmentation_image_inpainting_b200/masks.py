@@ -67,13 +67,12 @@ class HoleMask(torch.Tensor):
             return HoleMask([(plane[0], c, 0)], n, h, w)
         planes = torch.empty((c, n, h, w), dtype=torch.uint8, device=mask.device)
         _lib.check(_lib.load().pcb_mask_planes_from_dense(m.data_ptr(), n, c, h, w, planes.data_ptr(), _stream()))
-        if channel_uniform is None and 1 < c <= _lib.MAX_PARTS and not torch.cuda.is_current_stream_capturing():
+        if channel_uniform is None and c > 1 and not torch.cuda.is_current_stream_capturing():
             if bool((planes == planes[:1]).all()):              # one sync, eager mode only
                 return HoleMask([(planes[0], c, 0)], n, h, w)
-        if c > _lib.MAX_PARTS:
-            if not bool((planes == planes[:1]).all()):          # device sync; only for wide user-supplied masks
-                raise NotImplementedError("dense masks with more than 8 channels must be channel-uniform")
-            return HoleMask([(planes[0], c, 0)], n, h, w)
+        # genuinely per-channel masks (partial_convolution.py:62-64 accepts any [N,C,H,W] mask): one plane per channel.  A
+        # convolution whose (source, plane) partition exceeds the kernels' part table (PCB_MAX_PARTS) takes the general
+        # dense-mask route in ops.partial_conv -- slower, still exact, still on the GPU.
         return HoleMask([(planes[i], 1, 0) for i in range(c)], n, h, w)
 
     @staticmethod

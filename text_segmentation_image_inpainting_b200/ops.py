@@ -187,6 +187,11 @@ def upsample2x_lazy(x: torch.Tensor) -> "LazyCat":
     return LazyCat([as_feature_padded(x)], [1])
 
 
+class TooManyParts(Exception):
+    """The (source, mask-plane) partition of a convolution does not fit the kernels' part table: ops.partial_conv falls back to
+    the general dense-mask formulation."""
+
+
 class ConvGeom:
     """One partial-convolution problem: geometry + the channel partition (x source, mask plane) per part."""
 
@@ -230,7 +235,7 @@ class ConvGeom:
                 if a < b_:
                     self.parts.append((xi, a - lo, b_ - a, plane, mup))
         if len(self.parts) > _lib.MAX_PARTS:
-            raise NotImplementedError(f"more than {_lib.MAX_PARTS} (source, mask-plane) parts in one convolution")
+            raise TooManyParts(f"more than {_lib.MAX_PARTS} (source, mask-plane) parts in one convolution")
         self.signature = (self.dtype, cin, cout, kh, kw, groups, tuple(p[2] for p in self.parts), tuple(self.x_cstrides),
                           tuple(self.x_ups), s, d)
 
@@ -685,7 +690,10 @@ def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_
     cout = weight.shape[0]
     if weight.shape[1] * groups != cin:
         raise _lib.PcbError(f"weight expects {weight.shape[1] * groups} input channels, got {cin}")
-    geom = ConvGeom(xs, ups, cout, tuple(weight.shape[2:]), stride, padding, dilation, groups, same_holes, no_guard, parts, plain=plain)
+    try:
+        geom = ConvGeom(xs, ups, cout, tuple(weight.shape[2:]), stride, padding, dilation, groups, same_holes, no_guard, parts, plain=plain)
+    except TooManyParts:
+        return _partial_conv_dense_masks(x, hm, weight, bias, stride, padding, dilation, groups, same_holes, no_guard, cache)
     wprep = prepare_weight(weight, geom, cache if cache is not None else {})
     y, msum, newmask = PartialConvFn.apply(geom, wprep, weight, bias, handoff, *xs)
     planes = [newmask[g] for g in range(geom.mg)]
@@ -698,6 +706,55 @@ def partial_conv(x, mask, weight, bias, stride, padding, dilation, groups, same_
         cog = cout // groups
         new = HoleMask([(planes[g], cog, 0) for g in range(groups)], n, geom.ho, geom.wo)
     return y, new
+
+
+def _partial_conv_dense_masks(x, hm: HoleMask, weight, bias, stride, padding, dilation, groups, same_holes, no_guard, cache):
+    """General per-channel masks (partial_convolution.py:62-64 accepts ANY [N,C,H,W] mask): when the mask has more distinct
+    (source, plane) parts than the kernels' part table holds (PCB_MAX_PARTS), the partial convolution is computed the way the
+    reference states it, on the GPU, from this library's own kernels:
+        c = conv(x * m; W)              -- the same convolution kernels in `plain` mode (tensor cores when eligible)
+        s = conv(m; ones) per group     -- exact fp32 mode (mask sums reach cin*k*k: never in bf16)
+        y = where(s == 0, 0, c / s + b) ; m' = (s != 0)
+    Slower than the fused path (the dense mask is materialised); exact; differentiable through the same autograd Functions."""
+    if isinstance(x, LazyCat):
+        x = x.materialize()
+    x = as_feature_padded(x)
+    cin, cout = x.shape[1], weight.shape[0]
+    m = hm.dense()                                                   # fp32 [N, C, H, W]
+    if m.shape[1] != cin:
+        m = m[:, :1].expand(-1, cin, -1, -1)
+    xm = (x * m.to(x.dtype)).contiguous(memory_format=CL)
+    c_raw, _ = partial_conv(xm, None, weight, None, stride, padding, dilation, groups, cache=cache, plain=True)
+    kh, kw = weight.shape[2:]
+    with torch.no_grad():
+        if same_holes:
+            ones = torch.ones((1, 1, kh, kw), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+            s, _ = partial_conv(m[:, :1].contiguous(memory_format=CL), None, ones, None, stride, padding, dilation, 1, plain=True)
+            s = s * float(cin)                                       # :61 (total in_channels, also for depthwise)
+            mg = 1
+        else:
+            ones = torch.ones((groups, cin // groups, kh, kw), dtype=torch.float32, device=x.device).contiguous(memory_format=CL)
+            s, _ = partial_conv(m.contiguous(memory_format=CL), None, ones, None, stride, padding, dilation, groups, plain=True)
+            mg = groups
+        hole = s == 0
+        rep = cout // mg
+        s_full = s.repeat_interleave(rep, dim=1) if rep > 1 else s
+        hole_full = s_full == 0
+    b = bias.view(1, -1, 1, 1).to(torch.float32) if bias is not None else None
+    y = c_raw.float() / (s_full if no_guard else s_full.masked_fill(hole_full, 1.0))
+    if b is not None:
+        y = y + b
+    if not no_guard:
+        y = y.masked_fill(hole_full, 0.0)
+    y = y.to(x.dtype).contiguous(memory_format=CL)
+    n, _, ho, wo = y.shape
+    if no_guard:
+        planes = [torch.ones((n, ho, wo), dtype=torch.uint8, device=x.device)]
+        return y, HoleMask.from_plane(planes[0], cout, 0)
+    newmask = (~hole).to(torch.uint8)                                # [N, mg, Ho, Wo]
+    if mg == 1:
+        return y, HoleMask.from_plane(newmask[:, 0].contiguous(), cout, 0)
+    return y, HoleMask([(newmask[:, g].contiguous(), rep, 0) for g in range(mg)], n, ho, wo)
 
 
 # ------------------------------------------------------------------------------------------------
