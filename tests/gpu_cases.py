@@ -328,9 +328,18 @@ def run_net(cls_name, dev, dtype, tag=""):
     for k, gr in ref_grads.items():
         kinds.setdefault((gr.dim(), k.rsplit(".", 1)[-1]), []).append(float(gr.abs().max()))
     floors = {kk: 1e-2 * float(np.median(v)) for kk, v in kinds.items()}
+    num, den = {}, {}
     for k, gr in ref_grads.items():
-        denom = max(float(gr.abs().max()), floors[(gr.dim(), k.rsplit(".", 1)[-1])], 1e-30)
-        errs["g." + k] = float((params[k].grad.detach().float().cpu() - gr).abs().max()) / denom
+        kind = (gr.dim(), k.rsplit(".", 1)[-1])
+        got = params[k].grad.detach().float().cpu()
+        denom = max(float(gr.abs().max()), floors[kind], 1e-30)
+        errs["g." + k] = float((got - gr).abs().max()) / denom
+        num[kind] = num.get(kind, 0.0) + float((got - gr).double().pow(2).sum())
+        den[kind] = den.get(kind, 0.0) + float(gr.double().pow(2).sum())
+    # and per KIND of parameter (conv weights / BatchNorm scales / BatchNorm shifts / conv biases): relative L2 over the
+    # concatenation of all tensors of the kind -- insensitive to which individual tensors are mathematically zero
+    for kind in num:
+        errs[f"gl2.{kind[0]}d.{kind[1]}"] = (num[kind] / max(den[kind], 1e-60)) ** 0.5
     return errs
 
 

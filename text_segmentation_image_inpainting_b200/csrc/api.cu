@@ -82,19 +82,24 @@ PCB_API int pcb_conv_weight_refresh(const pcb_conv *c, const float *w_master_krs
 }
 
 // 1 when the forward kernel this problem dispatches to can accumulate the per-channel BatchNorm statistics of its output itself
-PCB_API int pcb_conv_fuses_bn_stats(const pcb_conv *c) { return (c && use_tc(c) && pcb_tc_fuses_bn_stats(c)) ? 1 : 0; }
+PCB_API int pcb_conv_fuses_bn_stats(const pcb_conv *c) {
+    if (!c || c->force_generic) return 0;
+    if (use_dw(c)) return pcb_dw_fuses_bn_stats(c) ? 1 : 0;
+    return (use_tc(c) && pcb_tc_fuses_bn_stats(c)) ? 1 : 0;
+}
 
 static int pconv_forward_impl(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, float *msum,
                               uint8_t *newmask, void *workspace, bool mask_pass_done, double *bn_sums, pcb_stream_t stream) {
     if (int rc = validate(c, true)) return rc;
     PCB_CHECK(w_fwd && y && msum && newmask && y_cstride >= c->cout, "pcb_pconv_forward: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!mask_pass_done)
+    if (c->plain) msum = nullptr;                         // ordinary convolution: no mask pass, renormaliser 1 (msum / newmask untouched)
+    else if (!mask_pass_done)
         if (int rc = pcb_mask_sums(c, msum, newmask, st)) return rc;
     PCB_CHECK(bn_sums == nullptr || pcb_conv_fuses_bn_stats(c), "pcb_pconv_forward_bn: this problem's kernel does not fuse the BatchNorm statistics (ask pcb_conv_fuses_bn_stats first)");
     if (use_dw(c)) {
         PCB_CHECK(y_cstride % 8 == 0, "depthwise forward: y channel stride must be a multiple of 8");
-        return pcb_dw_forward(c, w_fwd, bias, y, y_cstride, msum, st);
+        return pcb_dw_forward(c, w_fwd, bias, y, y_cstride, msum, bn_sums, st);
     }
     if (use_tc(c)) {
         PCB_CHECK(workspace != nullptr, "pcb_pconv_forward: workspace required for the tensor-core path");

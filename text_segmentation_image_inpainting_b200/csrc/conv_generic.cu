@@ -140,7 +140,7 @@ __global__ void generic_fwd_kernel(const GParams G, const T *__restrict__ w, con
             continue;
         }
         const int g = (mg == 1) ? 0 : co / cog;
-        const float s = msum[g * total + m];
+        const float s = msum ? msum[g * total + m] : 1.f;               // null: plain convolution (renormaliser 1)
         const float b = bias ? bias[co] : 0.f;
         float v;
         if (G.no_guard) v = acc[j] / s + b;                                    // :134 (NaN/inf on s == 0, as the reference)

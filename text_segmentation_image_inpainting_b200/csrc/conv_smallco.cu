@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(SC_THREADS, 3) smallco_fwd_kernel(const ScPara
                 const int ox = tx0 + mt * 16 + g + 8 * half;
                 if (oy >= P.ho || ox >= P.wo) continue;
                 const long long q = (static_cast<long long>(img) * P.ho + oy) * P.wo + ox;
-                const float s = P.msum[q];
+                const float s = P.msum ? P.msum[q] : 1.f;               // null: plain convolution
                 const bool hole = (s == 0.f) && !P.no_guard;
                 const float inv = hole ? 0.f : 1.0f / s;
                 const int co = 2 * t;

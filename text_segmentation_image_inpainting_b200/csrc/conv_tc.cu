@@ -130,7 +130,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                 float inv = 0.f;
                 bool hole = false;
                 if (MODE == 0 && rvalid) {
-                    const float s = P.msum[m];
+                    const float s = P.msum ? P.msum[m] : 1.f;                // null: plain convolution (renormaliser 1)
                     hole = (s == 0.f) && !P.no_guard;
                     inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
                 }
@@ -1937,7 +1937,7 @@ __global__ void splitk_finish_fwd_kernel(const float *__restrict__ part, int nco
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long m = i / cv;
         const int col = static_cast<int>(i - m * cv) * 8;
-        const float s = msum[m];
+        const float s = msum ? msum[m] : 1.f;
         const bool hole = (s == 0.f) && !no_guard;
         const float inv = hole ? 0.f : 1.0f / s;
         uint4 o;
@@ -2208,6 +2208,9 @@ int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t 
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     const Layout L = layout_of(c);
     if (smallco_ok(c)) return 0;
+    bool any_mask = false;
+    for (int p = 0; p < c->nparts; ++p) any_mask = any_mask || (c->parts[p].mask != nullptr);
+    if (tma_fwd_ok(c) && !any_mask) return 0;            // no holes: TMA's out-of-range zero fill is all the validity there is
     if (tma_fwd_ok(c)) {                                  // row-halo tiles: the fixers read the mask planes themselves
         int bw, bh, bn;
         tile_box(c->wo, c->ho, &bw, &bh, &bn);
@@ -2487,7 +2490,10 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= c->cout, "tensor-core wgrad: dc channel stride must be a multiple of 8");
     if (smallco_ok(c)) return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, zero_dw, st);
     uint64_t *tapmask = static_cast<uint64_t *>(workspace);
-    if (int rc = launch_tapmask(c, tapmask, st)) return rc;
+    bool any_mask = false;
+    for (int p = 0; p < c->nparts; ++p) any_mask = any_mask || (c->parts[p].mask != nullptr);
+    if (any_mask || !tma_wgrad_ok(c))                     // the TMA-fed kernel without holes needs no validity words
+        if (int rc = launch_tapmask(c, tapmask, st)) return rc;
     const size_t dw_bytes = sizeof(float) * c->cout * c->kh * c->kw * c->cin;
     if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, st));
     const Layout L = layout_of(c);

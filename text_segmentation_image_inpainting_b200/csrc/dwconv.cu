@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const DwParams P, const T *
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float b = bias ? bias[ch + j] : 0.f;
-            if (!P.msum) { o[j] = acc[j] + b; continue; }
+            if (!P.msum) { o[j] = acc[j] + b; continue; }                  // plain convolution
             const float s = P.msum[(P.mg == 1 ? 0 : static_cast<long long>(ch + j) * total) + m];
             if (P.no_guard) o[j] = acc[j] / s + b;
             else o[j] = (s == 0.f) ? 0.f : acc[j] / s + b;
@@ -168,6 +168,227 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const DwParams P, const T
     }
 }
 
+
+// =================================================================================================================
+// 3x3 depthwise kernels, second generation (any stride / dilation).  The first-generation kernels above spend most of their
+// instructions on 64-bit index divisions per element and reload the nine weight vectors for every output; at 8 x 512^2 they
+// reach ~13 % of the HBM roofline (ncu: issue-bound, not bandwidth-bound).  Here
+//   * a block owns a chunk of `cvb` channel vectors (8 channels each) x PL pixel lanes; a thread keeps ONE channel vector for
+//     its whole life, so the nine weight vectors (fwd / dgrad) or the nine gradient accumulators (wgrad) live in registers,
+//   * rows are walked by blockIdx.y in groups, pixels of a row by the PL lanes: all index math is 32-bit adds,
+//   * consecutive threads read consecutive 16-byte vectors of the same pixel (coalesced 16 * cvb byte segments), the 3x3
+//     neighbourhood re-reads hit L1 / L2,
+//   * the weight-gradient partials of the PL lanes are summed through shared memory in parallel and leave the block as one
+//     atomic per (channel, tap).
+// =================================================================================================================
+struct Dw3Geom { int cvb, pl, chunks; };
+
+inline Dw3Geom dw3_geom(int c) {
+    const int cv = c >> 3;
+    Dw3Geom g;
+    g.cvb = 1;
+    for (int d = 1; d <= 32 && d <= cv; ++d)
+        if (cv % d == 0) g.cvb = d;                 // largest divisor of cv that is <= 32
+    if (g.cvb < 8 && cv > 32) g.cvb = 32;           // awkward channel counts: 32-wide chunks, the last one partly idle
+    g.pl = 256 / g.cvb;
+    g.chunks = (cv + g.cvb - 1) / g.cvb;
+    return g;
+}
+
+template <typename T> __device__ __forceinline__ void dw3_load_weights(const T *__restrict__ w_t, int c, int ch, float (&wt)[9][8]) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) Vec8<T>::load(w_t + static_cast<long long>(tap) * c + ch, wt[tap]);
+}
+
+constexpr int DW3_ROWS = 8;                         // output rows per block (forward / dgrad)
+
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(256) dw3_fwd_kernel(const DwParams P, const T *__restrict__ x, const T *__restrict__ w_t,
+                                                      const float *__restrict__ bias, T *__restrict__ y, int cvb, int pl,
+                                                      double *__restrict__ bn_sums) {
+    __shared__ float s_stat[256][2];
+    const int vl = static_cast<int>(threadIdx.x) % cvb;
+    const int v = blockIdx.x * cvb + vl, lane_px = static_cast<int>(threadIdx.x) / cvb;
+    const bool active = lane_px < pl && v < (P.c >> 3);
+    if (!active && bn_sums == nullptr) return;
+    const int ch = v * 8;
+    float wt[9][8], bs[8], st_s[8], st_q[8];
+    if (active) dw3_load_weights(w_t, P.c, ch, wt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bs[j] = (active && bias) ? bias[ch + j] : 0.f; st_s[j] = 0.f; st_q[j] = 0.f; }
+    const int rows_total = P.n * P.ho;
+    const long long total = static_cast<long long>(rows_total) * P.wo;
+    for (int rr = 0; rr < DW3_ROWS; ++rr) {
+        const int row = blockIdx.y * DW3_ROWS + rr;
+        if (row >= rows_total || !active) break;
+        const int nn = row / P.ho, oh = row - nn * P.ho;
+        const int hi0 = oh * P.stride - P.pad_h;
+        for (int ow = lane_px; ow < P.wo; ow += pl) {
+            const int wi0 = ow * P.stride - P.pad_w;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int tr = 0; tr < 3; ++tr) {
+                const int hi = hi0 + tr * P.dil;
+                if (hi < 0 || hi >= P.h) continue;
+                const T *xrow = x + static_cast<long long>(nn * P.h + hi) * P.w * P.x_cstride + ch;
+#pragma unroll
+                for (int tc = 0; tc < 3; ++tc) {
+                    const int wi = wi0 + tc * P.dil;
+                    if (wi < 0 || wi >= P.w) continue;
+                    if (!PLAIN && !dw_mask(P, nn, hi, wi)) continue;
+                    float xv[8];
+                    Vec8<T>::load(xrow + static_cast<long long>(wi) * P.x_cstride, xv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wt[tr * 3 + tc][j], acc[j]);
+                }
+            }
+            const long long m = static_cast<long long>(row) * P.wo + ow;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (PLAIN) { o[j] = acc[j] + bs[j]; continue; }
+                const float s = P.msum[(P.mg == 1 ? 0 : static_cast<long long>(ch + j) * total) + m];
+                if (P.no_guard) o[j] = acc[j] / s + bs[j];
+                else o[j] = (s == 0.f) ? 0.f : acc[j] / s + bs[j];
+            }
+            Vec8<T>::store(y + m * P.y_cstride + ch, o);
+            if (bn_sums != nullptr) {                   // BatchNorm statistics of what was stored (bf16-rounded in bf16 mode)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float r = to_f32(from_f32<T>(o[j])); st_s[j] += r; st_q[j] = fmaf(r, r, st_q[j]); }
+            }
+        }
+    }
+    if (bn_sums != nullptr) {
+        // fused statistics pass of the BatchNorm that follows the depthwise convolution (BaseModels.py:95-99): per channel,
+        // the PL pixel lanes' partial sums are added through shared memory; one fp64 atomic per channel and block
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __syncthreads();
+            s_stat[threadIdx.x][0] = active ? st_s[j] : 0.f;
+            s_stat[threadIdx.x][1] = active ? st_q[j] : 0.f;
+            __syncthreads();
+            for (int col = threadIdx.x; col < cvb * 2; col += 256) {
+                const int cvl = col >> 1, q = col & 1;
+                const int vv = blockIdx.x * cvb + cvl;
+                if (vv >= (P.c >> 3)) continue;
+                float tot = 0.f;
+                for (int l = 0; l < pl; ++l) tot += s_stat[l * cvb + cvl][q];
+                atomicAdd(bn_sums + static_cast<long long>(q) * P.c + vv * 8 + j, static_cast<double>(tot));
+            }
+        }
+    }
+}
+
+// dx[p][c] = mask(p) * sum_taps dc[(p + pad - tap*dil) / stride][c] * w[tap][c]   (stride is a power of two here)
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(256) dw3_dgrad_kernel(const DwParams P, const T *__restrict__ dc, int dc_cstride, const T *__restrict__ w_t,
+                                                        T *__restrict__ dx, int dx_cstride, int cvb, int pl, int sshift) {
+    const int v = blockIdx.x * cvb + static_cast<int>(threadIdx.x) % cvb, lane_px = static_cast<int>(threadIdx.x) / cvb;
+    if (lane_px >= pl || v >= (P.c >> 3)) return;
+    const int ch = v * 8;
+    float wt[9][8];
+    dw3_load_weights(w_t, P.c, ch, wt);
+    const int rows_total = P.n * P.h, smask = P.stride - 1;
+    for (int rr = 0; rr < DW3_ROWS; ++rr) {
+        const int row = blockIdx.y * DW3_ROWS + rr;
+        if (row >= rows_total) break;
+        const int nn = row / P.h, ih = row - nn * P.h;
+        for (int iw = lane_px; iw < P.w; iw += pl) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            if (PLAIN || dw_mask(P, nn, ih, iw)) {
+#pragma unroll
+                for (int tr = 0; tr < 3; ++tr) {
+                    const int th = ih + P.pad_h - tr * P.dil;
+                    if (th < 0 || (th & smask)) continue;
+                    const int oh = th >> sshift;
+                    if (oh >= P.ho) continue;
+                    const T *drow = dc + static_cast<long long>(nn * P.ho + oh) * P.wo * dc_cstride + ch;
+#pragma unroll
+                    for (int tc = 0; tc < 3; ++tc) {
+                        const int tw = iw + P.pad_w - tc * P.dil;
+                        if (tw < 0 || (tw & smask)) continue;
+                        const int ow = tw >> sshift;
+                        if (ow >= P.wo) continue;
+                        float dv[8];
+                        Vec8<T>::load(drow + static_cast<long long>(ow) * dc_cstride, dv);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(dv[j], wt[tr * 3 + tc][j], acc[j]);
+                    }
+                }
+            }
+            Vec8<T>::store(dx + (static_cast<long long>(row) * P.w + iw) * dx_cstride + ch, acc);
+        }
+    }
+}
+
+// dw[c][tap] += sum over output pixels of dc[p][c] * (x*m)[p @ tap][c]
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(256) dw3_wgrad_kernel(const DwParams P, const T *__restrict__ dc, int dc_cstride, const T *__restrict__ x,
+                                                        float *__restrict__ dw, int cvb, int pl, int rows_per_block) {
+    __shared__ float s_red[256][9];
+    const int vl = static_cast<int>(threadIdx.x) % cvb, lane_px = static_cast<int>(threadIdx.x) / cvb;
+    const int v = blockIdx.x * cvb + vl;
+    const bool active = lane_px < pl && v < (P.c >> 3);
+    const int ch = v * 8;
+    float acc[9][8];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[tap][j] = 0.f;
+    const int rows_total = P.n * P.ho;
+    if (active) {
+        for (int rr = 0; rr < rows_per_block; ++rr) {
+            const int row = blockIdx.y * rows_per_block + rr;
+            if (row >= rows_total) break;
+            const int nn = row / P.ho, oh = row - nn * P.ho;
+            const int hi0 = oh * P.stride - P.pad_h;
+            const T *dcrow = dc + static_cast<long long>(row) * P.wo * dc_cstride + ch;
+            for (int ow = lane_px; ow < P.wo; ow += pl) {
+                float dv[8];
+                Vec8<T>::load(dcrow + static_cast<long long>(ow) * dc_cstride, dv);
+                const int wi0 = ow * P.stride - P.pad_w;
+#pragma unroll
+                for (int tr = 0; tr < 3; ++tr) {
+                    const int hi = hi0 + tr * P.dil;
+                    if (hi < 0 || hi >= P.h) continue;
+                    const T *xrow = x + static_cast<long long>(nn * P.h + hi) * P.w * P.x_cstride + ch;
+#pragma unroll
+                    for (int tc = 0; tc < 3; ++tc) {
+                        const int wi = wi0 + tc * P.dil;
+                        if (wi < 0 || wi >= P.w) continue;
+                        if (!PLAIN && !dw_mask(P, nn, hi, wi)) continue;
+                        float xv[8];
+                        Vec8<T>::load(xrow + static_cast<long long>(wi) * P.x_cstride, xv);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[tr * 3 + tc][j] = fmaf(dv[j], xv[j], acc[tr * 3 + tc][j]);
+                    }
+                }
+            }
+        }
+    }
+    // per channel j of the vector: stage the 9 tap partials of every thread, then cvb * 9 threads each sum one (vector, tap) column
+    // over the PL pixel lanes and leave with ONE atomic
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) s_red[threadIdx.x][tap] = active ? acc[tap][j] : 0.f;
+        __syncthreads();
+        for (int col = threadIdx.x; col < cvb * 9; col += 256) {
+            const int cvl = col / 9, tap = col - cvl * 9;
+            const int vv = blockIdx.x * cvb + cvl;
+            if (vv >= (P.c >> 3)) continue;
+            float tot = 0.f;
+            for (int l = 0; l < pl; ++l) tot += s_red[l * cvb + cvl][tap];
+            atomicAdd(dw + static_cast<long long>(vv * 8 + j) * 9 + tap, tot);
+        }
+    }
+}
+
 template <typename T>
 __global__ void dw_weight_transpose_kernel(const float *__restrict__ wm, int c, int taps, T *__restrict__ w_t) {
     const long long total = static_cast<long long>(c) * taps;
@@ -212,11 +433,28 @@ int pcb_dw_weight_prepare(const pcb_conv *c, const float *w_master, void *w_t, c
     return 0;
 }
 
-int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *y, int y_cstride, const float *msum, cudaStream_t st) {
+bool pcb_dw_fuses_bn_stats(const pcb_conv *c) {
+    return pcb_dw_eligible(c) && c->kh == 3 && c->kw == 3 && !getenv("PCB_DW_GEN1") && !getenv("PCB_DISABLE_FUSED_BN_STATS");
+}
+
+int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *y, int y_cstride, const float *msum, double *bn_sums,
+                   cudaStream_t st) {
+    PCB_CHECK(bn_sums == nullptr || pcb_dw_fuses_bn_stats(c), "depthwise forward: fused BatchNorm statistics need the 3x3 kernels");
     DwParams P;
     fill(P, c);
     P.y_cstride = y_cstride;
     P.msum = msum;       // plain mode: mask_sums wrote 1.0 everywhere, so the same epilogue applies
+    if (c->kh == 3 && c->kw == 3 && !getenv("PCB_DW_GEN1")) {
+        const Dw3Geom g = dw3_geom(c->cin);
+        const dim3 grid(g.chunks, (c->n * c->ho + DW3_ROWS - 1) / DW3_ROWS);
+        const bool plain = c->plain && c->parts[0].mask == nullptr;
+#define PCB_DW3_FWD(TT, PL_) dw3_fwd_kernel<TT, PL_><<<grid, 256, 0, st>>>(P, static_cast<const TT *>(c->parts[0].x), static_cast<const TT *>(w_t), bias, static_cast<TT *>(y), g.cvb, g.pl, bn_sums)
+        if (c->dtype == PCB_BF16) { if (plain) PCB_DW3_FWD(bf16, true); else PCB_DW3_FWD(bf16, false); }
+        else { if (plain) PCB_DW3_FWD(float, true); else PCB_DW3_FWD(float, false); }
+#undef PCB_DW3_FWD
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     const long long nvec = static_cast<long long>(c->n) * c->ho * c->wo * (c->cin / 8);
     if (c->dtype == PCB_BF16) dw_fwd_kernel<bf16><<<dw_grid(nvec), 256, 0, st>>>(P, static_cast<const bf16 *>(c->parts[0].x), static_cast<const bf16 *>(w_t), bias, static_cast<bf16 *>(y));
     else dw_fwd_kernel<float><<<dw_grid(nvec), 256, 0, st>>>(P, static_cast<const float *>(c->parts[0].x), static_cast<const float *>(w_t), bias, static_cast<float *>(y));
@@ -227,6 +465,19 @@ int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *
 int pcb_dw_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_t, void *dx, int dx_cstride, cudaStream_t st) {
     DwParams P;
     fill(P, c);
+    if (c->kh == 3 && c->kw == 3 && (c->stride & (c->stride - 1)) == 0 && !getenv("PCB_DW_GEN1")) {
+        const Dw3Geom g = dw3_geom(c->cin);
+        const dim3 grid(g.chunks, (c->n * c->h + DW3_ROWS - 1) / DW3_ROWS);
+        const bool plain = c->plain && c->parts[0].mask == nullptr;
+        int sshift = 0;
+        while ((1 << sshift) < c->stride) ++sshift;
+#define PCB_DW3_DG(TT, PL_) dw3_dgrad_kernel<TT, PL_><<<grid, 256, 0, st>>>(P, static_cast<const TT *>(dc), dc_cstride, static_cast<const TT *>(w_t), static_cast<TT *>(dx), dx_cstride, g.cvb, g.pl, sshift)
+        if (c->dtype == PCB_BF16) { if (plain) PCB_DW3_DG(bf16, true); else PCB_DW3_DG(bf16, false); }
+        else { if (plain) PCB_DW3_DG(float, true); else PCB_DW3_DG(float, false); }
+#undef PCB_DW3_DG
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     const long long nvec = static_cast<long long>(c->n) * c->h * c->w * (c->cin / 8);
     if (c->dtype == PCB_BF16) dw_dgrad_kernel<bf16><<<dw_grid(nvec), 256, 0, st>>>(P, static_cast<const bf16 *>(dc), dc_cstride, static_cast<const bf16 *>(w_t), static_cast<bf16 *>(dx), dx_cstride);
     else dw_dgrad_kernel<float><<<dw_grid(nvec), 256, 0, st>>>(P, static_cast<const float *>(dc), dc_cstride, static_cast<const float *>(w_t), static_cast<float *>(dx), dx_cstride);
@@ -239,6 +490,22 @@ int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, b
     fill(P, c);
     const int taps = c->kh * c->kw;
     if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cin * taps, st));
+    if (c->kh == 3 && c->kw == 3 && !getenv("PCB_DW_GEN1")) {
+        const Dw3Geom g = dw3_geom(c->cin);
+        // about two resident waves of blocks; every block ends with cvb * 72 atomics
+        const int rows_total = c->n * c->ho;
+        int row_groups = std::max(1, std::min(rows_total, (4 * pcb_num_sms() + g.chunks - 1) / g.chunks));
+        const int rpbk = (rows_total + row_groups - 1) / row_groups;
+        row_groups = (rows_total + rpbk - 1) / rpbk;
+        const dim3 grid(g.chunks, row_groups);
+        const bool plain = c->plain && c->parts[0].mask == nullptr;
+#define PCB_DW3_WG(TT, PL_) dw3_wgrad_kernel<TT, PL_><<<grid, 256, 0, st>>>(P, static_cast<const TT *>(dc), dc_cstride, static_cast<const TT *>(c->parts[0].x), dw, g.cvb, g.pl, rpbk)
+        if (c->dtype == PCB_BF16) { if (plain) PCB_DW3_WG(bf16, true); else PCB_DW3_WG(bf16, false); }
+        else { if (plain) PCB_DW3_WG(float, true); else PCB_DW3_WG(float, false); }
+#undef PCB_DW3_WG
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     const long long total = static_cast<long long>(c->n) * c->ho * c->wo;
     const int rpb = 256 / (c->cin / 8);
     long long blocks = (total + rpb * 16 - 1) / (rpb * 16);

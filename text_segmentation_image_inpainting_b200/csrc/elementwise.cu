@@ -166,52 +166,60 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const T *__restr
 // 8 channels from the complete fp64 sums (produced by the convolution epilogue or pcb_bn_stats_acc), block 0 additionally
 // updates the running statistics and writes the per-channel coefficients the backward needs.
 //   coef: [4][c] floats = scale (gamma * invstd) | shift (beta - mean * scale) | mean | invstd
+// (fp64 arithmetic runs at 1/64 of the fp32 rate on this GPU: the coefficient prologue is done ONCE per channel and block,
+// cooperatively, and handed to the threads through shared memory -- with every thread finalising its own 8 channels the
+// prologue alone cost ~1 us per block and put a 10 us floor under every launch.)
 template <typename T, int ACT>
 __global__ void __launch_bounds__(EW_THREADS) bn_fwd_fused_kernel(const T *__restrict__ x, long long count, int c, const double *__restrict__ sums,
                                                                   const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                   float *running_mean, float *running_var, long long *nbt, float momentum, float eps,
                                                                   int act, float slope, const T *__restrict__ residual, T *__restrict__ y,
                                                                   float *__restrict__ coef) {
+    extern __shared__ float s_coef[];                                 // [2][c]: scale | shift
+    const double inv_n = 1.0 / static_cast<double>(count);
+    const bool writer = blockIdx.x == 0;
+    if (writer && threadIdx.x == 0 && nbt) *nbt += 1;
+    for (int ch = threadIdx.x; ch < c; ch += EW_THREADS) {
+        const double m = sums[ch] * inv_n;
+        double var = sums[c + ch] * inv_n - m * m;                    // biased (normalisation)
+        if (var < 0) var = 0;
+        const float mean = static_cast<float>(m), fvar = static_cast<float>(var);
+        const float invstd = 1.0f / sqrtf(fvar + eps);                // fp32 like torch's batch_norm kernels
+        const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+        const float sc = g * invstd, sh = b - mean * g * invstd;
+        s_coef[ch] = sc; s_coef[c + ch] = sh;
+        if (writer) {
+            coef[ch] = sc; coef[c + ch] = sh; coef[2 * c + ch] = mean; coef[3 * c + ch] = invstd;
+            if (running_mean) {
+                const float unbiased = count > 1 ? fvar * (static_cast<float>(count) / static_cast<float>(count - 1)) : fvar;
+                running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+                running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+            }
+        }
+    }
+    __syncthreads();
     const int cv = c >> 3, rpb = EW_THREADS / cv;
     const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
     if (r >= rpb) return;
     float sc[8], sh[8];
-    const double inv_n = 1.0 / static_cast<double>(count);
-    const bool writer = blockIdx.x == 0 && r == 0;
-    if (writer && v == 0 && nbt) *nbt += 1;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int ch = v * 8 + j;
-        const double m = sums[ch] * inv_n;
-        double var = sums[c + ch] * inv_n - m * m;                    // biased (normalisation)
-        if (var < 0) var = 0;
-        const float mean = static_cast<float>(m);
-        const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);      // fp32 like torch's batch_norm kernels
-        const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-        sc[j] = g * invstd;
-        sh[j] = b - mean * g * invstd;
-        if (writer) {
-            coef[ch] = sc[j]; coef[c + ch] = sh[j]; coef[2 * c + ch] = mean; coef[3 * c + ch] = invstd;
-            if (running_mean) {
-                const double unbiased = count > 1 ? var * static_cast<double>(count) / static_cast<double>(count - 1) : var;
-                running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
-                running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
-            }
-        }
-    }
+    for (int j = 0; j < 8; ++j) { sc[j] = s_coef[v * 8 + j]; sh[j] = s_coef[c + v * 8 + j]; }
     const long long step = static_cast<long long>(gridDim.x) * rpb;
+    const T *px = x + v * 8;
+    const T *pr = residual ? residual + v * 8 : nullptr;
+    T *py = y + v * 8;
 #pragma unroll 4
     for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += step) {
         float f[8], rres[8];
-        Vec8<T>::load(x + row * c + v * 8, f);
-        if (residual) Vec8<T>::load(residual + row * c + v * 8, rres);
+        Vec8<T>::load(px + row * c, f);
+        if (pr) Vec8<T>::load(pr + row * c, rres);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float z = apply_act(f[j] * sc[j] + sh[j], ACT, slope);
-            if (residual) z += rres[j];
+            if (pr) z += rres[j];
             f[j] = z;
         }
-        Vec8<T>::store(y + row * c + v * 8, f);
+        Vec8<T>::store(py + row * c, f);
     }
 }
 
@@ -277,25 +285,30 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_bwd_apply_kernel(const T *__
                                                                      float slope, const double *__restrict__ sum_g, const double *__restrict__ sum_gx,
                                                                      int training, const float *__restrict__ msum, T *__restrict__ dx,
                                                                      float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    const int cv = c >> 3, rpb = EW_THREADS / cv;
-    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
-    if (r >= rpb) return;
+    extern __shared__ float s_coef[];                                 // [5][c]: scale | shift | mean | B | C (see above)
     const float inv_count = 1.0f / static_cast<float>(count);
     const bool full = scale && training;
-    const bool writer = full && blockIdx.x == 0 && r == 0;            // parameter gradients: dgamma = sum gz*xhat, dbeta = sum gz
-    float sc[8], sh[8], mu[8], cb[8], cc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int ch = v * 8 + j;
-        sc[j] = scale ? scale[ch] : 1.f; sh[j] = scale ? shift[ch] : 0.f;
-        mu[j] = full ? mean[ch] : 0.f;
+    const bool writer = full && blockIdx.x == 0;                      // parameter gradients: dgamma = sum gz*xhat, dbeta = sum gz
+    for (int ch = threadIdx.x; ch < c; ch += EW_THREADS) {            // once per channel and block (fp64 -> fp32 conversions are slow)
+        const float a = scale ? scale[ch] : 1.f;
         const float sg = full ? static_cast<float>(sum_g[ch]) : 0.f, sgx = full ? static_cast<float>(sum_gx[ch]) : 0.f;
-        cb[j] = full ? -sc[j] * invstd[ch] * sgx * inv_count : 0.f;
-        cc[j] = full ? -sc[j] * sg * inv_count : 0.f;
+        s_coef[ch] = a; s_coef[c + ch] = scale ? shift[ch] : 0.f; s_coef[2 * c + ch] = full ? mean[ch] : 0.f;
+        s_coef[3 * c + ch] = full ? -a * invstd[ch] * sgx * inv_count : 0.f;
+        s_coef[4 * c + ch] = full ? -a * sg * inv_count : 0.f;
         if (writer) {
             if (dgamma) dgamma[ch] = sgx;
             if (dbeta) dbeta[ch] = sg;
         }
+    }
+    __syncthreads();
+    const int cv = c >> 3, rpb = EW_THREADS / cv;
+    const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+    if (r >= rpb) return;
+    float sc[8], sh[8], mu[8], cb[8], cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = v * 8 + j;
+        sc[j] = s_coef[ch]; sh[j] = s_coef[c + ch]; mu[j] = s_coef[2 * c + ch]; cb[j] = s_coef[3 * c + ch]; cc[j] = s_coef[4 * c + ch];
     }
     const float ca = (scale != nullptr) ? 1.f : 0.f;                  // no BN at all: d = gz
     const long long step = static_cast<long long>(gridDim.x) * rpb;
@@ -739,10 +752,10 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_forward_fused(const
                                     pcb_stream_t stream) {
     PCB_CHECK(x && y && sums && coef && count > 0 && c > 0 && c % 8 == 0 && c <= 2048, "pcb_bn_forward_fused: bad arguments (c must be a multiple of 8, <= 2048)");
     PCB_CHECK((running_mean == nullptr) == (running_var == nullptr), "pcb_bn_forward_fused: running statistics come in pairs");
-    const int grid = ew_grid(count, (EW_THREADS / (c / 8)) * 4, 8);       // the per-thread coefficient prologue is amortised over >= 16 rows
+    const int grid = ew_grid(count, (EW_THREADS / (c / 8)) * 16, 8);      // >= 16 rows per thread: the block prologue is amortised
     PCB_ACT_SWITCH(act,
-        if (dtype == PCB_BF16) bn_fwd_fused_kernel<bf16, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y), coef);
-        else bn_fwd_fused_kernel<float, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const float *>(residual), static_cast<float *>(y), coef))
+        if (dtype == PCB_BF16) bn_fwd_fused_kernel<bf16, ACT><<<grid, EW_THREADS, 2 * c * sizeof(float), ST>>>(static_cast<const bf16 *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const bf16 *>(residual), static_cast<bf16 *>(y), coef);
+        else bn_fwd_fused_kernel<float, ACT><<<grid, EW_THREADS, 2 * c * sizeof(float), ST>>>(static_cast<const float *>(x), count, c, sums, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope, static_cast<const float *>(residual), static_cast<float *>(y), coef))
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -834,7 +847,7 @@ static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, 
     PCB_CHECK(!msum || (c % 8 == 0 && c <= 2048), "pcb_bn_act_backward_apply_renorm: channel count must be a multiple of 8 (<= 2048)");
     PCB_CHECK(!(scale && training) || (mean && invstd && sum_g && sum_gx), "pcb_bn_act_backward_apply: training needs statistics");
     const bool vec = c % 8 == 0 && c <= 2048;
-    const int grid = vec ? ew_grid(count, (EW_THREADS / (c / 8)) * 4, 6) : ew_grid(count * c, EW_THREADS * 4);
+    const int grid = vec ? ew_grid(count, (EW_THREADS / (c / 8)) * 16, 6) : ew_grid(count * c, EW_THREADS * 4);
     if (!vec) {
         if (dtype == PCB_BF16) bn_bwd_apply_scalar_kernel<bf16><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<bf16 *>(dx));
         else bn_bwd_apply_scalar_kernel<float><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count * c, count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, static_cast<float *>(dx));
@@ -847,8 +860,8 @@ static int bn_act_backward_apply_impl(const void *gy, const void *x, int dtype, 
     }
     // vector path: block 0 also writes the parameter gradients (dgamma = sum gz*xhat, dbeta = sum gz) -- no extra launch
     PCB_ACT_SWITCH(act,
-        if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
-        else bn_bwd_apply_kernel<float, ACT><<<grid, EW_THREADS, 0, ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx), dgamma, dbeta))
+        if (dtype == PCB_BF16) bn_bwd_apply_kernel<bf16, ACT><<<grid, EW_THREADS, 5 * c * sizeof(float), ST>>>(static_cast<const bf16 *>(gy), static_cast<const bf16 *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<bf16 *>(dx), dgamma, dbeta);
+        else bn_bwd_apply_kernel<float, ACT><<<grid, EW_THREADS, 5 * c * sizeof(float), ST>>>(static_cast<const float *>(gy), static_cast<const float *>(x), count, c, scale, shift, mean, invstd, act, slope, sum_g, sum_gx, training, msum, static_cast<float *>(dx), dgamma, dbeta))
     PCB_LAUNCH_CHECK();
     return 0;
 }

@@ -101,7 +101,18 @@ class B200Conv2d(nn.Conv2d):
 
     def forward(self, x):
         from .. import ops
-        return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups, cache=self._wcache)
+        # Conv_block linked the BatchNorm(+act) it placed behind this convolution: when that BatchNorm is in training mode the
+        # convolution accumulates the per-channel sum / sum of squares of its output in its own epilogue and parks them on the
+        # BatchNorm, which then skips its statistics pass over y (keyed by y's address and shape: any other input is ignored).
+        hint = self.__dict__.get("_bn_hint")
+        handoff = None
+        if hint is not None and hint[0].training and hint[0].weight is not None and x.is_cuda:
+            handoff = ops.RenormHandoff(want_stats=True)
+        y = ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups, cache=self._wcache,
+                       handoff=handoff)
+        if handoff is not None and handoff.bn_sums is not None:
+            hint.__dict__["_pending_stats"] = (y.data_ptr(), tuple(y.shape), handoff.bn_sums)
+        return y
 
 
 class B200BNAct(nn.Sequential):
@@ -111,7 +122,9 @@ class B200BNAct(nn.Sequential):
     def forward(self, x, residual=None):
         from .. import ops
         act = self[1] if len(self) > 1 else None
-        return ops.bn_act(x, self[0], act, residual=residual)
+        pend = self.__dict__.pop("_pending_stats", None)
+        pre = pend[2] if (pend is not None and self[0].training and pend[0] == x.data_ptr() and pend[1] == tuple(x.shape)) else None
+        return ops.bn_act(x, self[0], act, residual=residual, pre_sums=pre)
 
 
 def Conv_block(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True, BN=False,
@@ -120,6 +133,7 @@ def Conv_block(in_channels, out_channels, kernel_size, stride=1, padding=0, dila
     m = [B200Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)]
     if BN:
         m.append(B200BNAct(nn.BatchNorm2d(out_channels), activation) if activation else B200BNAct(nn.BatchNorm2d(out_channels)))
+        m[0].__dict__["_bn_hint"] = m[1]            # plain attribute (not a registered submodule: state_dict keys unchanged)
     if BN is False and activation is not None:
         m.append(activation)
     return m

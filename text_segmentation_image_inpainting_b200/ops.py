@@ -403,6 +403,11 @@ class PartialConvFn(torch.autograd.Function):
             # the BatchNorm backward of the block already divided by the mask sums (RenormHandoff): gy IS dc
             dc = gy
             dcs = nhwc_layout(dc)
+        elif geom.plain and not ctx.has_bias and geom.cout % 8 == 0 and nhwc_layout(gy) == geom.cout and gy.data_ptr() % 16 == 0:
+            # ordinary convolution without bias: the renormaliser is 1 and there is no bias gradient -- the "renormalisation
+            # backward" would be a copy of gy (it was 15 % of a segmentation step)
+            dc = gy
+            dcs = geom.cout
         else:
             dc = padded_empty(geom.n, geom.cout, geom.ho, geom.wo, tdtype, dev) if geom.dtype == PCB_BF16 else \
                 torch.empty((geom.n, geom.cout, geom.ho, geom.wo), dtype=tdtype, device=dev, memory_format=CL)
@@ -896,7 +901,7 @@ class BNActFn(torch.autograd.Function):
         return dx, dgamma, dbeta, (gy if has_res else None), None, None, None, None, None, None, None, None, None, None
 
 
-def bn_act(x, bn, act, residual=None, handoff=None):
+def bn_act(x, bn, act, residual=None, handoff=None, pre_sums=None):
     """`bn`: nn.BatchNorm2d or None; `act`: nn activation module / None.  `handoff`: the RenormHandoff of the partial
     convolution whose output `x` is, when this call is that output's only consumer."""
     x = as_feature(x)
@@ -910,7 +915,10 @@ def bn_act(x, bn, act, residual=None, handoff=None):
     if handoff is not None and handoff.eligible and bn.training and x.requires_grad and x.shape[1] % 8 == 0 and x.shape[1] <= 2048 \
             and x.is_contiguous(memory_format=CL):
         msum, handoff.fused = handoff.msum, True
-    pre_sums = handoff.bn_sums if (handoff is not None and bn.training and bn.weight is not None) else None
+    if pre_sums is None:
+        pre_sums = handoff.bn_sums if (handoff is not None and bn.training and bn.weight is not None) else None
+    if pre_sums is not None and not (bn.training and x.is_contiguous(memory_format=CL)):
+        pre_sums = None
     return BNActFn.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                          bn.training, momentum, bn.eps, code, slope, msum, pre_sums)
 
@@ -1041,14 +1049,14 @@ def _dense8(x: torch.Tensor):
     return buf.as_strided((n, c8, h, w), (h * w * c8, 1, w * c8, c8)), c
 
 
-def conv2d(x, weight, bias, stride, padding, dilation, groups, cache=None):
+def conv2d(x, weight, bias, stride, padding, dilation, groups, cache=None, handoff=None):
     """nn.Conv2d on the same kernels as the partial convolution (`plain`: mask ignored, renormaliser 1)."""
     x = as_feature_padded(x)
     if x.dtype == torch.bfloat16 and x.shape[1] < 8 and nhwc_layout(x) % 8 != 0 and groups == 1:
         buf = padded_empty(*x.shape, x.dtype, x.device)          # 16-byte pixels -> row-packed tensor-core path
         buf.copy_(x)
         x = buf
-    y, _ = partial_conv(x, None, weight, bias, stride, padding, dilation, groups, cache=cache, plain=True)
+    y, _ = partial_conv(x, None, weight, bias, stride, padding, dilation, groups, cache=cache, plain=True, handoff=handoff)
     return y
 
 
