@@ -2131,13 +2131,17 @@ bool tma_halo_ok(const pcb_conv *c, int bw, int bh, int bn, int block_n) {
     return 3 * stage <= 208 * 1024;
 }
 
-// widest N tile that divides `cols` and still leaves at least one tile per SM
+// widest N tile that divides `cols` and still leaves at least one tile per SM; low-resolution layers (a handful of M tiles
+// against a multi-megabyte weight matrix) get NARROWER N tiles: each CTA's operand stream is latency-bound (~100 GB/s through a
+// 4..8-stage ring), so the time of such a layer is (bytes per CTA) / that rate -- more, smaller CTAs stream the weights in parallel
 int pick_bn(int cols, long long m_total) {
     const long long m_tiles = (m_total + BLOCK_M - 1) / BLOCK_M;
     if (cols % 256 == 0 && m_tiles * (cols / 256) >= pcb_num_sms()) return 256;
-    if (cols % 128 == 0) return 128;
     if (cols <= 32) return 32;
-    return 64;
+    int bn = (cols % 128 == 0) ? 128 : 64;
+    if (!getenv("PCB_NO_NARROW_N"))
+        while (bn > 32 && cols % (bn / 2) == 0 && m_tiles * (cols / bn) < pcb_num_sms() / 2) bn /= 2;
+    return bn;
 }
 
 template <int MODE>
@@ -2270,7 +2274,7 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
             if (int rc = make_tmap_nhwc(&ta[p], src, c8, c->w, c->h, c->n, cs, P.box_w + hx, P.box_h, P.box_n, c->stride)) return rc;
         }
         if (c->nparts < 2) ta[1] = ta[0];
-        P.ncols = (bn == 32) ? 32 : L.rows_f;
+        P.ncols = (c->cout <= 32) ? 32 : L.rows_f;
         P.wk_base = 0; P.wk_col = L.ktap; P.wk_row = c->kw * L.ktap;
         if (int rc = make_tmap_2d(&tm, w_fwd, L.rows_f, L.kf, L.kf, bn)) return rc;
         P.ksplit = pick_ksplit(m_total, P.ncols, bn, L.ktap / BLOCK_K);
@@ -2326,7 +2330,6 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     if (tma_dgrad_ok(c)) {
         tile_box(c->w, c->h, &P.box_w, &P.box_h, &P.box_n);
         bn = pick_bn(L.ktap, m_total);
-        if (bn == 32) bn = 64;
         const bool halo = tma_halo_ok(c, P.box_w, P.box_h, P.box_n, bn);
         P.wk_base = 0; P.wk_col = L.cout64; P.wk_row = c->kw * L.cout64;
         CUtensorMap ta;
@@ -2358,7 +2361,6 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
         const long long m_class = static_cast<long long>(c->n) * hh * hw;
         tile_box(hw, hh, &P.box_w, &P.box_h, &P.box_n);
         bn = pick_bn(L.ktap, m_class);
-        if (bn == 32) bn = 64;
         if (int rc = make_tmap_2d(&tm, w_dgrad, rup(L.ktap, 128), L.kd, L.kd, bn)) return rc;
         // The classes write disjoint pixels.  When one class does not fill the GPU (low-resolution layers) the four launches
         // run concurrently: fork onto three internal streams after an event on `st`, join before returning (also valid

@@ -389,6 +389,234 @@ __global__ void __launch_bounds__(256) dw3_wgrad_kernel(const DwParams P, const 
     }
 }
 
+
+// =================================================================================================================
+// 3x3 depthwise, stride 1, padding == dilation (every depthwise layer of the reference's segmentation networks), ordinary
+// (mask-free) convolution: third generation.  Measured on the second generation (ncu, 1152 channels @ 64x64, dilation 8): nine
+// 16-byte loads per output vector whose vertical re-use distance (dilation x row x channels) exceeds L1, i.e. 9x the
+// algorithmic bytes out of L2 and ~13 % of the HBM roofline.  Here
+//   * a thread owns one output COLUMN x one channel QUAD (4 channels, 8-byte accesses) and walks down the rows of ONE
+//     dilation phase (rows a, a+d, a+2d, ...): a dilated 3x3 convolution is a plain 3x3 convolution inside each phase, so
+//     every input row is loaded once per thread (its three horizontal taps x-d, x, x+d) and scattered into the three output
+//     rows it contributes to, which live in registers (a sliding window of accumulators) -- 3 loads per output instead of 9,
+//     two of them L1 hits (the row segment is shared with the neighbouring columns of the block);
+//   * weights (9 x 4 floats) and, for the weight gradient, the 9 x 4 partial sums stay in registers;
+//   * the same kernel computes the data gradient (taps flipped, dc in the role of x);
+//   * the forward can accumulate the BatchNorm statistics of its output (see dw3_fwd_kernel).
+// =================================================================================================================
+template <typename T> struct Vec4;
+template <> struct Vec4<bf16> {
+    static __device__ __forceinline__ void load(const bf16 *p, float (&v)[4]) {
+        const uint2 r = *reinterpret_cast<const uint2 *>(p);
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store(bf16 *p, const float (&v)[4]) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 r;
+        r.x = *reinterpret_cast<uint32_t *>(&a); r.y = *reinterpret_cast<uint32_t *>(&b);
+        *reinterpret_cast<uint2 *>(p) = r;
+    }
+};
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) {
+        const float4 a = *reinterpret_cast<const float4 *>(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+struct Dw4Geom { int cq, xt, chunks, xtiles, nseg, rseg; };
+
+inline Dw4Geom dw4_geom(int c, int w, int h, int dil) {
+    Dw4Geom g;
+    const int quads = c >> 2;
+    g.cq = 1;
+    for (int d = 1; d <= 32 && d <= quads; ++d)
+        if (quads % d == 0) g.cq = d;               // largest divisor of the quad count that is <= 32 (64-byte .. 256-byte pixel segments)
+    g.xt = 256 / g.cq;
+    if (g.xt > w) g.xt = w;
+    g.chunks = quads / g.cq;
+    g.xtiles = (w + g.xt - 1) / g.xt;
+    const int nj = (h + dil - 1) / dil;              // rows of one phase
+    g.rseg = 32;
+    g.nseg = (nj + g.rseg - 1) / g.rseg;
+    return g;
+}
+
+// y[oy][ox][c] = b[c] + sum_{tr,tc} w[tr][tc][c] * x[oy + (tr-1) d][ox + (tc-1) d][c]      (FLIP: w[2-tr][2-tc], no bias: data gradient)
+template <typename T, bool FLIP>
+__global__ void __launch_bounds__(256) dw4_s1_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ w_t, const float *__restrict__ bias,
+                                                     T *__restrict__ y, int y_cstride, double *__restrict__ bn_sums,
+                                                     int n, int h, int w, int c, int dil, int cq, int xt, int nseg, int rseg) {
+    __shared__ float s_stat[256][2];
+    const int ql = static_cast<int>(threadIdx.x) % cq, xl = static_cast<int>(threadIdx.x) / cq;
+    const int ch = (blockIdx.x * cq + ql) * 4, ox = blockIdx.y * xt + xl;
+    const bool active = xl < xt && ox < w;
+    int z = blockIdx.z;
+    const int seg = z % nseg; z /= nseg;
+    const int a = z % dil, nn = z / dil;
+    float wt[3][3][4], bs[4], st_s[4], st_q[4];
+#pragma unroll
+    for (int tr = 0; tr < 3; ++tr)
+#pragma unroll
+        for (int tc = 0; tc < 3; ++tc) {
+            const int tap = FLIP ? (2 - tr) * 3 + (2 - tc) : tr * 3 + tc;
+            Vec4<T>::load(w_t + static_cast<long long>(tap) * c + ch, wt[tr][tc]);
+        }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bs[j] = (bias && !FLIP) ? bias[ch + j] : 0.f; st_s[j] = 0.f; st_q[j] = 0.f; }
+    if (active) {
+        const int nj = (h - a + dil - 1) / dil;                        // rows of this phase: iy = a + dil * i, i in [0, nj)
+        const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);            // output sub-rows of this segment
+        const bool cl = ox - dil >= 0, cr = ox + dil < w;
+        const T *xb = x + static_cast<long long>(nn) * h * w * x_cstride + ch;
+        T *yb = y + static_cast<long long>(nn) * h * w * y_cstride + ch;
+        float acc0[4], acc1[4];                                        // output sub-rows i-1 and i while input sub-row i is processed
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+        for (int i = max(j0 - 1, 0); i < min(j1 + 1, nj); ++i) {
+            const int iy = a + dil * i;
+            const T *xr = xb + (static_cast<long long>(iy) * w + ox) * x_cstride;
+            float xv[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { xv[0][j] = 0.f; xv[2][j] = 0.f; }
+            Vec4<T>::load(xr, xv[1]);
+            if (cl) Vec4<T>::load(xr - static_cast<long long>(dil) * x_cstride, xv[0]);
+            if (cr) Vec4<T>::load(xr + static_cast<long long>(dil) * x_cstride, xv[2]);
+            float acc2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // input row i is tap row 2 of output i-1, tap row 1 of output i, tap row 0 of output i+1
+                acc0[j] = fmaf(wt[2][0][j], xv[0][j], fmaf(wt[2][1][j], xv[1][j], fmaf(wt[2][2][j], xv[2][j], acc0[j])));
+                acc1[j] = fmaf(wt[1][0][j], xv[0][j], fmaf(wt[1][1][j], xv[1][j], fmaf(wt[1][2][j], xv[2][j], acc1[j])));
+                acc2[j] = fmaf(wt[0][0][j], xv[0][j], fmaf(wt[0][1][j], xv[1][j], wt[0][2][j] * xv[2][j]));
+            }
+            // output sub-row i-1 is complete unless input row i was the last of the phase (then i is complete too, below)
+            if (i - 1 >= j0) {
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = acc0[j] + bs[j];
+                Vec4<T>::store(yb + (static_cast<long long>(a + dil * (i - 1)) * w + ox) * y_cstride, o);
+                if (bn_sums != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float r = to_f32(from_f32<T>(o[j])); st_s[j] += r; st_q[j] = fmaf(r, r, st_q[j]); }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc0[j] = acc1[j]; acc1[j] = acc2[j]; }
+        }
+        // the loop stopped at input row min(j1, nj - 1): output row j1 - 1 (now in acc0) still misses nothing iff j1 == nj
+        // (no row below) -- otherwise it received its bottom tap from input row j1 inside the loop and was stored there
+        if (j1 == nj && j1 - 1 >= j0 && j1 - 1 >= max(j0 - 1, 0)) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = acc0[j] + bs[j];
+            Vec4<T>::store(yb + (static_cast<long long>(a + dil * (j1 - 1)) * w + ox) * y_cstride, o);
+            if (bn_sums != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float r = to_f32(from_f32<T>(o[j])); st_s[j] += r; st_q[j] = fmaf(r, r, st_q[j]); }
+            }
+        }
+    }
+    if (bn_sums != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __syncthreads();
+            s_stat[threadIdx.x][0] = active ? st_s[j] : 0.f;
+            s_stat[threadIdx.x][1] = active ? st_q[j] : 0.f;
+            __syncthreads();
+            for (int col = threadIdx.x; col < cq * 2; col += 256) {
+                const int cql = col >> 1, q = col & 1;
+                float tot = 0.f;
+                for (int l = 0; l < xt; ++l) tot += s_stat[l * cq + cql][q];
+                atomicAdd(bn_sums + static_cast<long long>(q) * c + (blockIdx.x * cq + cql) * 4 + j, static_cast<double>(tot));
+            }
+        }
+    }
+}
+
+// dw[c][tr][tc] += sum_{oy,ox} dc[oy][ox][c] * x[oy + (tr-1) d][ox + (tc-1) d][c]
+template <typename T>
+__global__ void __launch_bounds__(256) dw4_s1_wgrad_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ dc, int dc_cstride,
+                                                           float *__restrict__ dw, int n, int h, int w, int c, int dil, int cq, int xt, int nseg, int rseg) {
+    __shared__ float s_red[256][9];
+    const int ql = static_cast<int>(threadIdx.x) % cq, xl = static_cast<int>(threadIdx.x) / cq;
+    const int ch = (blockIdx.x * cq + ql) * 4, ox = blockIdx.y * xt + xl;
+    const bool active = xl < xt && ox < w;
+    int z = blockIdx.z;
+    const int seg = z % nseg; z /= nseg;
+    const int a = z % dil, nn = z / dil;
+    float acc[3][3][4];
+#pragma unroll
+    for (int tr = 0; tr < 3; ++tr)
+#pragma unroll
+        for (int tc = 0; tc < 3; ++tc)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[tr][tc][j] = 0.f;
+    if (active) {
+        const int nj = (h - a + dil - 1) / dil;
+        const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);
+        const bool cl = ox - dil >= 0, cr = ox + dil < w;
+        const T *xb = x + static_cast<long long>(nn) * h * w * x_cstride + ch;
+        const T *db = dc + static_cast<long long>(nn) * h * w * dc_cstride + ch;
+        // x rows i-1, i, i+1 of the phase in a sliding window (unpacked): every x row is loaded once
+        float xw[3][3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int tc = 0; tc < 3; ++tc)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xw[r][tc][j] = 0.f;
+        auto load_row = [&](int i, float (&dst)[3][4]) {
+#pragma unroll
+            for (int tc = 0; tc < 3; ++tc)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[tc][j] = 0.f;
+            if (i < 0 || i >= nj) return;
+            const T *xr = xb + (static_cast<long long>(a + dil * i) * w + ox) * x_cstride;
+            Vec4<T>::load(xr, dst[1]);
+            if (cl) Vec4<T>::load(xr - static_cast<long long>(dil) * x_cstride, dst[0]);
+            if (cr) Vec4<T>::load(xr + static_cast<long long>(dil) * x_cstride, dst[2]);
+        };
+        load_row(j0 - 1, xw[0]);
+        load_row(j0, xw[1]);
+        for (int i = j0; i < j1; ++i) {
+            load_row(i + 1, xw[2]);
+            float dv[4];
+            Vec4<T>::load(db + (static_cast<long long>(a + dil * i) * w + ox) * dc_cstride, dv);
+#pragma unroll
+            for (int tr = 0; tr < 3; ++tr)
+#pragma unroll
+                for (int tc = 0; tc < 3; ++tc)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[tr][tc][j] = fmaf(dv[j], xw[tr][tc][j], acc[tr][tc][j]);
+#pragma unroll
+            for (int tc = 0; tc < 3; ++tc)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { xw[0][tc][j] = xw[1][tc][j]; xw[1][tc][j] = xw[2][tc][j]; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) s_red[threadIdx.x][tap] = active ? acc[tap / 3][tap % 3][j] : 0.f;
+        __syncthreads();
+        for (int col = threadIdx.x; col < cq * 9; col += 256) {
+            const int cql = col / 9, tap = col - cql * 9;
+            float tot = 0.f;
+            for (int l = 0; l < xt; ++l) tot += s_red[l * cq + cql][tap];
+            atomicAdd(dw + static_cast<long long>((blockIdx.x * cq + cql) * 4 + j) * 9 + tap, tot);
+        }
+    }
+}
+
+bool dw4_ok(const pcb_conv *c) {
+    return c->kh == 3 && c->kw == 3 && c->stride == 1 && c->pad_h == c->dil && c->pad_w == c->dil && c->plain && c->parts[0].mask == nullptr &&
+           c->cin % 4 == 0 && !getenv("PCB_DW_GEN2") && !getenv("PCB_DW_GEN1");
+}
+
 template <typename T>
 __global__ void dw_weight_transpose_kernel(const float *__restrict__ wm, int c, int taps, T *__restrict__ w_t) {
     const long long total = static_cast<long long>(c) * taps;
@@ -444,6 +672,14 @@ int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *
     fill(P, c);
     P.y_cstride = y_cstride;
     P.msum = msum;       // plain mode: mask_sums wrote 1.0 everywhere, so the same epilogue applies
+    if (dw4_ok(c)) {
+        const Dw4Geom g = dw4_geom(c->cin, c->w, c->h, c->dil);
+        const dim3 grid(g.chunks, g.xtiles, c->n * c->dil * g.nseg);
+        if (c->dtype == PCB_BF16) dw4_s1_kernel<bf16, false><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const bf16 *>(w_t), bias, static_cast<bf16 *>(y), y_cstride, bn_sums, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        else dw4_s1_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<const float *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const float *>(w_t), bias, static_cast<float *>(y), y_cstride, bn_sums, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     if (c->kh == 3 && c->kw == 3 && !getenv("PCB_DW_GEN1")) {
         const Dw3Geom g = dw3_geom(c->cin);
         const dim3 grid(g.chunks, (c->n * c->ho + DW3_ROWS - 1) / DW3_ROWS);
@@ -465,6 +701,14 @@ int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *
 int pcb_dw_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_t, void *dx, int dx_cstride, cudaStream_t st) {
     DwParams P;
     fill(P, c);
+    if (dw4_ok(c)) {                                      // stride 1, pad == dil: the data gradient is the same convolution with flipped taps
+        const Dw4Geom g = dw4_geom(c->cin, c->w, c->h, c->dil);
+        const dim3 grid(g.chunks, g.xtiles, c->n * c->dil * g.nseg);
+        if (c->dtype == PCB_BF16) dw4_s1_kernel<bf16, true><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(dc), dc_cstride, static_cast<const bf16 *>(w_t), nullptr, static_cast<bf16 *>(dx), dx_cstride, nullptr, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        else dw4_s1_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<const float *>(dc), dc_cstride, static_cast<const float *>(w_t), nullptr, static_cast<float *>(dx), dx_cstride, nullptr, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     if (c->kh == 3 && c->kw == 3 && (c->stride & (c->stride - 1)) == 0 && !getenv("PCB_DW_GEN1")) {
         const Dw3Geom g = dw3_geom(c->cin);
         const dim3 grid(g.chunks, (c->n * c->h + DW3_ROWS - 1) / DW3_ROWS);
@@ -490,6 +734,14 @@ int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, b
     fill(P, c);
     const int taps = c->kh * c->kw;
     if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cin * taps, st));
+    if (dw4_ok(c)) {
+        const Dw4Geom g = dw4_geom(c->cin, c->w, c->h, c->dil);
+        const dim3 grid(g.chunks, g.xtiles, c->n * c->dil * g.nseg);
+        if (c->dtype == PCB_BF16) dw4_s1_wgrad_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const bf16 *>(dc), dc_cstride, dw, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        else dw4_s1_wgrad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const float *>(dc), dc_cstride, dw, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        PCB_LAUNCH_CHECK();
+        return 0;
+    }
     if (c->kh == 3 && c->kw == 3 && !getenv("PCB_DW_GEN1")) {
         const Dw3Geom g = dw3_geom(c->cin);
         // about two resident waves of blocks; every block ends with cvb * 72 atomics

@@ -477,7 +477,7 @@ __global__ void renorm_bwd_kernel(const T *__restrict__ dy, int dys, const float
         const long long row = i / dcs;
         const int ch = static_cast<int>(i - row * dcs);
         if (ch >= c) { dc[i] = from_f32<T>(0.f); continue; }
-        const float s = msum[(mg == 1 ? 0 : (ch / cog)) * count + row];
+        const float s = msum ? msum[(mg == 1 ? 0 : (ch / cog)) * count + row] : 1.f;     // null: plain convolution
         const float g = to_f32(dy[row * dys + ch]);
         float d, gb;
         if (no_guard) { d = g / s; gb = (d - d) + g; }      // reference: g/s - g/s + g  (NaN where s == 0, like autograd there)
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(EW_THREADS) renorm_bwd_pixel8_kernel(const T *
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll 4
     for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < count; row += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float s = msum[row];
+        const float s = msum ? msum[row] : 1.f;
         float g[8], d[8];
         if (dys == 8) Vec8<T>::load(dy + row * 8, g);
         else {
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(EW_THREADS) renorm_bwd_vec_kernel(const T *__r
     if (r < rpb) {
 #pragma unroll 4
         for (long long row = static_cast<long long>(blockIdx.x) * rpb + r; row < count; row += static_cast<long long>(gridDim.x) * rpb) {
-            const float s = msum[row];
+            const float s = msum ? msum[row] : 1.f;
             float g[8], d[8];
             Vec8<T>::load(dy + row * dys + v * 8, g);
 #pragma unroll
@@ -882,7 +882,8 @@ extern "C" __attribute__((visibility("default"))) int pcb_bn_act_backward_apply_
 }
 
 extern "C" __attribute__((visibility("default"))) int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, int dy_cstride, const float *msum, void *dc, int dc_cstride, float *dbias, pcb_stream_t stream) {
-    PCB_CHECK(c && dy && msum && dc && dy_cstride >= c->cout && dc_cstride >= c->cout, "pcb_pconv_renorm_backward: bad arguments");
+    PCB_CHECK(c && dy && (msum || c->plain) && dc && dy_cstride >= c->cout && dc_cstride >= c->cout, "pcb_pconv_renorm_backward: bad arguments");
+    if (c->plain) msum = nullptr;                         // ordinary convolution: renormaliser 1 (the forward never wrote msum)
     const long long count = static_cast<long long>(c->n) * c->ho * c->wo;
     const int mg = (c->groups > 1 && !c->same_holes) ? c->groups : 1;
     if (dbias) PCB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, ST));
