@@ -426,7 +426,25 @@ template <> struct Vec4<float> {
     static __device__ __forceinline__ void store(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
 
-struct Dw4Geom { int cq, xt, chunks, xtiles, nseg, rseg; };
+// raw (still packed) 4-channel vector: loaded early, unpacked at use -- a queue of these keeps several rows of loads in flight
+template <typename T> struct Raw4;
+template <> struct Raw4<bf16> {
+    uint2 r;
+    __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
+    __device__ __forceinline__ void load(const bf16 *p) { r = __ldg(reinterpret_cast<const uint2 *>(p)); }
+    __device__ __forceinline__ void unpack(float (&v)[4]) const {
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+};
+template <> struct Raw4<float> {
+    float4 r;
+    __device__ __forceinline__ void zero() { r = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load(const float *p) { r = __ldg(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void unpack(float (&v)[4]) const { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+
+struct Dw4Geom { int cq, xt, chunks, xtiles, nseg, rseg, pgroups, ppb; };
 
 inline Dw4Geom dw4_geom(int c, int w, int h, int dil) {
     Dw4Geom g;
@@ -441,21 +459,28 @@ inline Dw4Geom dw4_geom(int c, int w, int h, int dil) {
     const int nj = (h + dil - 1) / dil;              // rows of one phase
     g.rseg = 32;
     g.nseg = (nj + g.rseg - 1) / g.rseg;
+    // a block walks `ppb` dilation phases one after the other (short phases -- large dilation -- would otherwise make blocks
+    // of a few rows whose weight loads and statistics flush dominate): about 32 rows of work per thread
+    g.ppb = 1;
+    while (g.ppb * 2 <= dil && g.ppb * 2 * nj <= 32 && dil % (g.ppb * 2) == 0) g.ppb *= 2;
+    g.pgroups = dil / g.ppb;
     return g;
 }
 
 // y[oy][ox][c] = b[c] + sum_{tr,tc} w[tr][tc][c] * x[oy + (tr-1) d][ox + (tc-1) d][c]      (FLIP: w[2-tr][2-tc], no bias: data gradient)
+constexpr int DW4_Q = 4;                            // rows of loads in flight per thread (queue of raw vectors)
 template <typename T, bool FLIP>
-__global__ void __launch_bounds__(256) dw4_s1_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ w_t, const float *__restrict__ bias,
-                                                     T *__restrict__ y, int y_cstride, double *__restrict__ bn_sums,
-                                                     int n, int h, int w, int c, int dil, int cq, int xt, int nseg, int rseg) {
+__global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ w_t, const float *__restrict__ bias,
+                                                        T *__restrict__ y, int y_cstride, double *__restrict__ bn_sums,
+                                                        int n, int h, int w, int c, int dil, int cq, int xt, int nseg, int rseg, int ppb) {
     __shared__ float s_stat[256][2];
     const int ql = static_cast<int>(threadIdx.x) % cq, xl = static_cast<int>(threadIdx.x) / cq;
     const int ch = (blockIdx.x * cq + ql) * 4, ox = blockIdx.y * xt + xl;
     const bool active = xl < xt && ox < w;
     int z = blockIdx.z;
     const int seg = z % nseg; z /= nseg;
-    const int a = z % dil, nn = z / dil;
+    const int pgroups = dil / ppb;
+    const int pg = z % pgroups, nn = z / pgroups;
     float wt[3][3][4], bs[4], st_s[4], st_q[4];
 #pragma unroll
     for (int tr = 0; tr < 3; ++tr)
@@ -467,56 +492,63 @@ __global__ void __launch_bounds__(256) dw4_s1_kernel(const T *__restrict__ x, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) { bs[j] = (bias && !FLIP) ? bias[ch + j] : 0.f; st_s[j] = 0.f; st_q[j] = 0.f; }
     if (active) {
-        const int nj = (h - a + dil - 1) / dil;                        // rows of this phase: iy = a + dil * i, i in [0, nj)
-        const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);            // output sub-rows of this segment
         const bool cl = ox - dil >= 0, cr = ox + dil < w;
         const T *xb = x + static_cast<long long>(nn) * h * w * x_cstride + ch;
         T *yb = y + static_cast<long long>(nn) * h * w * y_cstride + ch;
-        float acc0[4], acc1[4];                                        // output sub-rows i-1 and i while input sub-row i is processed
+        const long long xoff_l = -static_cast<long long>(dil) * x_cstride, xoff_r = static_cast<long long>(dil) * x_cstride;
+        for (int a = pg * ppb; a < (pg + 1) * ppb; ++a) {
+            const int nj = (h - a + dil - 1) / dil;                    // rows of this phase: iy = a + dil * i, i in [0, nj)
+            const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);        // output sub-rows of this segment
+            const int i_lo = max(j0 - 1, 0), i_hi = min(j1 + 1, nj);   // input sub-rows [i_lo, i_hi)
+            if (j0 >= nj) continue;
+            Raw4<T> q[DW4_Q][3];
+            auto fetch = [&](int i, Raw4<T> (&dst)[3]) {
+                dst[0].zero(); dst[1].zero(); dst[2].zero();
+                if (i >= i_hi) return;
+                const T *xr = xb + (static_cast<long long>(a + dil * i) * w + ox) * x_cstride;
+                dst[1].load(xr);
+                if (cl) dst[0].load(xr + xoff_l);
+                if (cr) dst[2].load(xr + xoff_r);
+            };
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-        for (int i = max(j0 - 1, 0); i < min(j1 + 1, nj); ++i) {
-            const int iy = a + dil * i;
-            const T *xr = xb + (static_cast<long long>(iy) * w + ox) * x_cstride;
-            float xv[3][4];
+            for (int k = 0; k < DW4_Q; ++k) fetch(i_lo + k, q[k]);
+            float acc0[4], acc1[4];                                    // output sub-rows i-1 and i while input sub-row i is processed
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { xv[0][j] = 0.f; xv[2][j] = 0.f; }
-            Vec4<T>::load(xr, xv[1]);
-            if (cl) Vec4<T>::load(xr - static_cast<long long>(dil) * x_cstride, xv[0]);
-            if (cr) Vec4<T>::load(xr + static_cast<long long>(dil) * x_cstride, xv[2]);
-            float acc2[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // input row i is tap row 2 of output i-1, tap row 1 of output i, tap row 0 of output i+1
-                acc0[j] = fmaf(wt[2][0][j], xv[0][j], fmaf(wt[2][1][j], xv[1][j], fmaf(wt[2][2][j], xv[2][j], acc0[j])));
-                acc1[j] = fmaf(wt[1][0][j], xv[0][j], fmaf(wt[1][1][j], xv[1][j], fmaf(wt[1][2][j], xv[2][j], acc1[j])));
-                acc2[j] = fmaf(wt[0][0][j], xv[0][j], fmaf(wt[0][1][j], xv[1][j], wt[0][2][j] * xv[2][j]));
-            }
-            // output sub-row i-1 is complete unless input row i was the last of the phase (then i is complete too, below)
-            if (i - 1 >= j0) {
+            for (int j = 0; j < 4; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+            auto emit = [&](int jrow, const float (&accv)[4]) {
                 float o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = acc0[j] + bs[j];
-                Vec4<T>::store(yb + (static_cast<long long>(a + dil * (i - 1)) * w + ox) * y_cstride, o);
+                for (int j = 0; j < 4; ++j) o[j] = accv[j] + bs[j];
+                Vec4<T>::store(yb + (static_cast<long long>(a + dil * jrow) * w + ox) * y_cstride, o);
                 if (bn_sums != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { const float r = to_f32(from_f32<T>(o[j])); st_s[j] += r; st_q[j] = fmaf(r, r, st_q[j]); }
                 }
+            };
+            for (int i0 = i_lo; i0 < i_hi; i0 += DW4_Q) {
+#pragma unroll
+                for (int k = 0; k < DW4_Q; ++k) {
+                    const int i = i0 + k;
+                    if (i < i_hi) {
+                        float xv[3][4];
+                        q[k][0].unpack(xv[0]); q[k][1].unpack(xv[1]); q[k][2].unpack(xv[2]);
+                        fetch(i + DW4_Q, q[k]);                        // refill the slot: DW4_Q rows of loads stay in flight
+                        float acc2[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // input row i is tap row 2 of output i-1, tap row 1 of output i, tap row 0 of output i+1
+                            acc0[j] = fmaf(wt[2][0][j], xv[0][j], fmaf(wt[2][1][j], xv[1][j], fmaf(wt[2][2][j], xv[2][j], acc0[j])));
+                            acc1[j] = fmaf(wt[1][0][j], xv[0][j], fmaf(wt[1][1][j], xv[1][j], fmaf(wt[1][2][j], xv[2][j], acc1[j])));
+                            acc2[j] = fmaf(wt[0][0][j], xv[0][j], fmaf(wt[0][1][j], xv[1][j], wt[0][2][j] * xv[2][j]));
+                        }
+                        if (i - 1 >= j0) emit(i - 1, acc0);            // complete: it just received its bottom tap row
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { acc0[j] = acc1[j]; acc1[j] = acc2[j]; }
+                    }
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { acc0[j] = acc1[j]; acc1[j] = acc2[j]; }
-        }
-        // the loop stopped at input row min(j1, nj - 1): output row j1 - 1 (now in acc0) still misses nothing iff j1 == nj
-        // (no row below) -- otherwise it received its bottom tap from input row j1 inside the loop and was stored there
-        if (j1 == nj && j1 - 1 >= j0 && j1 - 1 >= max(j0 - 1, 0)) {
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = acc0[j] + bs[j];
-            Vec4<T>::store(yb + (static_cast<long long>(a + dil * (j1 - 1)) * w + ox) * y_cstride, o);
-            if (bn_sums != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float r = to_f32(from_f32<T>(o[j])); st_s[j] += r; st_q[j] = fmaf(r, r, st_q[j]); }
-            }
+            // the last input row of the PHASE has no row below it: its own output (now in acc0) is complete as well
+            if (j1 == nj && j1 - 1 >= j0) emit(j1 - 1, acc0);
         }
     }
     if (bn_sums != nullptr) {
@@ -527,10 +559,10 @@ __global__ void __launch_bounds__(256) dw4_s1_kernel(const T *__restrict__ x, in
             s_stat[threadIdx.x][1] = active ? st_q[j] : 0.f;
             __syncthreads();
             for (int col = threadIdx.x; col < cq * 2; col += 256) {
-                const int cql = col >> 1, q = col & 1;
+                const int cql = col >> 1, qq = col & 1;
                 float tot = 0.f;
-                for (int l = 0; l < xt; ++l) tot += s_stat[l * cq + cql][q];
-                atomicAdd(bn_sums + static_cast<long long>(q) * c + (blockIdx.x * cq + cql) * 4 + j, static_cast<double>(tot));
+                for (int l = 0; l < xt; ++l) tot += s_stat[l * cq + cql][qq];
+                atomicAdd(bn_sums + static_cast<long long>(qq) * c + (blockIdx.x * cq + cql) * 4 + j, static_cast<double>(tot));
             }
         }
     }
@@ -538,15 +570,17 @@ __global__ void __launch_bounds__(256) dw4_s1_kernel(const T *__restrict__ x, in
 
 // dw[c][tr][tc] += sum_{oy,ox} dc[oy][ox][c] * x[oy + (tr-1) d][ox + (tc-1) d][c]
 template <typename T>
-__global__ void __launch_bounds__(256) dw4_s1_wgrad_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ dc, int dc_cstride,
-                                                           float *__restrict__ dw, int n, int h, int w, int c, int dil, int cq, int xt, int nseg, int rseg) {
+__global__ void __launch_bounds__(256, 2) dw4_s1_wgrad_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ dc, int dc_cstride,
+                                                              float *__restrict__ dw, int n, int h, int w, int c, int dil, int cq, int xt, int nseg, int rseg,
+                                                              int ppb) {
     __shared__ float s_red[256][9];
     const int ql = static_cast<int>(threadIdx.x) % cq, xl = static_cast<int>(threadIdx.x) / cq;
     const int ch = (blockIdx.x * cq + ql) * 4, ox = blockIdx.y * xt + xl;
     const bool active = xl < xt && ox < w;
     int z = blockIdx.z;
     const int seg = z % nseg; z /= nseg;
-    const int a = z % dil, nn = z / dil;
+    const int pgroups = dil / ppb;
+    const int pg = z % pgroups, nn = z / pgroups;
     float acc[3][3][4];
 #pragma unroll
     for (int tr = 0; tr < 3; ++tr)
@@ -555,46 +589,68 @@ __global__ void __launch_bounds__(256) dw4_s1_wgrad_kernel(const T *__restrict__
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[tr][tc][j] = 0.f;
     if (active) {
-        const int nj = (h - a + dil - 1) / dil;
-        const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);
         const bool cl = ox - dil >= 0, cr = ox + dil < w;
         const T *xb = x + static_cast<long long>(nn) * h * w * x_cstride + ch;
         const T *db = dc + static_cast<long long>(nn) * h * w * dc_cstride + ch;
-        // x rows i-1, i, i+1 of the phase in a sliding window (unpacked): every x row is loaded once
-        float xw[3][3][4];
+        const long long xoff_l = -static_cast<long long>(dil) * x_cstride, xoff_r = static_cast<long long>(dil) * x_cstride;
+        for (int a = pg * ppb; a < (pg + 1) * ppb; ++a) {
+            const int nj = (h - a + dil - 1) / dil;
+            const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);
+            if (j0 >= nj) continue;
+            // queue slot k holds the raw x row (i + 1) (three taps) and the raw dc row i of a future step: DW4_Q rows in flight
+            Raw4<T> qx[DW4_Q][3], qd[DW4_Q];
+            auto fetch = [&](int i, Raw4<T> (&dx3)[3], Raw4<T> &dd) {      // x row i + 1 and dc row i
+                dx3[0].zero(); dx3[1].zero(); dx3[2].zero(); dd.zero();
+                if (i >= j1) return;
+                dd.load(db + (static_cast<long long>(a + dil * i) * w + ox) * dc_cstride);
+                if (i + 1 < nj) {
+                    const T *xr = xb + (static_cast<long long>(a + dil * (i + 1)) * w + ox) * x_cstride;
+                    dx3[1].load(xr);
+                    if (cl) dx3[0].load(xr + xoff_l);
+                    if (cr) dx3[2].load(xr + xoff_r);
+                }
+            };
+            // x rows j0-1 and j0 of the phase (unpacked sliding window rows 0 and 1)
+            float xw[3][3][4];
+            {
+                Raw4<T> t3[3];
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int i = j0 - 1 + rr;
+                    t3[0].zero(); t3[1].zero(); t3[2].zero();
+                    if (i >= 0 && i < nj) {
+                        const T *xr = xb + (static_cast<long long>(a + dil * i) * w + ox) * x_cstride;
+                        t3[1].load(xr);
+                        if (cl) t3[0].load(xr + xoff_l);
+                        if (cr) t3[2].load(xr + xoff_r);
+                    }
+                    if (rr == 0) { t3[0].unpack(xw[0][0]); t3[1].unpack(xw[0][1]); t3[2].unpack(xw[0][2]); }
+                    else { t3[0].unpack(xw[1][0]); t3[1].unpack(xw[1][1]); t3[2].unpack(xw[1][2]); }
+                }
+            }
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < DW4_Q; ++k) fetch(j0 + k, qx[k], qd[k]);
+            for (int i0 = j0; i0 < j1; i0 += DW4_Q) {
 #pragma unroll
-            for (int tc = 0; tc < 3; ++tc)
+                for (int k = 0; k < DW4_Q; ++k) {
+                    const int i = i0 + k;
+                    if (i < j1) {
+                        float dv[4];
+                        qx[k][0].unpack(xw[2][0]); qx[k][1].unpack(xw[2][1]); qx[k][2].unpack(xw[2][2]);
+                        qd[k].unpack(dv);
+                        fetch(i + DW4_Q, qx[k], qd[k]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xw[r][tc][j] = 0.f;
-        auto load_row = [&](int i, float (&dst)[3][4]) {
+                        for (int tr = 0; tr < 3; ++tr)
 #pragma unroll
-            for (int tc = 0; tc < 3; ++tc)
+                            for (int tc = 0; tc < 3; ++tc)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[tc][j] = 0.f;
-            if (i < 0 || i >= nj) return;
-            const T *xr = xb + (static_cast<long long>(a + dil * i) * w + ox) * x_cstride;
-            Vec4<T>::load(xr, dst[1]);
-            if (cl) Vec4<T>::load(xr - static_cast<long long>(dil) * x_cstride, dst[0]);
-            if (cr) Vec4<T>::load(xr + static_cast<long long>(dil) * x_cstride, dst[2]);
-        };
-        load_row(j0 - 1, xw[0]);
-        load_row(j0, xw[1]);
-        for (int i = j0; i < j1; ++i) {
-            load_row(i + 1, xw[2]);
-            float dv[4];
-            Vec4<T>::load(db + (static_cast<long long>(a + dil * i) * w + ox) * dc_cstride, dv);
+                                for (int j = 0; j < 4; ++j) acc[tr][tc][j] = fmaf(dv[j], xw[tr][tc][j], acc[tr][tc][j]);
 #pragma unroll
-            for (int tr = 0; tr < 3; ++tr)
+                        for (int tc = 0; tc < 3; ++tc)
 #pragma unroll
-                for (int tc = 0; tc < 3; ++tc)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[tr][tc][j] = fmaf(dv[j], xw[tr][tc][j], acc[tr][tc][j]);
-#pragma unroll
-            for (int tc = 0; tc < 3; ++tc)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { xw[0][tc][j] = xw[1][tc][j]; xw[1][tc][j] = xw[2][tc][j]; }
+                            for (int j = 0; j < 4; ++j) { xw[0][tc][j] = xw[1][tc][j]; xw[1][tc][j] = xw[2][tc][j]; }
+                    }
+                }
+            }
         }
     }
 #pragma unroll
@@ -674,9 +730,9 @@ int pcb_dw_forward(const pcb_conv *c, const void *w_t, const float *bias, void *
     P.msum = msum;       // plain mode: mask_sums wrote 1.0 everywhere, so the same epilogue applies
     if (dw4_ok(c)) {
         const Dw4Geom g = dw4_geom(c->cin, c->w, c->h, c->dil);
-        const dim3 grid(g.chunks, g.xtiles, c->n * c->dil * g.nseg);
-        if (c->dtype == PCB_BF16) dw4_s1_kernel<bf16, false><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const bf16 *>(w_t), bias, static_cast<bf16 *>(y), y_cstride, bn_sums, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
-        else dw4_s1_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<const float *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const float *>(w_t), bias, static_cast<float *>(y), y_cstride, bn_sums, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        const dim3 grid(g.chunks, g.xtiles, c->n * g.pgroups * g.nseg);
+        if (c->dtype == PCB_BF16) dw4_s1_kernel<bf16, false><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const bf16 *>(w_t), bias, static_cast<bf16 *>(y), y_cstride, bn_sums, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg, g.ppb);
+        else dw4_s1_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<const float *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const float *>(w_t), bias, static_cast<float *>(y), y_cstride, bn_sums, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg, g.ppb);
         PCB_LAUNCH_CHECK();
         return 0;
     }
@@ -703,9 +759,9 @@ int pcb_dw_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     fill(P, c);
     if (dw4_ok(c)) {                                      // stride 1, pad == dil: the data gradient is the same convolution with flipped taps
         const Dw4Geom g = dw4_geom(c->cin, c->w, c->h, c->dil);
-        const dim3 grid(g.chunks, g.xtiles, c->n * c->dil * g.nseg);
-        if (c->dtype == PCB_BF16) dw4_s1_kernel<bf16, true><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(dc), dc_cstride, static_cast<const bf16 *>(w_t), nullptr, static_cast<bf16 *>(dx), dx_cstride, nullptr, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
-        else dw4_s1_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<const float *>(dc), dc_cstride, static_cast<const float *>(w_t), nullptr, static_cast<float *>(dx), dx_cstride, nullptr, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        const dim3 grid(g.chunks, g.xtiles, c->n * g.pgroups * g.nseg);
+        if (c->dtype == PCB_BF16) dw4_s1_kernel<bf16, true><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(dc), dc_cstride, static_cast<const bf16 *>(w_t), nullptr, static_cast<bf16 *>(dx), dx_cstride, nullptr, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg, g.ppb);
+        else dw4_s1_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<const float *>(dc), dc_cstride, static_cast<const float *>(w_t), nullptr, static_cast<float *>(dx), dx_cstride, nullptr, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg, g.ppb);
         PCB_LAUNCH_CHECK();
         return 0;
     }
@@ -736,9 +792,9 @@ int pcb_dw_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, b
     if (zero_dw) PCB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * c->cin * taps, st));
     if (dw4_ok(c)) {
         const Dw4Geom g = dw4_geom(c->cin, c->w, c->h, c->dil);
-        const dim3 grid(g.chunks, g.xtiles, c->n * c->dil * g.nseg);
-        if (c->dtype == PCB_BF16) dw4_s1_wgrad_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const bf16 *>(dc), dc_cstride, dw, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
-        else dw4_s1_wgrad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const float *>(dc), dc_cstride, dw, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg);
+        const dim3 grid(g.chunks, g.xtiles, c->n * g.pgroups * g.nseg);
+        if (c->dtype == PCB_BF16) dw4_s1_wgrad_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16 *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const bf16 *>(dc), dc_cstride, dw, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg, g.ppb);
+        else dw4_s1_wgrad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(c->parts[0].x), c->parts[0].x_cstride, static_cast<const float *>(dc), dc_cstride, dw, c->n, c->h, c->w, c->cin, c->dil, g.cq, g.xt, g.nseg, g.rseg, g.ppb);
         PCB_LAUNCH_CHECK();
         return 0;
     }
