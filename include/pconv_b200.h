@@ -121,6 +121,11 @@ int pcb_pconv_renorm_backward(const pcb_conv *c, const void *dy, int dy_cstride,
  * parts[].mask are the INPUT masks (dx is zeroed at input holes); parts[].x is not read.      */
 int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_fwd, const void *w_dgrad,
                             void *const *dx, const int32_t *dx_cstride, pcb_stream_t stream);
+/* 1 when pcb_pconv_backward_data computes the gradient of a 2x-UPSAMPLED source part (x_up == 1) directly at that source's own
+ * (half) resolution -- dx[p] is then a [n, h/2, w/2, dx_cstride] buffer and no 2x2 reduction pass follows (sub-pixel path of the
+ * tcgen05 kernels: image_inpainting.py:183-185 + partial_convolution.py:229-231 folded into the convolution).  0: dx[p] of
+ * every part is a full-resolution [n, h, w, dx_cstride] buffer and the caller reduces 2x2 blocks itself. */
+int pcb_conv_dgrad_at_source_resolution(const pcb_conv *c);
 
 /* dw[co][r][s][ci] = sum_pixels dc[p][co] * (x*m)[p@tap][ci]   (fp32 KRSC, logical/unpadded, overwritten).
  * workspace: pcb_pconv_workspace(c) bytes (may be NULL when that is 0).                         */

@@ -31,6 +31,7 @@ _SIGS = {
     "pcb_version": (c_int, []),
     "pcb_launch_count": (ctypes.c_ulonglong, []),
     "pcb_conv_uses_tensor_cores": (c_int, [ctypes.POINTER(Conv)]),
+    "pcb_conv_dgrad_at_source_resolution": (c_int, [ctypes.POINTER(Conv)]),
     "pcb_pconv_workspace": (c_size_t, [ctypes.POINTER(Conv)]),
     "pcb_conv_weight_layout": (None, [ctypes.POINTER(Conv), ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "pcb_conv_weight_prepare": (c_int, [ctypes.POINTER(Conv), c_void_p, c_void_p, c_void_p, c_void_p]),

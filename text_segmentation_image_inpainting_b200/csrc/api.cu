@@ -54,6 +54,10 @@ static bool use_tc(const pcb_conv *c) { return !c->force_generic && !use_dw(c) &
 
 PCB_API int pcb_conv_uses_tensor_cores(const pcb_conv *c) { return (c && use_tc(c)) ? 1 : 0; }
 
+// 1 when pcb_pconv_backward_data writes the gradient of a 2x-UPSAMPLED source directly at that source's own (half) resolution:
+// dx[p] of such a part is then a [n, h/2, w/2, dx_cstride] buffer and no 2x2 reduction pass follows (the tcgen05 sub-pixel path)
+PCB_API int pcb_conv_dgrad_at_source_resolution(const pcb_conv *c) { return (c && use_tc(c) && pcb_tc_subpixel(c)) ? 1 : 0; }
+
 PCB_API size_t pcb_pconv_workspace(const pcb_conv *c) { return (c && use_tc(c)) ? pcb_tc_workspace(c) : 0; }
 
 PCB_API void pcb_conv_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_elems) {

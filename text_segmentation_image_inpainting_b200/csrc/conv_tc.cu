@@ -129,17 +129,21 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                 const bool rvalid = m < P.m_total;
                 float inv = 0.f;
                 bool hole = false;
-                if (MODE == 0 && rvalid) {
-                    const float s = P.msum ? P.msum[m] : 1.f;                // null: plain convolution (renormaliser 1)
-                    hole = (s == 0.f) && !P.no_guard;
-                    inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
-                }
                 int en = 0, eh = 0, ew = 0;
-                long long mo = m;                         // dgrad: pixel index in the full-resolution gradient
+                long long mo = m;                         // pixel index in the full-resolution output (fwd) / gradient (dgrad)
                 if (MODE == 1 && rvalid) {
                     en = m / (P.h * P.w); const int rem = m - en * P.h * P.w; eh = rem / P.w; ew = rem - eh * P.w;
                     eh = eh * P.sub + P.py; ew = ew * P.sub + P.px;
                     mo = (static_cast<long long>(en) * P.fh + eh) * P.fw + ew;
+                }
+                if (MODE == 0 && rvalid && P.sub != 1) {  // sub-pixel class launch: the tile grid is every `sub`-th output pixel
+                    en = m / (P.ho * P.wo); const int rem = m - en * P.ho * P.wo; eh = rem / P.wo; ew = rem - eh * P.wo;
+                    mo = (static_cast<long long>(en) * P.fh + eh * P.sub + P.py) * P.fw + ew * P.sub + P.px;
+                }
+                if (MODE == 0 && rvalid) {
+                    const float s = P.msum ? P.msum[mo] : 1.f;               // null: plain convolution (renormaliser 1)
+                    hole = (s == 0.f) && !P.no_guard;
+                    inv = hole ? 0.f : 1.0f / s;         // no_guard: 1/0 = inf -> 0*inf = NaN like the reference
                 }
                 if (P.partial != nullptr) {                // split-K: raw accumulators, reduced across CTAs with fp32 adds
     #pragma unroll 1
@@ -165,7 +169,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                     int nstore = 0;                      // channels to store from this 32-column chunk (multiple of 8)
                     float scale = inv;
                     if (MODE == 0) {
-                        if (rvalid && col < P.y_cstride) { orow = P.y + static_cast<long long>(m) * P.y_cstride + col; nstore = min(32, P.y_cstride - col); }
+                        if (rvalid && col < P.y_cstride) { orow = P.y + mo * P.y_cstride + col; nstore = min(32, P.y_cstride - col); }
                     } else {
                         scale = 1.f;
                         for (int p = 0; p < P.nparts; ++p) {
@@ -1119,6 +1123,265 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         ptx::tc_fence_after();
         if (PAIR) ptx::tmem_dealloc_pair<TCOLS>(tmem_base);
         else ptx::tmem_dealloc<TCOLS>(tmem_base);
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// SUB-PIXEL (table-driven) variant of the TMA-fed kernel: convolutions whose input is cat([nearest-2x-upsample(x0), x1])
+// (models/image_inpainting.py:183-185) WITHOUT materialising the upsampled tensor and WITHOUT multiplying by replicated pixels.
+//
+// Output pixel (2k+py, 2j+px) of a k x k convolution over up2x(x0) reads source pixel (k + floor((py + tr*d - p)/2), ...): within
+// one parity class (py, px) the convolution over the upsampled part IS a convolution over the SOURCE with a smaller kernel whose
+// taps are sums of the original taps (3x3, pad 1: 2x2 effective taps -- 4/9 of the multiplications); the skip part x1 keeps its
+// k x k taps and is read with a traversal stride of 2.  The hole mask of the upsampled part was upsampled with it
+// (HoleMask.upsampled), so masking commutes.  One launch computes one class: its M tiles are boxes of the class grid
+// [n][h/2][w/2]; what each K step loads is listed in a small table built on the host:
+//     item = { part (tensor map), (dx, dy) added to the tile origin scaled by the part's step, nb weight tiles (taps served by
+//              one A tile through row-shifted descriptors), weight K index of the first, step between them }
+// The same kernel computes the data gradient w.r.t. x0 directly at SOURCE resolution (MODE 1): its A operand is dc read with a
+// traversal stride of 2 per (class, effective tap) item -- 16/36 of the multiplications of "full-resolution gradient + 2x2 sum",
+// and neither the full-resolution gradient nor the reduction pass exists.
+// Roles / pipeline / epilogue exactly as in pconv_tc_tma_kernel (no CTA pairs, no split-K).
+// -------------------------------------------------------------------------------------------------
+constexpr int SP_MAX_ITEMS = 40;
+struct SpItem { int part, dx, dy, wk, nb, wk_step, shift0, dshift; };
+struct SpTable {
+    int n_items;
+    int step[TC_MAX_PARTS];         // tile origin (class grid) -> part coordinates: origin * step + (dx, dy)
+    int es[TC_MAX_PARTS];           // traversal stride of the part's tensor map (pixels between consecutive tile rows)
+    int ph[TC_MAX_PARTS], pw[TC_MAX_PARTS];     // the part's own pixel grid (its mask plane has exactly this resolution)
+    int arows[TC_MAX_PARTS];        // pixel rows one TMA tile of the part delivers (128 + the halo of the part's tensor-map box)
+    int rows_max;                   // pixel rows of the largest A tile
+    SpItem it[SP_MAX_ITEMS];
+};
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+pconv_tc_sp_kernel(const __grid_constant__ TcParams P, const __grid_constant__ SpTable TB, const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
+    constexpr uint32_t B_BYTES = BLOCK_N * 128;
+    constexpr int TCOLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = align1024(ptx::smem_u32(smem_raw));
+    const int S = P.stages;
+    int nb_max = 1;
+    for (int i = 0; i < TB.n_items; ++i) nb_max = max(nb_max, TB.it[i].nb);
+    const uint32_t A_ROOM = (static_cast<uint32_t>(TB.rows_max) * 128u + 1023u) & ~1023u;
+    const uint32_t STAGE = A_ROOM + nb_max * B_BYTES;
+    const uint32_t sBar = smem_base + S * STAGE;
+    const uint32_t bar_full = sBar, bar_fixed = sBar + 8 * MAX_RING, bar_empty = sBar + 16 * MAX_RING;
+    const uint32_t bar_tmem_full = sBar + 32 * MAX_RING, bar_tmem_empty = bar_tmem_full + 16;
+    const uint32_t s_tmem_ptr = bar_tmem_empty + 16;
+    uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    uint32_t *tmem_ptr_generic = reinterpret_cast<uint32_t *>(smem_gen + (s_tmem_ptr - smem_base));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int n_tiles = P.ncols / BLOCK_N;
+    const int m_tiles = (P.m_total + BLOCK_M - 1) / BLOCK_M;
+    const int num_tiles = m_tiles * n_tiles;
+    const int tile0 = static_cast<int>(blockIdx.x), tstep = static_cast<int>(gridDim.x);
+    const bool fix = P.use_fix != 0;
+    // the tile grid: [n][gh][gw] = the class grid (MODE 0: P.ho x P.wo) or the source grid (MODE 1: P.h x P.w)
+    const int gw = (MODE == 0) ? P.wo : P.w, gh = (MODE == 0) ? P.ho : P.h;
+    const int plane = gw * gh;
+    // per part: 64-channel K blocks and the K steps of the last block that hold real channels
+    int nbk[TC_MAX_PARTS], klast[TC_MAX_PARTS];
+#pragma unroll
+    for (int p = 0; p < TC_MAX_PARTS; ++p) {
+        const int kext = (MODE == 0) ? P.parts[p].kext : P.dc_kext, c8 = (MODE == 0) ? P.parts[p].c8 : P.dc_c8;
+        nbk[p] = (p < ((MODE == 0) ? P.nparts : 1)) ? kext / BLOCK_K : 0;
+        klast[p] = nbk[p] ? min(4, (c8 - (nbk[p] - 1) * BLOCK_K + 15) >> 4) : 4;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_RING; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_fixed + 8 * s, 4); ptx::mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_tmem_full + 8 * s, 1); ptx::mbar_init(bar_tmem_empty + 8 * s, 128); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_w); ptx::prefetch_tmap(&tmap_a0); ptx::prefetch_tmap(&tmap_a1); }
+    if (warp == 1) { ptx::tmem_alloc<TCOLS>(s_tmem_ptr); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    float *s_stat = nullptr;
+    int stat_n0 = -1;
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        int s = 0;
+        uint32_t ph = 1;
+        bool dead = false;
+        for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int img = m0 / plane, rem = m0 - img * plane;
+            const int oy = rem / gw, ox = rem - oy * gw;
+            for (int i = 0; i < TB.n_items && !dead; ++i) {
+                const SpItem it = TB.it[i];
+                const CUtensorMap *ma = (it.part == 0) ? &tmap_a0 : &tmap_a1;
+                const int x = ox * TB.step[it.part] + it.dx, y = oy * TB.step[it.part] + it.dy;
+                const uint32_t a_bytes = static_cast<uint32_t>(TB.arows[it.part]) * 128u;      // what the part's box delivers
+                for (int cb = 0; cb < nbk[it.part]; ++cb) {
+                    if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_empty + 8 * s, ph, P.abort_flag, 321))) { dead = true; break; }
+                    if (ptx::elect_one()) {
+                        const uint32_t full = bar_full + 8 * s, dst = smem_base + s * STAGE;
+                        ptx::mbar_arrive_expect_tx(full, a_bytes + it.nb * B_BYTES);
+                        ptx::tma_load_4d(dst, ma, cb * BLOCK_K, x, y, img, full);
+                        uint32_t bdst = dst + A_ROOM;
+                        for (int tc = 0, kb = it.wk + cb * BLOCK_K; tc < it.nb; ++tc, kb += it.wk_step, bdst += B_BYTES)
+                            ptx::tma_load_2d(bdst, &tmap_w, kb, n0, full);
+                    }
+                    __syncwarp();
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+        const uint32_t ready = fix ? bar_fixed : bar_full;
+        const uint64_t desc_a0 = ptx::make_smem_desc(smem_base, 16, 1024);
+        const uint64_t desc_b0 = ptx::make_smem_desc(smem_base + A_ROOM, 16, 1024);
+        const uint32_t stage16 = STAGE >> 4;
+        int s = 0, tile_iter = 0;
+        uint32_t ph = 0;
+        bool dead = false;
+        for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
+            const int acc = tile_iter & 1;
+            if (!__all_sync(0xffffffffu, ptx::mbar_wait(bar_tmem_empty + 8 * acc, ((tile_iter >> 1) & 1) ^ 1, P.abort_flag, 326))) { dead = true; break; }
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t accum = 0;
+            for (int i = 0; i < TB.n_items && !dead; ++i) {
+                const SpItem it = TB.it[i];
+                for (int cb = 0; cb < nbk[it.part]; ++cb) {
+                    if (!__all_sync(0xffffffffu, ptx::mbar_wait(ready + 8 * s, ph, P.abort_flag, 324))) { dead = true; break; }
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        uint64_t da = desc_a0 + static_cast<uint64_t>(s * stage16 + it.shift0), db = desc_b0 + static_cast<uint64_t>(s * stage16);
+                        const int ksteps = (cb + 1 < nbk[it.part]) ? 4 : klast[it.part];
+                        for (int tc = 0; tc < it.nb; ++tc, da += it.dshift, db += B_BYTES >> 4)
+                            for (int k = 0; k < ksteps; ++k)
+                                ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (accum | tc | k) != 0);
+                        ptx::umma_commit(bar_empty + 8 * s);
+                    }
+                    __syncwarp();
+                    accum = 1;
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+            if (!dead && ptx::elect_one()) ptx::umma_commit(bar_tmem_full + 8 * acc);
+            __syncwarp();
+            ++tile_iter;
+        }
+    } else if (warp < 6) {
+        // ================================ fixers: zero the hole rows of every landed A tile ================================
+        if (fix) {
+            const int t = (warp - 2) * 32 + lane;
+            int s = 0;
+            uint32_t ph = 0;
+            bool dead = false;
+            // bit i of b0 / b1: row t / row t + 128 of item i's A tile is a hole (rows outside the image were zero-filled by TMA)
+            auto load_bits = [&](int tl, uint64_t &b0, uint64_t &b1) {
+                b0 = b1 = 0ull;
+                if (tl >= num_tiles) return;
+                const int m0 = (tl / n_tiles) * BLOCK_M;
+                const int img = m0 / plane, rem = m0 - img * plane;
+                const int oy = rem / gw, ox = rem - oy * gw;
+                for (int i = 0; i < TB.n_items; ++i) {
+                    const SpItem it = TB.it[i];
+                    const uint8_t *mk = P.parts[it.part].mask;
+                    if (mk == nullptr) continue;
+                    const int pwid = TB.pw[it.part], phei = TB.ph[it.part], es = TB.es[it.part];
+                    const int hrows = TB.arows[it.part] - BLOCK_M;
+                    const int x0 = ox * TB.step[it.part] + it.dx, y0 = oy * TB.step[it.part] + it.dy;
+                    int tx, ty, tn;
+                    if (hrows > 0 || (P.box_h == 1 && P.box_n == 1)) { tx = t; ty = 0; tn = 0; }
+                    else { tx = t % P.box_w; ty = (t / P.box_w) % P.box_h; tn = t / (P.box_w * P.box_h); }
+                    const int X = x0 + tx * es, Y = y0 + ty * es, IM = img + tn;
+                    if (X >= 0 && X < pwid && Y >= 0 && Y < phei && IM < P.n &&
+                        __ldg(mk + (static_cast<long long>(IM) * phei + Y) * pwid + X) == 0) b0 |= 1ull << i;
+                    if (t < hrows) {
+                        const int X1 = x0 + (t + 128) * es;
+                        if (X1 >= 0 && X1 < pwid && Y >= 0 && Y < phei && __ldg(mk + (static_cast<long long>(IM) * phei + Y) * pwid + X1) == 0) b1 |= 1ull << i;
+                    }
+                }
+            };
+            uint64_t n0b, n1b;
+            load_bits(tile0, n0b, n1b);
+            for (int tile = tile0; tile < num_tiles && !dead; tile += tstep) {
+                const uint64_t c0b = n0b, c1b = n1b;
+                load_bits(tile + tstep, n0b, n1b);
+                for (int i = 0; i < TB.n_items && !dead; ++i) {
+                    const bool h0 = (c0b >> i) & 1ull, h1 = (c1b >> i) & 1ull;
+                    const bool any_hole = __any_sync(0xffffffffu, h0 || h1);
+                    const int nb_i = nbk[TB.it[i].part];
+                    for (int cb = 0; cb < nb_i; ++cb) {
+                        if (!ptx::mbar_wait(bar_full + 8 * s, ph, P.abort_flag, 322)) { dead = true; break; }
+                        if (any_hole) {
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                            if (h0) {
+                                uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + t * 128);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) r[k] = z;
+                            }
+                            if (h1) {
+                                uint4 *r = reinterpret_cast<uint4 *>(smem_gen + s * STAGE + (t + 128) * 128);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) r[k] = z;
+                            }
+                            ptx::fence_proxy_async_smem();
+                        }
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(bar_fixed + 8 * s);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue warps (6-9) ================================
+        int tile_iter = 0;
+        s_stat = (MODE == 0 && P.bn_sums != nullptr)
+                     ? reinterpret_cast<float *>(smem_gen + (((s_tmem_ptr + 32u) & ~15u) - smem_base)) + (warp & 3) * STAT_FLOATS_PER_WARP : nullptr;
+        if (s_stat) {
+            for (int i = lane; i < STAT_FLOATS_PER_WARP; i += 32) s_stat[i] = 0.f;
+            __syncwarp();
+        }
+        for (int tile = tile0; tile < num_tiles; tile += tstep) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int acc = tile_iter & 1;
+            if (s_stat && n0 != stat_n0) {
+                if (stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
+                stat_n0 = n0;
+            }
+            if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 323)) { stat_n0 = -1; break; }
+            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0, s_stat);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
+            ++tile_iter;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (s_stat != nullptr && stat_n0 >= 0) {
+        const float *base = s_stat - (warp & 3) * STAT_FLOATS_PER_WARP;
+        for (int col = (warp & 3) * 32 + lane; col < BLOCK_N; col += 128) {
+            const int co = stat_n0 + col;
+            if (co < P.bn_c) {
+                float a = 0.f, q = 0.f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) { a += base[w4 * STAT_FLOATS_PER_WARP + col]; q += base[w4 * STAT_FLOATS_PER_WARP + 256 + col]; }
+                atomicAdd(P.bn_sums + co, static_cast<double>(a));
+                atomicAdd(P.bn_sums + P.bn_c + co, static_cast<double>(q));
+            }
+        }
+    }
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TCOLS>(tmem_base);
     }
 }
 
@@ -2152,6 +2415,313 @@ int launch_tc(TcParams &P, const CUtensorMap &tm, int bn, cudaStream_t st) {
 
 }  // namespace
 
+static bool smallco_ok(const pcb_conv *c);
+namespace {
+
+// ---- sub-pixel path: plan, weights, launches -------------------------------------------------------
+// one spatial axis: for output parity q, tap t of a (k, dilation d, padding p) kernel over the 2x-upsampled source reads source
+// offset floor((q + t*d - p) / 2); the distinct offsets e0 .. e0+ne-1 are the effective taps, tapbits[q][e] the original taps
+// that collapse onto effective tap e
+struct SpAxis { int e0[2], ne[2], tapbits[2][4]; bool ok; };
+
+int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+SpAxis sp_axis(int k, int d, int p) {
+    SpAxis A;
+    memset(&A, 0, sizeof(A));
+    A.ok = k <= 4;
+    for (int q = 0; q < 2 && A.ok; ++q) {
+        A.e0[q] = floordiv2(q - p);
+        const int last = floordiv2(q + (k - 1) * d - p);
+        A.ne[q] = last - A.e0[q] + 1;
+        if (A.ne[q] < 1 || A.ne[q] > 4) { A.ok = false; break; }
+        for (int t = 0; t < k; ++t) A.tapbits[q][floordiv2(q + t * d - p) - A.e0[q]] |= 1 << t;
+        for (int e = 0; e < A.ne[q]; ++e)
+            if (!A.tapbits[q][e]) A.ok = false;               // a gap between effective taps (dilation > 2): not handled here
+    }
+    return A;
+}
+
+struct SpPlan {
+    bool ok;
+    int pu, ps;                      // the upsampled part and the other one (-1: none)
+    SpAxis ay, ax;
+    int net[4], eoff[4], net_total;  // effective taps of the upsampled part per class (class = py * 2 + px)
+    int kext_u, kext_s, c8_u, c8_s;
+    long long kc[4], clsoff[4], sp_fwd_elems, sp_dg_elems, kd_sp;
+    int bw, bh, bn;                  // M tile box of the class grid [n][h/2][w/2]
+};
+
+SpPlan sp_plan(const pcb_conv *c) {
+    SpPlan S;
+    memset(&S, 0, sizeof(S));
+    S.pu = S.ps = -1;
+    if (getenv("PCB_DISABLE_SUBPIXEL") || getenv("PCB_DISABLE_TMA") || !common_ok(c) || is_rowpack(c)) return S;
+    if (c->stride != 1 || c->ho != c->h || c->wo != c->w || ((c->h | c->w) & 1) || c->nparts > 2) return S;
+    for (int p = 0; p < c->nparts; ++p) {
+        if (c->parts[p].x_up) { if (S.pu >= 0) return S; S.pu = p; }
+        else { if (S.ps >= 0) return S; S.ps = p; }
+    }
+    if (S.pu < 0) return S;
+    // the hole mask of each part must live at the part's own resolution (HoleMask.upsampled keeps them together)
+    if (c->parts[S.pu].mask && c->parts[S.pu].mask_up != 1) return S;
+    if (S.ps >= 0 && c->parts[S.ps].mask && c->parts[S.ps].mask_up != 0) return S;
+    if (smallco_ok(c)) return S;
+    S.ay = sp_axis(c->kh, c->dil, c->pad_h);
+    S.ax = sp_axis(c->kw, c->dil, c->pad_w);
+    if (!S.ay.ok || !S.ax.ok) return S;
+    if (!tile_box(c->w / 2, c->h / 2, &S.bw, &S.bh, &S.bn)) return S;
+    const Layout L = layout_of(c);
+    S.kext_u = L.kext[S.pu]; S.c8_u = rup(c->parts[S.pu].c, 8);
+    S.kext_s = S.ps >= 0 ? L.kext[S.ps] : 0; S.c8_s = S.ps >= 0 ? rup(c->parts[S.ps].c, 8) : 0;
+    const int taps = c->kh * c->kw;
+    long long off = 0;
+    int eo = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+        S.net[cls] = S.ay.ne[cls >> 1] * S.ax.ne[cls & 1];
+        S.eoff[cls] = eo; eo += S.net[cls];
+        S.kc[cls] = static_cast<long long>(S.net[cls]) * S.kext_u + static_cast<long long>(S.ps >= 0 ? taps : 0) * S.kext_s;
+        S.clsoff[cls] = off; off += static_cast<long long>(L.rows_f) * S.kc[cls];
+        // worst-case item count of one class launch (no halo re-use)
+        if (S.net[cls] + (S.ps >= 0 ? taps : 0) > SP_MAX_ITEMS) return S;
+    }
+    S.net_total = eo;
+    if (S.net_total > SP_MAX_ITEMS) return S;
+    S.sp_fwd_elems = off;
+    S.kd_sp = static_cast<long long>(S.net_total) * L.cout64;
+    S.sp_dg_elems = static_cast<long long>(rup(S.kext_u, 128)) * S.kd_sp;
+    S.ok = true;
+    return S;
+}
+
+struct SpWParams {
+    int cout, taps, cin, kw, cout64, rows_f;
+    int choff_u, c_u, kext_u, choff_s, c_s, kext_s, has_skip;
+    int net[4], eoff[4], nex[4], slot0[4];       // per class: eff taps, their prefix, eff columns, first slot index
+    int ybits[2][4], xbits[2][4];
+    long long kc[4], clsoff[4], kd_sp;
+};
+
+// slot = (class, effective tap of the upsampled part | original tap of the skip part); one block per (cout, slot)
+__global__ void sp_weight_prepare_kernel(const float *__restrict__ wm, const SpWParams W, bf16 *__restrict__ w_f, bf16 *__restrict__ w_d) {
+    const int co = blockIdx.x;
+    int slot = blockIdx.y, cls = 0;
+    while (cls < 3 && slot >= W.slot0[cls + 1]) ++cls;
+    slot -= W.slot0[cls];
+    const float *wrow = wm + static_cast<long long>(co) * W.taps * W.cin;
+    if (slot < W.net[cls]) {
+        const int ey = slot / W.nex[cls], ex = slot - ey * W.nex[cls];
+        const int yb = W.ybits[cls >> 1][ey], xb = W.xbits[cls & 1][ex];
+        for (int ci = threadIdx.x; ci < W.c_u; ci += blockDim.x) {
+            float v = 0.f;
+            for (int tr = 0; tr < 4; ++tr)
+                if ((yb >> tr) & 1)
+                    for (int tc = 0; tc < 4; ++tc)
+                        if ((xb >> tc) & 1) v += wrow[static_cast<long long>(tr * W.kw + tc) * W.cin + W.choff_u + ci];
+            const bf16 b = __float2bfloat16_rn(v);
+            w_f[W.clsoff[cls] + static_cast<long long>(co) * W.kc[cls] + static_cast<long long>(slot) * W.kext_u + ci] = b;
+            w_d[static_cast<long long>(ci) * W.kd_sp + static_cast<long long>(W.eoff[cls] + slot) * W.cout64 + co] = b;
+        }
+    } else if (W.has_skip) {
+        const int tap = slot - W.net[cls];
+        for (int ci = threadIdx.x; ci < W.c_s; ci += blockDim.x)
+            w_f[W.clsoff[cls] + static_cast<long long>(co) * W.kc[cls] + static_cast<long long>(W.net[cls]) * W.kext_u + static_cast<long long>(tap) * W.kext_s + ci] =
+                __float2bfloat16_rn(wrow[static_cast<long long>(tap) * W.cin + W.choff_s + ci]);
+    }
+}
+
+int sp_weight_prepare(const pcb_conv *c, const SpPlan &S, const Layout &L, const float *w_master, bf16 *w_f, bf16 *w_d, cudaStream_t st) {
+    SpWParams W;
+    memset(&W, 0, sizeof(W));
+    W.cout = c->cout; W.taps = c->kh * c->kw; W.cin = c->cin; W.kw = c->kw; W.cout64 = L.cout64; W.rows_f = L.rows_f;
+    int off = 0;
+    for (int p = 0; p < c->nparts; ++p) {
+        if (p == S.pu) { W.choff_u = off; W.c_u = c->parts[p].c; }
+        if (p == S.ps) { W.choff_s = off; W.c_s = c->parts[p].c; }
+        off += c->parts[p].c;
+    }
+    W.kext_u = S.kext_u; W.kext_s = S.kext_s; W.has_skip = S.ps >= 0; W.kd_sp = S.kd_sp;
+    int slot = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+        W.net[cls] = S.net[cls]; W.eoff[cls] = S.eoff[cls]; W.nex[cls] = S.ax.ne[cls & 1]; W.slot0[cls] = slot;
+        slot += S.net[cls] + (S.ps >= 0 ? W.taps : 0);
+        W.kc[cls] = S.kc[cls]; W.clsoff[cls] = S.clsoff[cls];
+    }
+    for (int q = 0; q < 2; ++q)
+        for (int e = 0; e < 4; ++e) { W.ybits[q][e] = S.ay.tapbits[q][e]; W.xbits[q][e] = S.ax.tapbits[q][e]; }
+    sp_weight_prepare_kernel<<<dim3(c->cout, slot), 128, 0, st>>>(w_master, W, w_f, w_d);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BLOCK_N, int MODE>
+int launch_sp_n(TcParams &P, const SpTable &TB, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, cudaStream_t st) {
+    int nb_max = 1;
+    for (int i = 0; i < TB.n_items; ++i) nb_max = std::max(nb_max, TB.it[i].nb);
+    const size_t a_room = (static_cast<size_t>(TB.rows_max) * 128 + 1023) / 1024 * 1024;
+    const size_t stage = a_room + static_cast<size_t>(nb_max) * BLOCK_N * 128;
+    P.stages = static_cast<int>(std::min<size_t>(MAX_RING, (208 * 1024) / stage));
+    PCB_CHECK(P.stages >= 2, "sub-pixel conv: stage of %zu bytes does not fit twice", stage);
+    const size_t smem = 1024 + P.stages * stage + 32 * MAX_RING + 64 + STAT_SMEM_BYTES;
+    auto kern = pconv_tc_sp_kernel<BLOCK_N, MODE>;
+    PCB_SMEM_OPT_IN(kern, 224 * 1024);
+    const int num_tiles = ((P.m_total + BLOCK_M - 1) / BLOCK_M) * (P.ncols / BLOCK_N);
+    const int grid = std::min(num_tiles, pcb_num_sms());
+    kern<<<grid, TMA_THREADS, smem, st>>>(P, TB, tw, ta0, ta1);
+    PCB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int MODE>
+int launch_sp(TcParams &P, const SpTable &TB, const CUtensorMap &tw, const CUtensorMap &ta0, const CUtensorMap &ta1, int bn, cudaStream_t st) {
+    if (bn == 256) return launch_sp_n<256, MODE>(P, TB, tw, ta0, ta1, st);
+    if (bn == 128) return launch_sp_n<128, MODE>(P, TB, tw, ta0, ta1, st);
+    if (bn == 64) return launch_sp_n<64, MODE>(P, TB, tw, ta0, ta1, st);
+    return launch_sp_n<32, MODE>(P, TB, tw, ta0, ta1, st);
+}
+
+// internal streams for the four class launches of low-resolution layers (one set per device and host thread)
+struct ClassStreams4 { cudaStream_t aux[3]; cudaEvent_t ev_fork, ev_join[3]; bool ready; };
+int class_streams(ClassStreams4 **out) {
+    static thread_local ClassStreams4 cs_all[PCB_MAX_DEVICES] = {};
+    ClassStreams4 &CS = cs_all[pcb_cur_device()];
+    if (!CS.ready) {
+        for (int i = 0; i < 3; ++i) {
+            PCB_CUDA(cudaStreamCreateWithFlags(&CS.aux[i], cudaStreamNonBlocking));
+            PCB_CUDA(cudaEventCreateWithFlags(&CS.ev_join[i], cudaEventDisableTiming));
+        }
+        PCB_CUDA(cudaEventCreateWithFlags(&CS.ev_fork, cudaEventDisableTiming));
+        CS.ready = true;
+    }
+    *out = &CS;
+    return 0;
+}
+
+// forward over cat([up2x(x_u), x_s]): four class launches (see pconv_tc_sp_kernel)
+int sp_forward(const pcb_conv *c, const SpPlan &S, const Layout &L, const bf16 *w_sp, const float *bias, void *y, int y_cstride, const float *msum,
+               double *bn_sums, int *flag, cudaStream_t st) {
+    const int hc = c->h / 2, wc = c->w / 2;
+    const long long m_class = static_cast<long long>(c->n) * hc * wc;
+    TcParams P;
+    base_params(P, c, L);
+    fill_parts(c, L, P.parts, nullptr, 0);
+    P.ho = hc; P.wo = wc; P.m_total = static_cast<int>(m_class);
+    P.sub = 2; P.fh = c->ho; P.fw = c->wo;
+    P.bias = bias; P.msum = msum; P.y = static_cast<bf16 *>(y); P.y_cstride = y_cstride; P.abort_flag = flag;
+    P.bn_sums = bn_sums; P.bn_c = c->cout;
+    P.box_w = S.bw; P.box_h = S.bh; P.box_n = S.bn;
+    const int cols = (c->cout <= 32) ? 32 : L.rows_f;
+    const int bn = pick_bn(cols, m_class);
+    P.ncols = cols;
+    for (int p = 0; p < c->nparts; ++p)
+        if (c->parts[p].mask) P.use_fix = 1;
+    const bool row_tiles = S.bw == 128 && S.bh == 1 && S.bn == 1;       // halo re-use possible for the traversal-stride-1 part
+    const int taps = c->kh * c->kw;
+    const long long class_tiles = ((m_class + BLOCK_M - 1) / BLOCK_M) * (cols / bn);
+    const bool fork = class_tiles < pcb_num_sms() && !getenv("PCB_DISABLE_CLASS_STREAMS");
+    ClassStreams4 *CS = nullptr;
+    if (fork) {
+        if (int rc = class_streams(&CS)) return rc;
+        PCB_CUDA(cudaEventRecord(CS->ev_fork, st));
+    }
+    for (int cls = 0; cls < 4; ++cls) {
+        const int py = cls >> 1, px = cls & 1;
+        const int ney = S.ay.ne[py], nex = S.ax.ne[px], ey0 = S.ay.e0[py], ex0 = S.ax.e0[px];
+        SpTable TB;
+        memset(&TB, 0, sizeof(TB));
+        const int pu = S.pu, ps = S.ps;
+        TB.step[pu] = 1; TB.es[pu] = 1; TB.ph[pu] = hc; TB.pw[pu] = wc;
+        const bool halo_u = row_tiles && nex > 1 && !getenv("PCB_DISABLE_TMA_HALO");
+        TB.arows[pu] = BLOCK_M + (halo_u ? nex - 1 : 0);
+        int ni = 0;
+        for (int e = 0; e < ney; ++e) {
+            if (halo_u) {
+                SpItem &it = TB.it[ni++];
+                it.part = pu; it.dx = ex0; it.dy = ey0 + e; it.nb = nex; it.wk = (e * nex) * S.kext_u; it.wk_step = S.kext_u; it.shift0 = 0; it.dshift = 8;
+            } else {
+                for (int f = 0; f < nex; ++f) {
+                    SpItem &it = TB.it[ni++];
+                    it.part = pu; it.dx = ex0 + f; it.dy = ey0 + e; it.nb = 1; it.wk = (e * nex + f) * S.kext_u; it.wk_step = 0; it.shift0 = 0; it.dshift = 0;
+                }
+            }
+        }
+        if (ps >= 0) {
+            TB.step[ps] = 2; TB.es[ps] = 2; TB.ph[ps] = c->h; TB.pw[ps] = c->w;
+            TB.arows[ps] = BLOCK_M;                                      // (a 129-pixel box at traversal stride 2 would exceed the 256-element TMA box limit)
+            for (int tr = 0; tr < c->kh; ++tr)
+                for (int tc = 0; tc < c->kw; ++tc) {
+                    SpItem &it = TB.it[ni++];
+                    it.part = ps; it.dx = px + tc * c->dil - c->pad_w; it.dy = py + tr * c->dil - c->pad_h; it.nb = 1;
+                    it.wk = S.net[cls] * S.kext_u + (tr * c->kw + tc) * S.kext_s; it.wk_step = 0; it.shift0 = 0; it.dshift = 0;
+                }
+        }
+        TB.n_items = ni;
+        TB.rows_max = std::max(TB.arows[pu], ps >= 0 ? TB.arows[ps] : 0);
+        PCB_CHECK(ni <= SP_MAX_ITEMS, "sub-pixel conv: too many items");
+        CUtensorMap ta[TC_MAX_PARTS], tw;
+        memset(ta, 0, sizeof(ta));
+        if (int rc = make_tmap_nhwc(&ta[pu], c->parts[pu].x, S.c8_u, wc, hc, c->n, c->parts[pu].x_cstride, S.bw + (halo_u ? nex - 1 : 0), S.bh, S.bn, 1)) return rc;
+        if (ps >= 0) {
+            if (int rc = make_tmap_nhwc(&ta[ps], c->parts[ps].x, S.c8_s, c->w, c->h, c->n, c->parts[ps].x_cstride, S.bw, S.bh, S.bn, 2)) return rc;
+        } else ta[1 - pu] = ta[pu];
+        if (int rc = make_tmap_2d(&tw, w_sp + S.clsoff[cls], L.rows_f, S.kc[cls], S.kc[cls], bn)) return rc;
+        TcParams Q = P;
+        Q.py = py; Q.px = px;
+        cudaStream_t cs = (fork && cls > 0) ? CS->aux[cls - 1] : st;
+        if (fork && cls > 0) PCB_CUDA(cudaStreamWaitEvent(cs, CS->ev_fork, 0));
+        if (int rc = launch_sp<0>(Q, TB, tw, ta[0], ta[1], bn, cs)) return rc;
+        if (fork && cls > 0) {
+            PCB_CUDA(cudaEventRecord(CS->ev_join[cls - 1], cs));
+            PCB_CUDA(cudaStreamWaitEvent(st, CS->ev_join[cls - 1], 0));
+        }
+    }
+    return 0;
+}
+
+// data gradient w.r.t. the upsampled part, written directly at SOURCE resolution: dx_u[k][j] = mask_u[k][j] * sum over classes and
+// effective taps of dc[2(k - ey) + py][2(j - ex) + px] . Weff^T
+int sp_dgrad_up(const pcb_conv *c, const SpPlan &S, const Layout &L, const void *dc, int dc_cstride, const bf16 *w_sp_dg, void *dx_u, int dx_cstride,
+                int *flag, cudaStream_t st) {
+    const int hs = c->h / 2, ws = c->w / 2;
+    const long long m_src = static_cast<long long>(c->n) * hs * ws;
+    TcParams P;
+    base_params(P, c, L);
+    P.h = hs; P.w = ws; P.m_total = static_cast<int>(m_src);
+    P.sub = 1; P.py = 0; P.px = 0; P.fh = hs; P.fw = ws;
+    P.nparts = 1;
+    memset(P.parts, 0, sizeof(P.parts));
+    TcPart &pt = P.parts[0];
+    pt.c = c->parts[S.pu].c; pt.c8 = S.c8_u; pt.kext = S.kext_u; pt.koff = 0; pt.mask = c->parts[S.pu].mask; pt.mup = 0;
+    pt.dx = static_cast<bf16 *>(dx_u); pt.dx_cstride = dx_cstride;
+    PCB_CHECK(dx_cstride % 8 == 0 && dx_cstride >= S.c8_u && (reinterpret_cast<uintptr_t>(dx_u) & 15) == 0, "sub-pixel dgrad: dx must be 16-byte aligned with a channel stride that is a multiple of 8");
+    P.dc = static_cast<const bf16 *>(dc); P.dc_cstride = dc_cstride; P.dc_c8 = rup(c->cout, 8); P.dc_kext = L.cout64;
+    P.abort_flag = flag;
+    P.ncols = S.kext_u;
+    P.box_w = S.bw; P.box_h = S.bh; P.box_n = S.bn;
+    const int bn = pick_bn(S.kext_u, m_src);
+    SpTable TB;
+    memset(&TB, 0, sizeof(TB));
+    TB.step[0] = 2; TB.es[0] = 2; TB.ph[0] = c->ho; TB.pw[0] = c->wo; TB.arows[0] = BLOCK_M; TB.rows_max = BLOCK_M;
+    int ni = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+        const int py = cls >> 1, px = cls & 1;
+        const int ney = S.ay.ne[py], nex = S.ax.ne[px];
+        for (int e = 0; e < ney; ++e)
+            for (int f = 0; f < nex; ++f) {
+                SpItem &it = TB.it[ni++];
+                it.part = 0; it.dx = px - 2 * (S.ax.e0[px] + f); it.dy = py - 2 * (S.ay.e0[py] + e); it.nb = 1;
+                it.wk = (S.eoff[cls] + e * nex + f) * L.cout64; it.wk_step = 0; it.shift0 = 0; it.dshift = 0;
+            }
+    }
+    TB.n_items = ni;
+    CUtensorMap ta, tw;
+    if (int rc = make_tmap_nhwc(&ta, dc, P.dc_c8, c->wo, c->ho, c->n, dc_cstride, S.bw, S.bh, S.bn, 2)) return rc;
+    if (int rc = make_tmap_2d(&tw, w_sp_dg, rup(S.kext_u, 128), S.kd_sp, S.kd_sp, bn)) return rc;
+    return launch_sp<1>(P, TB, tw, ta, ta, bn, st);
+}
+
+}  // namespace
+
 static bool smallco_ok(const pcb_conv *c) { return common_ok(c) && !is_rowpack(c) && pcb_smallco_eligible(c); }
 static pcb_smallco_layout smallco_layout(const Layout &L) {
     pcb_smallco_layout S;
@@ -2176,7 +2746,12 @@ void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_el
     const Layout L = layout_of(c);
     *fwd_elems = static_cast<size_t>(L.rows_f) * L.kf;
     *dgrad_elems = L.rowpack ? 0 : static_cast<size_t>(rup(L.ktap, 128)) * L.kd;
+    // sub-pixel path (conv over a 2x-upsampled source): the per-class effective-tap matrices follow the regular operands
+    const SpPlan S = sp_plan(c);
+    if (S.ok) { *fwd_elems += static_cast<size_t>(S.sp_fwd_elems); *dgrad_elems += static_cast<size_t>(S.sp_dg_elems); }
 }
+
+bool pcb_tc_subpixel(const pcb_conv *c) { return sp_plan(c).ok; }
 
 int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st) {
     const Layout L = layout_of(c);
@@ -2196,6 +2771,12 @@ int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd,
         dim3 tg((c->cin + 31) / 32, (c->cout + 31) / 32, W.taps);
         tc_weight_prepare_tiled_kernel<<<tg, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd), (w_dgrad && de) ? static_cast<bf16 *>(w_dgrad) : nullptr);
         PCB_LAUNCH_CHECK();
+        const SpPlan S = sp_plan(c);
+        if (S.ok) {
+            PCB_CHECK(w_dgrad != nullptr, "sub-pixel weights need the dgrad operand buffer");
+            return sp_weight_prepare(c, S, L, w_master, static_cast<bf16 *>(w_fwd) + static_cast<size_t>(L.rows_f) * L.kf,
+                                     static_cast<bf16 *>(w_dgrad) + static_cast<size_t>(rup(L.ktap, 128)) * L.kd, st);
+        }
         return 0;
     }
     const long long total = static_cast<long long>(c->cout) * W.taps * c->cin;
@@ -2203,6 +2784,12 @@ int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd,
     tc_weight_prepare_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd),
                                                                    (w_dgrad && de) ? static_cast<bf16 *>(w_dgrad) : nullptr);
     PCB_LAUNCH_CHECK();
+    const SpPlan S = sp_plan(c);
+    if (S.ok) {
+        PCB_CHECK(w_dgrad != nullptr, "sub-pixel weights need the dgrad operand buffer");
+        return sp_weight_prepare(c, S, L, w_master, static_cast<bf16 *>(w_fwd) + static_cast<size_t>(L.rows_f) * L.kf,
+                                 static_cast<bf16 *>(w_dgrad) + static_cast<size_t>(rup(L.ktap, 128)) * L.kd, st);
+    }
     return 0;
 }
 
@@ -2212,6 +2799,7 @@ int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t 
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     const Layout L = layout_of(c);
     if (smallco_ok(c)) return 0;
+    if (sp_plan(c).ok) return 0;                          // sub-pixel path: its fixers read the mask planes themselves
     bool any_mask = false;
     for (int p = 0; p < c->nparts; ++p) any_mask = any_mask || (c->parts[p].mask != nullptr);
     if (tma_fwd_ok(c) && !any_mask) return 0;            // no holes: TMA's out-of-range zero fill is all the validity there is
@@ -2239,6 +2827,13 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     if (!mask_pass_done)
         if (int rc = pcb_tc_forward_mask_pass(c, tapmask, st)) return rc;
     if (smallco_ok(c)) return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
+    {
+        const SpPlan S = sp_plan(c);
+        if (S.ok) {
+            PCB_CHECK(bn_sums == nullptr || pcb_tc_fuses_bn_stats(c), "fused BatchNorm statistics requested from a kernel that does not produce them");
+            return sp_forward(c, S, L, static_cast<const bf16 *>(w_fwd) + static_cast<size_t>(L.rows_f) * L.kf, bias, y, y_cstride, msum, bn_sums, flag, st);
+        }
+    }
     TcParams P;
     base_params(P, c, L);
     P.m_total = static_cast<int>(m_total);
@@ -2312,6 +2907,19 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= rup(c->cout, 8), "tensor-core dgrad: dc channel stride must be a multiple of 8");
     const Layout L = layout_of(c);
     if (smallco_ok(c)) return pcb_smallco_dgrad(c, smallco_layout(L), dc, dc_cstride, w_dgrad, dx, dx_cstride, st);
+    // sub-pixel path: the gradient of the upsampled part is computed directly at source resolution (dx[pu] is a SOURCE-resolution
+    // buffer, see pcb_conv_dgrad_at_source_resolution); the other part goes through the regular kernel below
+    const SpPlan SPL = sp_plan(c);
+    void *dx_local[TC_MAX_PARTS] = {nullptr, nullptr};
+    for (int p = 0; p < c->nparts && p < TC_MAX_PARTS; ++p) dx_local[p] = dx[p];
+    if (SPL.ok) {
+        if (dx[SPL.pu] != nullptr)
+            if (int rc = sp_dgrad_up(c, SPL, L, dc, dc_cstride, static_cast<const bf16 *>(w_dgrad) + static_cast<size_t>(rup(L.ktap, 128)) * L.kd,
+                                     dx[SPL.pu], dx_cstride[SPL.pu], flag, st)) return rc;
+        dx_local[SPL.pu] = nullptr;
+        if (SPL.ps < 0 || dx[SPL.ps] == nullptr) return 0;
+    }
+    dx = dx_local;
     TcParams P;
     base_params(P, c, L);
     P.m_total = static_cast<int>(m_total);

@@ -468,7 +468,34 @@ inline Dw4Geom dw4_geom(int c, int w, int h, int dil) {
 }
 
 // y[oy][ox][c] = b[c] + sum_{tr,tc} w[tr][tc][c] * x[oy + (tr-1) d][ox + (tc-1) d][c]      (FLIP: w[2-tr][2-tc], no bias: data gradient)
-constexpr int DW4_Q = 4;                            // rows of loads in flight per thread (queue of raw vectors)
+// The arithmetic is packed fp32 (FFMA2: two fp32 FMAs per instruction on sm_100): these kernels are ISSUE-bound, not
+// bandwidth-bound (ncu: 42 % issue-active at 24 % occupancy, ~100 instructions per 16 bytes moved in the scalar version), so
+// halving the FMA count and walking pointers instead of re-deriving 64-bit addresses is what moves them towards the roofline.
+struct F4 { float2 lo, hi; };
+__device__ __forceinline__ F4 f4_zero() { F4 r; r.lo = make_float2(0.f, 0.f); r.hi = make_float2(0.f, 0.f); return r; }
+__device__ __forceinline__ F4 f4_fma(const F4 &a, const F4 &b, const F4 &c) { F4 r; r.lo = __ffma2_rn(a.lo, b.lo, c.lo); r.hi = __ffma2_rn(a.hi, b.hi, c.hi); return r; }
+__device__ __forceinline__ F4 f4_mul(const F4 &a, const F4 &b) { F4 r; r.lo = __fmul2_rn(a.lo, b.lo); r.hi = __fmul2_rn(a.hi, b.hi); return r; }
+__device__ __forceinline__ F4 f4_add(const F4 &a, const F4 &b) { F4 r; r.lo = __fadd2_rn(a.lo, b.lo); r.hi = __fadd2_rn(a.hi, b.hi); return r; }
+template <typename T> __device__ __forceinline__ F4 f4_of(const Raw4<T> &q) {
+    float v[4];
+    q.unpack(v);
+    F4 r; r.lo = make_float2(v[0], v[1]); r.hi = make_float2(v[2], v[3]);
+    return r;
+}
+template <typename T> __device__ __forceinline__ F4 f4_load(const T *p) { Raw4<T> q; q.load(p); return f4_of(q); }
+template <typename T> __device__ __forceinline__ void f4_store(T *p, const F4 &v) {
+    const float o[4] = {v.lo.x, v.lo.y, v.hi.x, v.hi.y};
+    Vec4<T>::store(p, o);
+}
+// the value as it will be read back from memory (bf16 mode: rounded), for the fused BatchNorm statistics
+template <typename T> __device__ __forceinline__ F4 f4_as_stored(const F4 &v) {
+    F4 r;
+    r.lo = make_float2(to_f32(from_f32<T>(v.lo.x)), to_f32(from_f32<T>(v.lo.y)));
+    r.hi = make_float2(to_f32(from_f32<T>(v.hi.x)), to_f32(from_f32<T>(v.hi.y)));
+    return r;
+}
+
+constexpr int DW4_Q = 3;                            // rows of loads in flight per thread = the period of the accumulator rotation
 template <typename T, bool FLIP>
 __global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ w_t, const float *__restrict__ bias,
                                                         T *__restrict__ y, int y_cstride, double *__restrict__ bn_sums,
@@ -481,82 +508,79 @@ __global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x,
     const int seg = z % nseg; z /= nseg;
     const int pgroups = dil / ppb;
     const int pg = z % pgroups, nn = z / pgroups;
-    float wt[3][3][4], bs[4], st_s[4], st_q[4];
+    F4 wt[3][3], bs = f4_zero(), st_s = f4_zero(), st_q = f4_zero();
 #pragma unroll
     for (int tr = 0; tr < 3; ++tr)
 #pragma unroll
         for (int tc = 0; tc < 3; ++tc) {
             const int tap = FLIP ? (2 - tr) * 3 + (2 - tc) : tr * 3 + tc;
-            Vec4<T>::load(w_t + static_cast<long long>(tap) * c + ch, wt[tr][tc]);
+            wt[tr][tc] = f4_load<T>(w_t + static_cast<long long>(tap) * c + ch);
         }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { bs[j] = (bias && !FLIP) ? bias[ch + j] : 0.f; st_s[j] = 0.f; st_q[j] = 0.f; }
+    if (bias && !FLIP) { bs.lo = make_float2(bias[ch], bias[ch + 1]); bs.hi = make_float2(bias[ch + 2], bias[ch + 3]); }
     if (active) {
         const bool cl = ox - dil >= 0, cr = ox + dil < w;
-        const T *xb = x + static_cast<long long>(nn) * h * w * x_cstride + ch;
-        T *yb = y + static_cast<long long>(nn) * h * w * y_cstride + ch;
         const long long xoff_l = -static_cast<long long>(dil) * x_cstride, xoff_r = static_cast<long long>(dil) * x_cstride;
+        const long long xrow = static_cast<long long>(dil) * w * x_cstride, yrow = static_cast<long long>(dil) * w * y_cstride;
         for (int a = pg * ppb; a < (pg + 1) * ppb; ++a) {
             const int nj = (h - a + dil - 1) / dil;                    // rows of this phase: iy = a + dil * i, i in [0, nj)
             const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);        // output sub-rows of this segment
-            const int i_lo = max(j0 - 1, 0), i_hi = min(j1 + 1, nj);   // input sub-rows [i_lo, i_hi)
             if (j0 >= nj) continue;
+            const int i_lo = max(j0 - 1, 0), i_hi = min(j1 + 1, nj);   // input sub-rows [i_lo, i_hi)
+            // running pointers: next row to fetch, next row to store
+            const T *pf = x + ((static_cast<long long>(nn) * h + a + static_cast<long long>(dil) * i_lo) * w + ox) * x_cstride + ch;
+            T *ps = y + ((static_cast<long long>(nn) * h + a + static_cast<long long>(dil) * j0) * w + ox) * y_cstride + ch;
+            int fetched = i_lo;
             Raw4<T> q[DW4_Q][3];
-            auto fetch = [&](int i, Raw4<T> (&dst)[3]) {
+            auto fetch = [&](Raw4<T> (&dst)[3]) {
                 dst[0].zero(); dst[1].zero(); dst[2].zero();
-                if (i >= i_hi) return;
-                const T *xr = xb + (static_cast<long long>(a + dil * i) * w + ox) * x_cstride;
-                dst[1].load(xr);
-                if (cl) dst[0].load(xr + xoff_l);
-                if (cr) dst[2].load(xr + xoff_r);
-            };
-#pragma unroll
-            for (int k = 0; k < DW4_Q; ++k) fetch(i_lo + k, q[k]);
-            float acc0[4], acc1[4];                                    // output sub-rows i-1 and i while input sub-row i is processed
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-            auto emit = [&](int jrow, const float (&accv)[4]) {
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = accv[j] + bs[j];
-                Vec4<T>::store(yb + (static_cast<long long>(a + dil * jrow) * w + ox) * y_cstride, o);
-                if (bn_sums != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { const float r = to_f32(from_f32<T>(o[j])); st_s[j] += r; st_q[j] = fmaf(r, r, st_q[j]); }
+                if (fetched < i_hi) {
+                    dst[1].load(pf);
+                    if (cl) dst[0].load(pf + xoff_l);
+                    if (cr) dst[2].load(pf + xoff_r);
                 }
+                ++fetched; pf += xrow;
             };
+#pragma unroll
+            for (int k = 0; k < DW4_Q; ++k) fetch(q[k]);
+            auto emit = [&](const F4 &accv) {
+                const F4 o = f4_add(accv, bs);
+                f4_store<T>(ps, o);
+                ps += yrow;
+                if (bn_sums != nullptr) { const F4 r = f4_as_stored<T>(o); st_s = f4_add(st_s, r); st_q = f4_fma(r, r, st_q); }
+            };
+            // three accumulators in rotating roles (period DW4_Q == 3): while input sub-row i is processed, `top` belongs to
+            // output row i-1 (receives tap row 2 and is complete), `mid` to output i (tap row 1), `bot` to output i+1 (tap row 0)
+            F4 acc[3] = {f4_zero(), f4_zero(), f4_zero()};
             for (int i0 = i_lo; i0 < i_hi; i0 += DW4_Q) {
 #pragma unroll
                 for (int k = 0; k < DW4_Q; ++k) {
                     const int i = i0 + k;
                     if (i < i_hi) {
-                        float xv[3][4];
-                        q[k][0].unpack(xv[0]); q[k][1].unpack(xv[1]); q[k][2].unpack(xv[2]);
-                        fetch(i + DW4_Q, q[k]);                        // refill the slot: DW4_Q rows of loads stay in flight
-                        float acc2[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            // input row i is tap row 2 of output i-1, tap row 1 of output i, tap row 0 of output i+1
-                            acc0[j] = fmaf(wt[2][0][j], xv[0][j], fmaf(wt[2][1][j], xv[1][j], fmaf(wt[2][2][j], xv[2][j], acc0[j])));
-                            acc1[j] = fmaf(wt[1][0][j], xv[0][j], fmaf(wt[1][1][j], xv[1][j], fmaf(wt[1][2][j], xv[2][j], acc1[j])));
-                            acc2[j] = fmaf(wt[0][0][j], xv[0][j], fmaf(wt[0][1][j], xv[1][j], wt[0][2][j] * xv[2][j]));
-                        }
-                        if (i - 1 >= j0) emit(i - 1, acc0);            // complete: it just received its bottom tap row
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { acc0[j] = acc1[j]; acc1[j] = acc2[j]; }
+                        const F4 x0 = f4_of(q[k][0]), x1 = f4_of(q[k][1]), x2 = f4_of(q[k][2]);
+                        fetch(q[k]);                                   // refill the slot: DW4_Q rows of loads stay in flight
+                        F4 &top = acc[k % 3], &mid = acc[(k + 1) % 3], &bot = acc[(k + 2) % 3];
+                        top = f4_fma(wt[2][0], x0, f4_fma(wt[2][1], x1, f4_fma(wt[2][2], x2, top)));
+                        mid = f4_fma(wt[1][0], x0, f4_fma(wt[1][1], x1, f4_fma(wt[1][2], x2, mid)));
+                        bot = f4_fma(wt[0][0], x0, f4_fma(wt[0][1], x1, f4_mul(wt[0][2], x2)));
+                        if (i - 1 >= j0) emit(top);                    // complete: it just received its bottom tap row
                     }
                 }
             }
-            // the last input row of the PHASE has no row below it: its own output (now in acc0) is complete as well
-            if (j1 == nj && j1 - 1 >= j0) emit(j1 - 1, acc0);
+            // the last input row of the PHASE has no row below it: its own output is complete as well.  It sits in the
+            // accumulator that was `mid` at the last processed row i_hi - 1, i.e. role index (i_hi - 1 - i_lo + 1) % 3.
+            if (j1 == nj && j1 - 1 >= j0) {
+                const int role = (i_hi - i_lo) % 3;                    // (selected without dynamic register indexing)
+                emit(role == 0 ? acc[0] : (role == 1 ? acc[1] : acc[2]));
+            }
         }
     }
     if (bn_sums != nullptr) {
+        const float ss[4] = {st_s.lo.x, st_s.lo.y, st_s.hi.x, st_s.hi.y}, sq[4] = {st_q.lo.x, st_q.lo.y, st_q.hi.x, st_q.hi.y};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             __syncthreads();
-            s_stat[threadIdx.x][0] = active ? st_s[j] : 0.f;
-            s_stat[threadIdx.x][1] = active ? st_q[j] : 0.f;
+            s_stat[threadIdx.x][0] = active ? ss[j] : 0.f;
+            s_stat[threadIdx.x][1] = active ? sq[j] : 0.f;
             __syncthreads();
             for (int col = threadIdx.x; col < cq * 2; col += 256) {
                 const int cql = col >> 1, qq = col & 1;
@@ -581,73 +605,65 @@ __global__ void __launch_bounds__(256, 2) dw4_s1_wgrad_kernel(const T *__restric
     const int seg = z % nseg; z /= nseg;
     const int pgroups = dil / ppb;
     const int pg = z % pgroups, nn = z / pgroups;
-    float acc[3][3][4];
+    F4 acc[3][3];
 #pragma unroll
     for (int tr = 0; tr < 3; ++tr)
 #pragma unroll
-        for (int tc = 0; tc < 3; ++tc)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[tr][tc][j] = 0.f;
+        for (int tc = 0; tc < 3; ++tc) acc[tr][tc] = f4_zero();
     if (active) {
         const bool cl = ox - dil >= 0, cr = ox + dil < w;
-        const T *xb = x + static_cast<long long>(nn) * h * w * x_cstride + ch;
-        const T *db = dc + static_cast<long long>(nn) * h * w * dc_cstride + ch;
         const long long xoff_l = -static_cast<long long>(dil) * x_cstride, xoff_r = static_cast<long long>(dil) * x_cstride;
+        const long long xrow = static_cast<long long>(dil) * w * x_cstride, drow = static_cast<long long>(dil) * w * dc_cstride;
         for (int a = pg * ppb; a < (pg + 1) * ppb; ++a) {
             const int nj = (h - a + dil - 1) / dil;
             const int j0 = seg * rseg, j1 = min(nj, j0 + rseg);
             if (j0 >= nj) continue;
-            // queue slot k holds the raw x row (i + 1) (three taps) and the raw dc row i of a future step: DW4_Q rows in flight
-            Raw4<T> qx[DW4_Q][3], qd[DW4_Q];
-            auto fetch = [&](int i, Raw4<T> (&dx3)[3], Raw4<T> &dd) {      // x row i + 1 and dc row i
-                dx3[0].zero(); dx3[1].zero(); dx3[2].zero(); dd.zero();
-                if (i >= j1) return;
-                dd.load(db + (static_cast<long long>(a + dil * i) * w + ox) * dc_cstride);
-                if (i + 1 < nj) {
-                    const T *xr = xb + (static_cast<long long>(a + dil * (i + 1)) * w + ox) * x_cstride;
-                    dx3[1].load(xr);
-                    if (cl) dx3[0].load(xr + xoff_l);
-                    if (cr) dx3[2].load(xr + xoff_r);
-                }
+            const T *xbase = x + ((static_cast<long long>(nn) * h + a) * w + ox) * x_cstride + ch;       // phase row 0
+            // x rows j0-1 and j0 of the phase: the first two rows of the sliding window
+            F4 xw[3][3];                                               // rows in rotating roles: role (k + r) % 3 = window row r at step k
+            auto load3 = [&](int i, F4 (&dst)[3]) {
+                dst[0] = dst[1] = dst[2] = f4_zero();
+                if (i < 0 || i >= nj) return;
+                const T *xr = xbase + static_cast<long long>(i) * xrow;
+                dst[1] = f4_load<T>(xr);
+                if (cl) dst[0] = f4_load<T>(xr + xoff_l);
+                if (cr) dst[2] = f4_load<T>(xr + xoff_r);
             };
-            // x rows j0-1 and j0 of the phase (unpacked sliding window rows 0 and 1)
-            float xw[3][3][4];
-            {
-                Raw4<T> t3[3];
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int i = j0 - 1 + rr;
-                    t3[0].zero(); t3[1].zero(); t3[2].zero();
-                    if (i >= 0 && i < nj) {
-                        const T *xr = xb + (static_cast<long long>(a + dil * i) * w + ox) * x_cstride;
-                        t3[1].load(xr);
-                        if (cl) t3[0].load(xr + xoff_l);
-                        if (cr) t3[2].load(xr + xoff_r);
+            load3(j0 - 1, xw[0]);
+            load3(j0, xw[1]);
+            // queue slot k: raw x row (i + 1) and raw dc row i of the step that will consume it
+            const T *pfx = xbase + static_cast<long long>(j0 + 1) * xrow;
+            const T *pfd = dc + ((static_cast<long long>(nn) * h + a + static_cast<long long>(dil) * j0) * w + ox) * dc_cstride + ch;
+            int fetched = j0;
+            Raw4<T> qx[DW4_Q][3], qd[DW4_Q];
+            auto fetch = [&](Raw4<T> (&dx3)[3], Raw4<T> &dd) {
+                dx3[0].zero(); dx3[1].zero(); dx3[2].zero(); dd.zero();
+                if (fetched < j1) {
+                    dd.load(pfd);
+                    if (fetched + 1 < nj) {
+                        dx3[1].load(pfx);
+                        if (cl) dx3[0].load(pfx + xoff_l);
+                        if (cr) dx3[2].load(pfx + xoff_r);
                     }
-                    if (rr == 0) { t3[0].unpack(xw[0][0]); t3[1].unpack(xw[0][1]); t3[2].unpack(xw[0][2]); }
-                    else { t3[0].unpack(xw[1][0]); t3[1].unpack(xw[1][1]); t3[2].unpack(xw[1][2]); }
                 }
-            }
+                ++fetched; pfx += xrow; pfd += drow;
+            };
 #pragma unroll
-            for (int k = 0; k < DW4_Q; ++k) fetch(j0 + k, qx[k], qd[k]);
+            for (int k = 0; k < DW4_Q; ++k) fetch(qx[k], qd[k]);
             for (int i0 = j0; i0 < j1; i0 += DW4_Q) {
 #pragma unroll
                 for (int k = 0; k < DW4_Q; ++k) {
-                    const int i = i0 + k;
-                    if (i < j1) {
-                        float dv[4];
-                        qx[k][0].unpack(xw[2][0]); qx[k][1].unpack(xw[2][1]); qx[k][2].unpack(xw[2][2]);
-                        qd[k].unpack(dv);
-                        fetch(i + DW4_Q, qx[k], qd[k]);
+                    if (i0 + k < j1) {
+                        F4 (&r0)[3] = xw[k % 3], (&r1)[3] = xw[(k + 1) % 3], (&r2)[3] = xw[(k + 2) % 3];
+                        r2[0] = f4_of(qx[k][0]); r2[1] = f4_of(qx[k][1]); r2[2] = f4_of(qx[k][2]);
+                        const F4 dv = f4_of(qd[k]);
+                        fetch(qx[k], qd[k]);
 #pragma unroll
-                        for (int tr = 0; tr < 3; ++tr)
-#pragma unroll
-                            for (int tc = 0; tc < 3; ++tc)
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) acc[tr][tc][j] = fmaf(dv[j], xw[tr][tc][j], acc[tr][tc][j]);
-#pragma unroll
-                        for (int tc = 0; tc < 3; ++tc)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { xw[0][tc][j] = xw[1][tc][j]; xw[1][tc][j] = xw[2][tc][j]; }
+                        for (int tc = 0; tc < 3; ++tc) {
+                            acc[0][tc] = f4_fma(dv, r0[tc], acc[0][tc]);
+                            acc[1][tc] = f4_fma(dv, r1[tc], acc[1][tc]);
+                            acc[2][tc] = f4_fma(dv, r2[tc], acc[2][tc]);
+                        }
                     }
                 }
             }
@@ -657,7 +673,11 @@ __global__ void __launch_bounds__(256, 2) dw4_s1_wgrad_kernel(const T *__restric
     for (int j = 0; j < 4; ++j) {
         __syncthreads();
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) s_red[threadIdx.x][tap] = active ? acc[tap / 3][tap % 3][j] : 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const F4 &v = acc[tap / 3][tap % 3];
+            const float e = (j == 0) ? v.lo.x : (j == 1) ? v.lo.y : (j == 2) ? v.hi.x : v.hi.y;
+            s_red[threadIdx.x][tap] = active ? e : 0.f;
+        }
         __syncthreads();
         for (int col = threadIdx.x; col < cq * 9; col += 256) {
             const int cql = col / 9, tap = col - cql * 9;

@@ -151,6 +151,7 @@ int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t 
 int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, void *y, int y_cstride, const float *msum,
                       uint64_t *tapmask, bool mask_pass_done, double *bn_sums, cudaStream_t st);
 bool pcb_tc_fuses_bn_stats(const pcb_conv *c);
+bool pcb_tc_subpixel(const pcb_conv *c);
 int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
                  cudaStream_t st);
 int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, cudaStream_t st);

@@ -237,7 +237,12 @@ class ConvGeom:
         if len(self.parts) > _lib.MAX_PARTS:
             raise TooManyParts(f"more than {_lib.MAX_PARTS} (source, mask-plane) parts in one convolution")
         self.signature = (self.dtype, cin, cout, kh, kw, groups, tuple(p[2] for p in self.parts), tuple(self.x_cstrides),
-                          tuple(self.x_ups), s, d)
+                          tuple(self.x_ups), tuple(p[4] for p in self.parts), tuple(p[3] is not None for p in self.parts), s, d,
+                          ph, pw, h & 1, w & 1)
+        # the sub-pixel path (conv over a 2x-upsampled source) carries extra operand matrices: its eligibility depends on the
+        # spatial size, so it is part of the operand-cache key
+        self.subpixel = bool(_lib.load().pcb_conv_dgrad_at_source_resolution(ctypes.byref(self.struct(None)))) if any(self.x_ups) else False
+        self.signature = self.signature + (self.subpixel,)
 
     def struct(self, xs: Optional[Sequence[torch.Tensor]], force_generic=False) -> Conv:
         c = Conv()
@@ -467,8 +472,11 @@ class PartialConvFn(torch.autograd.Function):
                     sink.on_written()
         gxs: List[Optional[torch.Tensor]] = [None] * len(xs)
         if any(need):
-            # full-resolution gradient buffer per source tensor; parts write their channel slices
-            full = [padded_empty(geom.n, geom.x_channels[i], geom.h, geom.w, tdtype, dev) if need[i] else None for i in range(len(xs))]
+            # gradient buffer per source tensor; parts write their channel slices.  Full resolution -- except on the sub-pixel
+            # path, which computes the gradient of a 2x-upsampled source directly at that source's resolution
+            at_src = bool(lib.pcb_conv_dgrad_at_source_resolution(ctypes.byref(c)))
+            full = [padded_empty(geom.n, geom.x_channels[i], geom.h >> (geom.x_ups[i] if at_src else 0), geom.w >> (geom.x_ups[i] if at_src else 0),
+                                 tdtype, dev) if need[i] else None for i in range(len(xs))]
             nparts = len(geom.parts)
             ptrs = (ctypes.c_void_p * nparts)()
             strides = (ctypes.c_int32 * nparts)()
@@ -489,7 +497,7 @@ class PartialConvFn(torch.autograd.Function):
             for i in range(len(xs)):
                 if full[i] is None:
                     continue
-                if geom.x_ups[i]:
+                if geom.x_ups[i] and not at_src:
                     g = padded_empty(geom.n, geom.x_channels[i], geom.h >> 1, geom.w >> 1, tdtype, dev)
                     src = full[i]
                     cs_src, cs_dst = nhwc_layout(src), nhwc_layout(g)
