@@ -2443,7 +2443,8 @@ SpAxis sp_axis(int k, int d, int p) {
 }
 
 struct SpPlan {
-    bool ok;
+    bool ok;                         // geometry admits the decomposition
+    bool fwd, dgrad;                 // which passes use it (see sp_plan)
     int pu, ps;                      // the upsampled part and the other one (-1: none)
     SpAxis ay, ax;
     int net[4], eoff[4], net_total;  // effective taps of the upsampled part per class (class = py * 2 + px)
@@ -2487,10 +2488,22 @@ SpPlan sp_plan(const pcb_conv *c) {
     }
     S.net_total = eo;
     if (S.net_total > SP_MAX_ITEMS) return S;
-    S.sp_fwd_elems = off;
     S.kd_sp = static_cast<long long>(S.net_total) * L.cout64;
-    S.sp_dg_elems = static_cast<long long>(rup(S.kext_u, 128)) * S.kd_sp;
     S.ok = true;
+    // Measured on B200 (8 x 512^2 U-Net, profiles/r02_subpixel.txt): these kernels are bound by the TMA unit's request rate
+    // (about one 128-byte tile row per 4 cycles and SM), not by the tensor pipe.
+    //  * DATA GRADIENT: one launch over the source grid replaces the full-resolution gradient of the upsampled part AND its 2x2
+    //    reduction pass -- a clear win wherever the source grid has at least a wave of tiles (192->64 @256^2: 0.28 -> 0.15 ms);
+    //    low-resolution layers keep the regular kernel (their launches are latency-bound either way).
+    //  * FORWARD: 37 % fewer MMAs but MORE tile rows per output pixel (the skip part is read with a traversal stride of 2, which
+    //    costs the TMA unit two rows per delivered row, and row-halo re-use is lost where the class grid is narrower than 128):
+    //    192->64 @256^2 0.26 -> 0.34 ms.  Off by default (PCB_SUBPIXEL_FWD=1 enables it; parity-tested either way).
+    const long long src_tiles = (static_cast<long long>(c->n) * (c->h / 2) * (c->w / 2) + BLOCK_M - 1) / BLOCK_M;
+    S.dgrad = src_tiles >= pcb_num_sms() / 2 || getenv("PCB_SUBPIXEL_ALL") != nullptr;
+    S.fwd = getenv("PCB_SUBPIXEL_FWD") != nullptr || getenv("PCB_SUBPIXEL_ALL") != nullptr;
+    S.sp_fwd_elems = S.fwd ? off : 0;
+    S.sp_dg_elems = S.dgrad ? static_cast<long long>(rup(S.kext_u, 128)) * S.kd_sp : 0;
+    if (!S.fwd && !S.dgrad) S.ok = false;
     return S;
 }
 
@@ -2500,6 +2513,7 @@ struct SpWParams {
     int net[4], eoff[4], nex[4], slot0[4];       // per class: eff taps, their prefix, eff columns, first slot index
     int ybits[2][4], xbits[2][4];
     long long kc[4], clsoff[4], kd_sp;
+    int want_fwd, want_dg;
 };
 
 // slot = (class, effective tap of the upsampled part | original tap of the skip part); one block per (cout, slot)
@@ -2519,14 +2533,34 @@ __global__ void sp_weight_prepare_kernel(const float *__restrict__ wm, const SpW
                     for (int tc = 0; tc < 4; ++tc)
                         if ((xb >> tc) & 1) v += wrow[static_cast<long long>(tr * W.kw + tc) * W.cin + W.choff_u + ci];
             const bf16 b = __float2bfloat16_rn(v);
-            w_f[W.clsoff[cls] + static_cast<long long>(co) * W.kc[cls] + static_cast<long long>(slot) * W.kext_u + ci] = b;
-            w_d[static_cast<long long>(ci) * W.kd_sp + static_cast<long long>(W.eoff[cls] + slot) * W.cout64 + co] = b;
+            if (W.want_fwd) w_f[W.clsoff[cls] + static_cast<long long>(co) * W.kc[cls] + static_cast<long long>(slot) * W.kext_u + ci] = b;
+            if (W.want_dg) w_d[static_cast<long long>(ci) * W.kd_sp + static_cast<long long>(W.eoff[cls] + slot) * W.cout64 + co] = b;
         }
-    } else if (W.has_skip) {
+    } else if (W.has_skip && W.want_fwd) {
         const int tap = slot - W.net[cls];
         for (int ci = threadIdx.x; ci < W.c_s; ci += blockDim.x)
             w_f[W.clsoff[cls] + static_cast<long long>(co) * W.kc[cls] + static_cast<long long>(W.net[cls]) * W.kext_u + static_cast<long long>(tap) * W.kext_s + ci] =
                 __float2bfloat16_rn(wrow[static_cast<long long>(tap) * W.cin + W.choff_s + ci]);
+    }
+}
+
+// dgrad-only variant: one block per (input channel of the upsampled part, slot), threads over cout -> coalesced writes of the
+// transposed matrix (the master reads are strided but L2-resident)
+__global__ void sp_weight_dg_kernel(const float *__restrict__ wm, const SpWParams W, bf16 *__restrict__ w_d) {
+    const int ci = blockIdx.x;
+    int slot = blockIdx.y, cls = 0;
+    while (cls < 3 && slot >= W.eoff[cls + 1]) ++cls;
+    slot -= W.eoff[cls];
+    const int ey = slot / W.nex[cls], ex = slot - ey * W.nex[cls];
+    const int yb = W.ybits[cls >> 1][ey], xb = W.xbits[cls & 1][ex];
+    for (int co = threadIdx.x; co < W.cout; co += blockDim.x) {
+        const float *wrow = wm + static_cast<long long>(co) * W.taps * W.cin + W.choff_u + ci;
+        float v = 0.f;
+        for (int tr = 0; tr < 4; ++tr)
+            if ((yb >> tr) & 1)
+                for (int tc = 0; tc < 4; ++tc)
+                    if ((xb >> tc) & 1) v += wrow[static_cast<long long>(tr * W.kw + tc) * W.cin];
+        w_d[static_cast<long long>(ci) * W.kd_sp + static_cast<long long>(W.eoff[cls] + slot) * W.cout64 + co] = __float2bfloat16_rn(v);
     }
 }
 
@@ -2541,6 +2575,7 @@ int sp_weight_prepare(const pcb_conv *c, const SpPlan &S, const Layout &L, const
         off += c->parts[p].c;
     }
     W.kext_u = S.kext_u; W.kext_s = S.kext_s; W.has_skip = S.ps >= 0; W.kd_sp = S.kd_sp;
+    W.want_fwd = S.fwd; W.want_dg = S.dgrad;
     int slot = 0;
     for (int cls = 0; cls < 4; ++cls) {
         W.net[cls] = S.net[cls]; W.eoff[cls] = S.eoff[cls]; W.nex[cls] = S.ax.ne[cls & 1]; W.slot0[cls] = slot;
@@ -2549,8 +2584,13 @@ int sp_weight_prepare(const pcb_conv *c, const SpPlan &S, const Layout &L, const
     }
     for (int q = 0; q < 2; ++q)
         for (int e = 0; e < 4; ++e) { W.ybits[q][e] = S.ay.tapbits[q][e]; W.xbits[q][e] = S.ax.tapbits[q][e]; }
-    sp_weight_prepare_kernel<<<dim3(c->cout, slot), 128, 0, st>>>(w_master, W, w_f, w_d);
-    PCB_LAUNCH_CHECK();
+    if (S.fwd) {
+        sp_weight_prepare_kernel<<<dim3(c->cout, slot), 128, 0, st>>>(w_master, W, w_f, w_d);
+        PCB_LAUNCH_CHECK();
+    } else if (S.dgrad) {
+        sp_weight_dg_kernel<<<dim3(W.c_u, S.net_total), 128, 0, st>>>(w_master, W, w_d);
+        PCB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -2751,7 +2791,7 @@ void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_el
     if (S.ok) { *fwd_elems += static_cast<size_t>(S.sp_fwd_elems); *dgrad_elems += static_cast<size_t>(S.sp_dg_elems); }
 }
 
-bool pcb_tc_subpixel(const pcb_conv *c) { return sp_plan(c).ok; }
+bool pcb_tc_subpixel(const pcb_conv *c) { const SpPlan S = sp_plan(c); return S.ok && S.dgrad; }
 
 int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st) {
     const Layout L = layout_of(c);
@@ -2799,7 +2839,7 @@ int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t 
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     const Layout L = layout_of(c);
     if (smallco_ok(c)) return 0;
-    if (sp_plan(c).ok) return 0;                          // sub-pixel path: its fixers read the mask planes themselves
+    { const SpPlan S = sp_plan(c); if (S.ok && S.fwd) return 0; }   // sub-pixel forward: its fixers read the mask planes themselves
     bool any_mask = false;
     for (int p = 0; p < c->nparts; ++p) any_mask = any_mask || (c->parts[p].mask != nullptr);
     if (tma_fwd_ok(c) && !any_mask) return 0;            // no holes: TMA's out-of-range zero fill is all the validity there is
@@ -2829,7 +2869,7 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     if (smallco_ok(c)) return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
     {
         const SpPlan S = sp_plan(c);
-        if (S.ok) {
+        if (S.ok && S.fwd) {
             PCB_CHECK(bn_sums == nullptr || pcb_tc_fuses_bn_stats(c), "fused BatchNorm statistics requested from a kernel that does not produce them");
             return sp_forward(c, S, L, static_cast<const bf16 *>(w_fwd) + static_cast<size_t>(L.rows_f) * L.kf, bias, y, y_cstride, msum, bn_sums, flag, st);
         }
@@ -2912,7 +2952,7 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     const SpPlan SPL = sp_plan(c);
     void *dx_local[TC_MAX_PARTS] = {nullptr, nullptr};
     for (int p = 0; p < c->nparts && p < TC_MAX_PARTS; ++p) dx_local[p] = dx[p];
-    if (SPL.ok) {
+    if (SPL.ok && SPL.dgrad) {
         if (dx[SPL.pu] != nullptr)
             if (int rc = sp_dgrad_up(c, SPL, L, dc, dc_cstride, static_cast<const bf16 *>(w_dgrad) + static_cast<size_t>(rup(L.ktap, 128)) * L.kd,
                                      dx[SPL.pu], dx_cstride[SPL.pu], flag, st)) return rc;
