@@ -16,6 +16,11 @@ import sys
 import threading
 import time
 
+# The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL's version banner under torchrun, the reference's
+# constructors): keep a handle on the real stdout for that line and point fd 1 at stderr for everything else.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -235,7 +240,7 @@ def run_reference(args):
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -496,9 +501,16 @@ def run_b200(args):
             "kernel_families_ms": {k: round(v[1], 4) for k, v in fam.items()},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
+        # graphs that captured NCCL collectives must die before the communicator (engine.TrainStep.close); the timer only
+        # guards the teardown itself -- the measurement is complete and printed at this point
+        import threading
+        threading.Timer(60.0, lambda: os._exit(0)).start()
+        ts.close()
+        barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

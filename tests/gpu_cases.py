@@ -223,7 +223,9 @@ LAZYCAT_CASES = {"lc_128up_64_to_64": (128, 64, 64, False), "lc_256up_64_to_128"
                  "lc_tail_64up_3_to_3": (64, 3, 3, True), "lc_64up_8_to_16": (64, 8, 16, True),
                  # TMA-fed path: the upsampled source is materialised in the workspace; second one uses row-halo tiles
                  "lc_tma_128up_64_to_64": (128, 64, 64, False, (2, 32, 32)), "lc_tma_halo_tail_64up_3_to_3": (64, 3, 3, True, (1, 8, 128)),
-                 "lc_tma_splitk_256up_64_to_128": (256, 64, 128, False, (2, 8, 8))}
+                 "lc_tma_splitk_256up_64_to_128": (256, 64, 128, False, (2, 8, 8)),
+                 # kernel-to-row tails (conv_k2r.cu) with the 1x1 problem on the TMA-fed kernels; 4-channel second part, 2 outputs
+                 "lc_k2r_tail_64up_3_to_3": (64, 3, 3, True, (2, 32, 64)), "lc_k2r_64up_4_to_2": (64, 4, 2, False, (2, 32, 32))}
 
 
 def lazycat_case(tag, dev, dtype=BF):

@@ -2774,7 +2774,14 @@ bool pcb_tc_eligible(const pcb_conv *c) { return common_ok(c) && !getenv("PCB_DI
 
 static bool tma_wgrad_ok(const pcb_conv *c);
 
+// kernel-to-row tails (conv_k2r.cu): their 1x1 operands follow the layer's regular ones, at 64-element boundaries
+static void k2r_bases(const Layout &L, size_t *fe, size_t *de) {
+    *fe = (static_cast<size_t>(L.rows_f) * L.kf + 63) / 64 * 64;
+    *de = (static_cast<size_t>(rup(L.ktap, 128)) * L.kd + 63) / 64 * 64;
+}
+
 size_t pcb_tc_workspace(const pcb_conv *c) {
+    if (smallco_ok(c) && pcb_k2r_ok(c)) return pcb_k2r_workspace(c);
     size_t bytes = tapmask_bytes(c);
     if (tma_fwd_ok(c) || tma_wgrad_ok(c))                // dense copies of the 2x-upsampled sources (TMA cannot replicate pixels)
         for (int p = 0; p < c->nparts; ++p)
@@ -2789,9 +2796,20 @@ void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_el
     // sub-pixel path (conv over a 2x-upsampled source): the per-class effective-tap matrices follow the regular operands
     const SpPlan S = sp_plan(c);
     if (S.ok) { *fwd_elems += static_cast<size_t>(S.sp_fwd_elems); *dgrad_elems += static_cast<size_t>(S.sp_dg_elems); }
+    if (smallco_ok(c) && pcb_k2r_ok(c)) {
+        size_t fb, db, fx, dx;
+        k2r_bases(L, &fb, &db);
+        pcb_k2r_weight_layout(c, &fx, &dx);
+        *fwd_elems = fb + fx; *dgrad_elems = db + dx;
+    }
 }
 
-bool pcb_tc_subpixel(const pcb_conv *c) { const SpPlan S = sp_plan(c); return S.ok && S.dgrad; }
+// true when the data gradient of the 2x-upsampled part is delivered at that part's own (source) resolution
+bool pcb_tc_subpixel(const pcb_conv *c) {
+    if (smallco_ok(c)) return pcb_k2r_ok(c);
+    const SpPlan S = sp_plan(c);
+    return S.ok && S.dgrad;
+}
 
 int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd, void *w_dgrad, bool zero_padding, cudaStream_t st) {
     const Layout L = layout_of(c);
@@ -2824,6 +2842,12 @@ int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd,
     tc_weight_prepare_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd),
                                                                    (w_dgrad && de) ? static_cast<bf16 *>(w_dgrad) : nullptr);
     PCB_LAUNCH_CHECK();
+    if (smallco_ok(c) && pcb_k2r_ok(c)) {
+        PCB_CHECK(w_dgrad != nullptr, "kernel-to-row weights need the dgrad operand buffer");
+        size_t fb, db;
+        k2r_bases(L, &fb, &db);
+        return pcb_k2r_weight_prepare(c, w_master, static_cast<bf16 *>(w_fwd) + fb, static_cast<bf16 *>(w_dgrad) + db, zero_padding, st);
+    }
     const SpPlan S = sp_plan(c);
     if (S.ok) {
         PCB_CHECK(w_dgrad != nullptr, "sub-pixel weights need the dgrad operand buffer");
@@ -2866,7 +2890,14 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     const Layout L = layout_of(c);
     if (!mask_pass_done)
         if (int rc = pcb_tc_forward_mask_pass(c, tapmask, st)) return rc;
-    if (smallco_ok(c)) return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
+    if (smallco_ok(c)) {
+        if (pcb_k2r_ok(c)) {
+            size_t fb, db;
+            k2r_bases(L, &fb, &db);
+            return pcb_k2r_forward(c, smallco_layout(L), w_fwd, static_cast<const bf16 *>(w_fwd) + fb, bias, y, y_cstride, msum, tapmask, st);
+        }
+        return pcb_smallco_forward(c, smallco_layout(L), w_fwd, bias, y, y_cstride, msum, st);
+    }
     {
         const SpPlan S = sp_plan(c);
         if (S.ok && S.fwd) {
@@ -2946,7 +2977,14 @@ int pcb_tc_dgrad(const pcb_conv *c, const void *dc, int dc_cstride, const void *
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= rup(c->cout, 8), "tensor-core dgrad: dc channel stride must be a multiple of 8");
     const Layout L = layout_of(c);
-    if (smallco_ok(c)) return pcb_smallco_dgrad(c, smallco_layout(L), dc, dc_cstride, w_dgrad, dx, dx_cstride, st);
+    if (smallco_ok(c)) {
+        if (pcb_k2r_ok(c)) {
+            size_t fb, db;
+            k2r_bases(L, &fb, &db);
+            return pcb_k2r_dgrad(c, smallco_layout(L), dc, dc_cstride, w_dgrad, static_cast<const bf16 *>(w_dgrad) + db, dx, dx_cstride, st);
+        }
+        return pcb_smallco_dgrad(c, smallco_layout(L), dc, dc_cstride, w_dgrad, dx, dx_cstride, st);
+    }
     // sub-pixel path: the gradient of the upsampled part is computed directly at source resolution (dx[pu] is a SOURCE-resolution
     // buffer, see pcb_conv_dgrad_at_source_resolution); the other part goes through the regular kernel below
     const SpPlan SPL = sp_plan(c);
@@ -3138,7 +3176,10 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= c->cout, "tensor-core wgrad: dc channel stride must be a multiple of 8");
-    if (smallco_ok(c)) return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, zero_dw, st);
+    if (smallco_ok(c)) {
+        if (pcb_k2r_ok(c)) return pcb_k2r_wgrad(c, dc, dc_cstride, dw, workspace, zero_dw, st);
+        return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, zero_dw, st);
+    }
     uint64_t *tapmask = static_cast<uint64_t *>(workspace);
     bool any_mask = false;
     for (int p = 0; p < c->nparts; ++p) any_mask = any_mask || (c->parts[p].mask != nullptr);

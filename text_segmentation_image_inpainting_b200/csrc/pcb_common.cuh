@@ -164,6 +164,16 @@ int pcb_smallco_forward(const pcb_conv *c, const pcb_smallco_layout &L, const vo
 int pcb_smallco_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, const void *w_dgrad, void *const *dx, const int *dx_cstride,
                       cudaStream_t st);
 int pcb_smallco_wgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, float *dw, bool zero_dw, cudaStream_t st);
+// RGB tails as a 1x1 GEMM at source resolution (conv_k2r.cu); the *_extra operands follow the layer's regular ones
+bool pcb_k2r_ok(const pcb_conv *c);
+void pcb_k2r_weight_layout(const pcb_conv *c, size_t *fwd_extra, size_t *dg_extra);
+size_t pcb_k2r_workspace(const pcb_conv *c);
+int pcb_k2r_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd_extra, void *w_dg_extra, bool zero_padding, cudaStream_t st);
+int pcb_k2r_forward(const pcb_conv *c, const pcb_smallco_layout &L, const void *w_fwd, const void *w_fwd_extra, const float *bias, void *y, int y_cstride,
+                    const float *msum, void *workspace, cudaStream_t st);
+int pcb_k2r_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, const void *w_dgrad, const void *w_dg_extra,
+                  void *const *dx, const int *dx_cstride, cudaStream_t st);
+int pcb_k2r_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, cudaStream_t st);
 // depthwise fast path (dwconv.cu)
 bool pcb_dw_eligible(const pcb_conv *c);
 int pcb_dw_weight_prepare(const pcb_conv *c, const float *w_master, void *w_t, cudaStream_t st);

@@ -316,6 +316,21 @@ class TrainStep:
         return loss
 
 
+    def close(self):
+        """Destroy the captured graphs (the step falls back to eager mode).  REQUIRED before
+        `torch.distributed.destroy_process_group()` when the all-reduce was captured (`overlap_active`): NCCL keeps a reference
+        per graph that holds captured collectives and its communicator teardown waits until those graphs are gone -- with the
+        graphs alive the process hangs at exit (measured: the 2-GPU bench printed its line and never returned)."""
+        if self.graph is not None or self.graph_update is not None:
+            torch.cuda.synchronize()
+            self.graph = None
+            self.graph_update = None
+            self._captured_operands = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+
+
 class SegTrainStep(TrainStep):
     """The same step for the dense segmentation networks (models/text_segmentation.py: `net(x)`, no masks): BASELINE.json
     configs[1] (TextSegament, batch 8) and configs[3] (XceptionTextSegment, batch 16, bf16).  `mask` is ignored."""
