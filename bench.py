@@ -326,8 +326,9 @@ def layer_profile(ts, x, mask, peaks, verbose):
     for name in ("r02_ncu_traffic.json", "r01_ncu_traffic_final.json"):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", name)))[dom[0]]
-            roof["traffic"] = t["dram_bytes"] / max(t["launches"], 1)
-            roof["traffic_note"] = f"mean dram__bytes_read+write per launch of the family, ncu --set full of one step (profiles/{name})"
+            roof["traffic"] = t["dram_bytes"] / max(roof["launches_per_step"], 1)
+            roof["traffic_note"] = (f"dram__bytes_read+write of all kernels of the family in one step (ncu --set full, profiles/{name}) / "
+                                    "launches_per_step: per layer call, like flops_per_step / launches_per_step")
             break
         except Exception:  # noqa: BLE001
             pass

@@ -164,47 +164,65 @@ __global__ void __launch_bounds__(256) gap_kernel(const T *__restrict__ x, long 
 }
 
 // ------------------------------------------------------------------------------------------------ scSE gate
-// one warp per pixel: sse = sigmoid(<x[p,:], ws>) ; y = x * (cse[n,:] + sse)
+// sse = sigmoid(<x[p,:], ws>) ; y = x * (cse[n,:] + sse).  A pixel is handled by a GROUP of gw lanes (gw = the power of two >=
+// min(c/8, 32)), lane vl of the group owning channel vectors vl, vl + gw, ...: a 24-channel tensor keeps 8 pixels per warp in
+// flight instead of 3 busy lanes out of 32 (the MobileNetV2 blocks that carry the gate have 16..320 channels).
+__device__ __forceinline__ float group_sum(float v, int gw) {
+    for (int o = gw >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+inline int scse_group_width(int c) {
+    const int cv = c >> 3;
+    int gw = 1;
+    while (gw < cv && gw < 32) gw <<= 1;
+    return gw;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) scse_fwd_kernel(const T *__restrict__ x, const float *__restrict__ cse, const float *__restrict__ ws,
-                                                       T *__restrict__ y, float *__restrict__ sse_out, long long npix, long long hw, int c) {
-    const int lane = threadIdx.x & 31;
+                                                       T *__restrict__ y, float *__restrict__ sse_out, long long npix, long long hw, int c, int gw) {
+    const int lane = threadIdx.x & 31, sub = lane / gw, vl = lane - sub * gw, ppw = 32 / gw;
     const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const int cv = c >> 3;
-    for (long long p = warp; p < npix; p += nwarps) {
-        const long long nn = p / hw;
+    for (long long p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
+        const long long p = p0 + sub;
+        const bool act = p < npix;
+        const long long nn = act ? p / hw : 0;
         float dot = 0.f;
-        for (int v = lane; v < cv; v += 32) {
-            float f[8];
-            Vec8<T>::load(x + p * c + v * 8, f);
+        if (act)
+            for (int v = vl; v < cv; v += gw) {
+                float f[8];
+                Vec8<T>::load(x + p * c + v * 8, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dot += f[j] * ws[v * 8 + j];
-        }
-        dot = warp_sum(dot);
+                for (int j = 0; j < 8; ++j) dot += f[j] * ws[v * 8 + j];
+            }
+        dot = group_sum(dot, gw);
         const float sse = 1.0f / (1.0f + __expf(-dot));
-        if (lane == 0) sse_out[p] = sse;
-        for (int v = lane; v < cv; v += 32) {
-            float f[8];
-            Vec8<T>::load(x + p * c + v * 8, f);
+        if (act && vl == 0) sse_out[p] = sse;
+        if (act)
+            for (int v = vl; v < cv; v += gw) {
+                float f[8];
+                Vec8<T>::load(x + p * c + v * 8, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] *= (cse[nn * c + v * 8 + j] + sse);
-            Vec8<T>::store(y + p * c + v * 8, f);
-        }
+                for (int j = 0; j < 8; ++j) f[j] *= (cse[nn * c + v * 8 + j] + sse);
+                Vec8<T>::store(y + p * c + v * 8, f);
+            }
     }
 }
 
 // dx = g*(cse+sse) + ws * [sse(1-sse) * sum_c g x] ; dcse[n,c] += sum_p g x ; dws[c] += sum_p x * sse(1-sse) * sum_c' g x
-// One warp per pixel, lane v owns channel vectors v, v+32, ... for EVERY pixel it sees, so the two per-channel reductions are
-// accumulated in registers across the warp's pixels and reach shared memory once per sample boundary / once at the end (the
-// first version issued two shared-memory atomics per element: 8-way contended, ~4x the time of the data movement).
+// Same lane groups; a lane owns the SAME channel vectors for every pixel it sees, so the two per-channel reductions are
+// accumulated in registers across the lane's pixels and reach memory once per sample boundary / once at the end (the first
+// version issued two shared-memory atomics per element: 8-way contended, ~4x the time of the data movement).
 constexpr int SCSE_VM_MAX = 4;                      // channel vectors per lane held in registers: c <= 1024
 template <typename T, int SCSE_VM>
 __global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ x, const float *__restrict__ cse,
                                                        const float *__restrict__ ws, const float *__restrict__ sse_in, T *__restrict__ dx,
-                                                       float *__restrict__ dcse, float *__restrict__ dws, long long npix, long long hw, int c) {
+                                                       float *__restrict__ dcse, float *__restrict__ dws, long long npix, long long hw, int c, int gw) {
     extern __shared__ float s_acc[];            // [c] : dws partial of the block
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int sub = lane / gw, vl = lane - sub * gw, ppw = 32 / gw;
     const int cv = c >> 3;
     const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
     const long long p_begin = blockIdx.x * per_block, p_end = min(npix, p_begin + per_block);
@@ -213,44 +231,46 @@ __global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy,
     float a_cse[SCSE_VM][8], a_ws[SCSE_VM][8], wsv[SCSE_VM][8];
 #pragma unroll
     for (int k = 0; k < SCSE_VM; ++k) {
-        const int v = lane + 32 * k;
+        const int v = vl + gw * k;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a_cse[k][j] = 0.f; a_ws[k][j] = 0.f; wsv[k][j] = v < cv ? ws[v * 8 + j] : 0.f; }
     }
     long long cur_n = -1;
-    auto flush_cse = [&]() {                       // this warp's per-sample partial -> global (one atomic per owned channel)
+    auto flush_cse = [&]() {                       // this lane's per-sample partial -> global (one atomic per owned channel)
         if (cur_n < 0) return;
 #pragma unroll
         for (int k = 0; k < SCSE_VM; ++k) {
-            const int v = lane + 32 * k;
+            const int v = vl + gw * k;
             if (v < cv) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { atomicAdd(dcse + cur_n * c + v * 8 + j, a_cse[k][j]); a_cse[k][j] = 0.f; }
             }
         }
     };
-    for (long long p = p_begin + wib; p < p_end; p += wpb) {
-        const long long nn = p / hw;
-        if (nn != cur_n) { flush_cse(); cur_n = nn; }
-        const float sse = sse_in[p];
+    for (long long p0 = p_begin + static_cast<long long>(wib) * ppw; p0 < p_end; p0 += static_cast<long long>(wpb) * ppw) {
+        const long long p = p0 + sub;
+        const bool act = p < p_end;
+        const long long nn = act ? p / hw : cur_n;
+        if (act && nn != cur_n) { flush_cse(); cur_n = nn; }
+        const float sse = act ? sse_in[p] : 0.f;
         float g[SCSE_VM][8], f[SCSE_VM][8];
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < SCSE_VM; ++k) {
-            const int v = lane + 32 * k;
-            if (v < cv) {
+            const int v = vl + gw * k;
+            if (act && v < cv) {
                 Vec8<T>::load(gy + p * c + v * 8, g[k]);
                 Vec8<T>::load(x + p * c + v * 8, f[k]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dot = fmaf(g[k][j], f[k][j], dot);
             }
         }
-        dot = warp_sum(dot);
+        dot = group_sum(dot, gw);
         const float dpre = dot * sse * (1.f - sse);
 #pragma unroll
         for (int k = 0; k < SCSE_VM; ++k) {
-            const int v = lane + 32 * k;
-            if (v < cv) {
+            const int v = vl + gw * k;
+            if (act && v < cv) {
                 float o[8], cs[8];
                 const float4 c0 = *reinterpret_cast<const float4 *>(cse + nn * c + v * 8), c1 = *reinterpret_cast<const float4 *>(cse + nn * c + v * 8 + 4);
                 cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
@@ -267,7 +287,7 @@ __global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy,
     flush_cse();
 #pragma unroll
     for (int k = 0; k < SCSE_VM; ++k) {
-        const int v = lane + 32 * k;
+        const int v = vl + gw * k;
         if (v < cv) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[v * 8 + j], a_ws[k][j]);
@@ -362,9 +382,10 @@ PCB_API int pcb_scse_forward(const void *x, const float *cse, const float *ws, v
                              pcb_stream_t stream) {
     PCB_CHECK(x && cse && ws && y && sse_out && c % 8 == 0, "pcb_scse_forward: bad arguments (channels must be a multiple of 8)");
     const long long npix = static_cast<long long>(n) * hw;
-    const int grid = sg_grid(npix * 32);
-    if (dtype == PCB_BF16) scse_fwd_kernel<bf16><<<grid, 256, 0, ST>>>(static_cast<const bf16 *>(x), cse, ws, static_cast<bf16 *>(y), sse_out, npix, hw, c);
-    else scse_fwd_kernel<float><<<grid, 256, 0, ST>>>(static_cast<const float *>(x), cse, ws, static_cast<float *>(y), sse_out, npix, hw, c);
+    const int gw = scse_group_width(c);
+    const int grid = sg_grid(npix * gw);
+    if (dtype == PCB_BF16) scse_fwd_kernel<bf16><<<grid, 256, 0, ST>>>(static_cast<const bf16 *>(x), cse, ws, static_cast<bf16 *>(y), sse_out, npix, hw, c, gw);
+    else scse_fwd_kernel<float><<<grid, 256, 0, ST>>>(static_cast<const float *>(x), cse, ws, static_cast<float *>(y), sse_out, npix, hw, c, gw);
     PCB_LAUNCH_CHECK();
     return 0;
 }
@@ -376,9 +397,10 @@ PCB_API int pcb_scse_backward(const void *gy, const void *x, const float *cse, c
     PCB_CUDA(cudaMemsetAsync(dcse, 0, sizeof(float) * n * c, ST));
     PCB_CUDA(cudaMemsetAsync(dws, 0, sizeof(float) * c, ST));
     PCB_CHECK(c <= 8 * 32 * SCSE_VM_MAX, "scSE backward: at most %d channels", 8 * 32 * SCSE_VM_MAX);
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((npix + 63) / 64, 4ll * pcb_num_sms())));
+    const int gw = scse_group_width(c);
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((npix * gw + 2047) / 2048, 4ll * pcb_num_sms())));
     const size_t smem = sizeof(float) * c;
-#define PCB_SCSE_BWD(T, VM) scse_bwd_kernel<T, VM><<<grid, 256, smem, ST>>>(static_cast<const T *>(gy), static_cast<const T *>(x), cse, ws, sse, static_cast<T *>(dx), dcse, dws, npix, hw, c)
+#define PCB_SCSE_BWD(T, VM) scse_bwd_kernel<T, VM><<<grid, 256, smem, ST>>>(static_cast<const T *>(gy), static_cast<const T *>(x), cse, ws, sse, static_cast<T *>(dx), dcse, dws, npix, hw, c, gw)
     if (dtype == PCB_BF16) {
         if (c <= 256) PCB_SCSE_BWD(bf16, 1); else if (c <= 512) PCB_SCSE_BWD(bf16, 2); else PCB_SCSE_BWD(bf16, 4);
     } else {

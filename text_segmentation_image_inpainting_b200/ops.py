@@ -392,10 +392,14 @@ class PartialConvFn(torch.autograd.Function):
                                 and geom.dtype == PCB_BF16)
         ctx.save_for_backward(msum, *xs)
         ctx.mark_non_differentiable(msum, newmask)
+        # without this autograd zero-fills a gradient tensor for msum and newmask on every backward (two fill kernels per layer)
+        ctx.set_materialize_grads(False)
         return y, msum, newmask
 
     @staticmethod
     def backward(ctx, gy, _gmsum, _gnewmask):
+        if gy is None:
+            return (None,) * (5 + len(ctx.saved_tensors) - 1)
         lib = _lib.load()
         msum, *xs = ctx.saved_tensors
         geom: ConvGeom = ctx.geom
