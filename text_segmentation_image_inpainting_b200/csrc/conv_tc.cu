@@ -2499,7 +2499,8 @@ SpPlan sp_plan(const pcb_conv *c) {
     //    costs the TMA unit two rows per delivered row, and row-halo re-use is lost where the class grid is narrower than 128):
     //    192->64 @256^2 0.26 -> 0.34 ms.  Off by default (PCB_SUBPIXEL_FWD=1 enables it; parity-tested either way).
     const long long src_tiles = (static_cast<long long>(c->n) * (c->h / 2) * (c->w / 2) + BLOCK_M - 1) / BLOCK_M;
-    S.dgrad = src_tiles >= pcb_num_sms() / 2 || getenv("PCB_SUBPIXEL_ALL") != nullptr;
+    // (768->256 @64^2, 64 source tiles: 0.091 ms against 0.096 + 0.025 ms of reduction pass; @32^2, 16 tiles: 0.101 against 0.067)
+    S.dgrad = src_tiles >= pcb_num_sms() / 3 || getenv("PCB_SUBPIXEL_ALL") != nullptr;
     S.fwd = getenv("PCB_SUBPIXEL_FWD") != nullptr || getenv("PCB_SUBPIXEL_ALL") != nullptr;
     S.sp_fwd_elems = S.fwd ? off : 0;
     S.sp_dg_elems = S.dgrad ? static_cast<long long>(rup(S.kext_u, 128)) * S.kd_sp : 0;

@@ -495,6 +495,7 @@ template <typename T> __device__ __forceinline__ F4 f4_as_stored(const F4 &v) {
     return r;
 }
 
+constexpr int DW4_QF = 6;                           // forward / data gradient: rows of loads in flight per thread (a multiple of 3)
 constexpr int DW4_Q = 3;                            // rows of loads in flight per thread = the period of the accumulator rotation
 template <typename T, bool FLIP>
 __global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x, int x_cstride, const T *__restrict__ w_t, const float *__restrict__ bias,
@@ -508,13 +509,17 @@ __global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x,
     const int seg = z % nseg; z /= nseg;
     const int pgroups = dil / ppb;
     const int pg = z % pgroups, nn = z / pgroups;
-    F4 wt[3][3], bs = f4_zero(), st_s = f4_zero(), st_q = f4_zero();
+    // weights stay PACKED (bf16: 2 registers per tap instead of 4) and are unpacked at use: the 18 registers this frees pay for a
+    // six-row load queue -- these kernels are bound by bytes in flight per SM, not by issue slots (profiles/r02_ncu_dw.txt)
+    constexpr int QF = sizeof(T) == 2 ? DW4_QF : DW4_Q;          // fp32 storage (exact mode): raw rows are twice as wide
+    Raw4<T> wt[3][3];
+    F4 bs = f4_zero(), st_s = f4_zero(), st_q = f4_zero();
 #pragma unroll
     for (int tr = 0; tr < 3; ++tr)
 #pragma unroll
         for (int tc = 0; tc < 3; ++tc) {
             const int tap = FLIP ? (2 - tr) * 3 + (2 - tc) : tr * 3 + tc;
-            wt[tr][tc] = f4_load<T>(w_t + static_cast<long long>(tap) * c + ch);
+            wt[tr][tc].load(w_t + static_cast<long long>(tap) * c + ch);
         }
     if (bias && !FLIP) { bs.lo = make_float2(bias[ch], bias[ch + 1]); bs.hi = make_float2(bias[ch + 2], bias[ch + 3]); }
     if (active) {
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x,
             const T *pf = x + ((static_cast<long long>(nn) * h + a + static_cast<long long>(dil) * i_lo) * w + ox) * x_cstride + ch;
             T *ps = y + ((static_cast<long long>(nn) * h + a + static_cast<long long>(dil) * j0) * w + ox) * y_cstride + ch;
             int fetched = i_lo;
-            Raw4<T> q[DW4_Q][3];
+            Raw4<T> q[QF][3];
             auto fetch = [&](Raw4<T> (&dst)[3]) {
                 dst[0].zero(); dst[1].zero(); dst[2].zero();
                 if (fetched < i_hi) {
@@ -541,27 +546,27 @@ __global__ void __launch_bounds__(256, 2) dw4_s1_kernel(const T *__restrict__ x,
                 ++fetched; pf += xrow;
             };
 #pragma unroll
-            for (int k = 0; k < DW4_Q; ++k) fetch(q[k]);
+            for (int k = 0; k < QF; ++k) fetch(q[k]);
             auto emit = [&](const F4 &accv) {
                 const F4 o = f4_add(accv, bs);
                 f4_store<T>(ps, o);
                 ps += yrow;
                 if (bn_sums != nullptr) { const F4 r = f4_as_stored<T>(o); st_s = f4_add(st_s, r); st_q = f4_fma(r, r, st_q); }
             };
-            // three accumulators in rotating roles (period DW4_Q == 3): while input sub-row i is processed, `top` belongs to
+            // three accumulators in rotating roles (period 3; QF is a multiple of it): while input sub-row i is processed, `top` belongs to
             // output row i-1 (receives tap row 2 and is complete), `mid` to output i (tap row 1), `bot` to output i+1 (tap row 0)
             F4 acc[3] = {f4_zero(), f4_zero(), f4_zero()};
-            for (int i0 = i_lo; i0 < i_hi; i0 += DW4_Q) {
+            for (int i0 = i_lo; i0 < i_hi; i0 += QF) {
 #pragma unroll
-                for (int k = 0; k < DW4_Q; ++k) {
+                for (int k = 0; k < QF; ++k) {
                     const int i = i0 + k;
                     if (i < i_hi) {
                         const F4 x0 = f4_of(q[k][0]), x1 = f4_of(q[k][1]), x2 = f4_of(q[k][2]);
-                        fetch(q[k]);                                   // refill the slot: DW4_Q rows of loads stay in flight
+                        fetch(q[k]);                                   // refill the slot: QF rows of loads stay in flight
                         F4 &top = acc[k % 3], &mid = acc[(k + 1) % 3], &bot = acc[(k + 2) % 3];
-                        top = f4_fma(wt[2][0], x0, f4_fma(wt[2][1], x1, f4_fma(wt[2][2], x2, top)));
-                        mid = f4_fma(wt[1][0], x0, f4_fma(wt[1][1], x1, f4_fma(wt[1][2], x2, mid)));
-                        bot = f4_fma(wt[0][0], x0, f4_fma(wt[0][1], x1, f4_mul(wt[0][2], x2)));
+                        top = f4_fma(f4_of(wt[2][0]), x0, f4_fma(f4_of(wt[2][1]), x1, f4_fma(f4_of(wt[2][2]), x2, top)));
+                        mid = f4_fma(f4_of(wt[1][0]), x0, f4_fma(f4_of(wt[1][1]), x1, f4_fma(f4_of(wt[1][2]), x2, mid)));
+                        bot = f4_fma(f4_of(wt[0][0]), x0, f4_fma(f4_of(wt[0][1]), x1, f4_mul(f4_of(wt[0][2]), x2)));
                         if (i - 1 >= j0) emit(top);                    // complete: it just received its bottom tap row
                     }
                 }

@@ -212,46 +212,39 @@ __global__ void __launch_bounds__(256) scse_fwd_kernel(const T *__restrict__ x, 
 }
 
 // dx = g*(cse+sse) + ws * [sse(1-sse) * sum_c g x] ; dcse[n,c] += sum_p g x ; dws[c] += sum_p x * sse(1-sse) * sum_c' g x
-// Same lane groups; a lane owns the SAME channel vectors for every pixel it sees, so the two per-channel reductions are
-// accumulated in registers across the lane's pixels and reach memory once per sample boundary / once at the end (the first
-// version issued two shared-memory atomics per element: 8-way contended, ~4x the time of the data movement).
+// Same lane groups; a block works inside ONE sample (blockIdx = sample * bps + slice) and a lane owns the SAME channel vectors for
+// every pixel it sees, so both per-channel reductions are accumulated in registers over the lane's pixels, combined across the
+// block in shared memory and reach global memory as one atomic per channel per block.  (v1 issued two shared-memory atomics
+// per element; v2 one global atomic per lane and channel: with 8 lane groups per warp that was 2k same-address atomics per block.)
 constexpr int SCSE_VM_MAX = 4;                      // channel vectors per lane held in registers: c <= 1024
 template <typename T, int SCSE_VM>
 __global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ x, const float *__restrict__ cse,
                                                        const float *__restrict__ ws, const float *__restrict__ sse_in, T *__restrict__ dx,
-                                                       float *__restrict__ dcse, float *__restrict__ dws, long long npix, long long hw, int c, int gw) {
-    extern __shared__ float s_acc[];            // [c] : dws partial of the block
+                                                       float *__restrict__ dcse, float *__restrict__ dws, long long hw, int c, int gw, int bps) {
+    extern __shared__ float s_acc[];            // [2][c] : dcse partial, dws partial of the block
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int sub = lane / gw, vl = lane - sub * gw, ppw = 32 / gw;
     const int cv = c >> 3;
-    const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
-    const long long p_begin = blockIdx.x * per_block, p_end = min(npix, p_begin + per_block);
-    for (int i = threadIdx.x; i < c; i += blockDim.x) s_acc[i] = 0.f;
+    const long long nn = blockIdx.x / bps;
+    const int slice = blockIdx.x - static_cast<int>(nn) * bps;
+    const long long per_block = (hw + bps - 1) / bps;
+    const long long p_begin = nn * hw + slice * per_block, p_end = min((nn + 1) * hw, p_begin + per_block);
+    for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
-    float a_cse[SCSE_VM][8], a_ws[SCSE_VM][8], wsv[SCSE_VM][8];
+    float a_cse[SCSE_VM][8], a_ws[SCSE_VM][8], wsv[SCSE_VM][8], cs[SCSE_VM][8];
 #pragma unroll
     for (int k = 0; k < SCSE_VM; ++k) {
         const int v = vl + gw * k;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a_cse[k][j] = 0.f; a_ws[k][j] = 0.f; wsv[k][j] = v < cv ? ws[v * 8 + j] : 0.f; }
-    }
-    long long cur_n = -1;
-    auto flush_cse = [&]() {                       // this lane's per-sample partial -> global (one atomic per owned channel)
-        if (cur_n < 0) return;
-#pragma unroll
-        for (int k = 0; k < SCSE_VM; ++k) {
-            const int v = vl + gw * k;
-            if (v < cv) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { atomicAdd(dcse + cur_n * c + v * 8 + j, a_cse[k][j]); a_cse[k][j] = 0.f; }
-            }
+        for (int j = 0; j < 8; ++j) {
+            a_cse[k][j] = 0.f; a_ws[k][j] = 0.f;
+            wsv[k][j] = v < cv ? ws[v * 8 + j] : 0.f;
+            cs[k][j] = v < cv ? cse[nn * c + v * 8 + j] : 0.f;
         }
-    };
+    }
     for (long long p0 = p_begin + static_cast<long long>(wib) * ppw; p0 < p_end; p0 += static_cast<long long>(wpb) * ppw) {
         const long long p = p0 + sub;
         const bool act = p < p_end;
-        const long long nn = act ? p / hw : cur_n;
-        if (act && nn != cur_n) { flush_cse(); cur_n = nn; }
         const float sse = act ? sse_in[p] : 0.f;
         float g[SCSE_VM][8], f[SCSE_VM][8];
         float dot = 0.f;
@@ -271,12 +264,10 @@ __global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy,
         for (int k = 0; k < SCSE_VM; ++k) {
             const int v = vl + gw * k;
             if (act && v < cv) {
-                float o[8], cs[8];
-                const float4 c0 = *reinterpret_cast<const float4 *>(cse + nn * c + v * 8), c1 = *reinterpret_cast<const float4 *>(cse + nn * c + v * 8 + 4);
-                cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+                float o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    o[j] = fmaf(g[k][j], cs[j] + sse, wsv[k][j] * dpre);
+                    o[j] = fmaf(g[k][j], cs[k][j] + sse, wsv[k][j] * dpre);
                     a_cse[k][j] = fmaf(g[k][j], f[k][j], a_cse[k][j]);
                     a_ws[k][j] = fmaf(f[k][j], dpre, a_ws[k][j]);
                 }
@@ -284,17 +275,22 @@ __global__ void __launch_bounds__(256) scse_bwd_kernel(const T *__restrict__ gy,
             }
         }
     }
-    flush_cse();
+    // lanes of a warp that own the same vectors (different pixel sub-groups) combine first, then one shared atomic per channel and warp
 #pragma unroll
     for (int k = 0; k < SCSE_VM; ++k) {
         const int v = vl + gw * k;
-        if (v < cv) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[v * 8 + j], a_ws[k][j]);
+        for (int j = 0; j < 8; ++j) {
+            float a = a_cse[k][j], b = a_ws[k][j];
+            for (int o = gw; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (sub == 0 && v < cv) { atomicAdd(&s_acc[v * 8 + j], a); atomicAdd(&s_acc[c + v * 8 + j], b); }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dws + i, s_acc[i]);
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        atomicAdd(dcse + nn * c + i, s_acc[i]);
+        atomicAdd(dws + i, s_acc[c + i]);
+    }
 }
 
 // broadcast add: dx[n,p,c] += g[n,c] / hw   (backward of the global average pool)
@@ -398,9 +394,12 @@ PCB_API int pcb_scse_backward(const void *gy, const void *x, const float *cse, c
     PCB_CUDA(cudaMemsetAsync(dws, 0, sizeof(float) * c, ST));
     PCB_CHECK(c <= 8 * 32 * SCSE_VM_MAX, "scSE backward: at most %d channels", 8 * 32 * SCSE_VM_MAX);
     const int gw = scse_group_width(c);
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((npix * gw + 2047) / 2048, 4ll * pcb_num_sms())));
-    const size_t smem = sizeof(float) * c;
-#define PCB_SCSE_BWD(T, VM) scse_bwd_kernel<T, VM><<<grid, 256, smem, ST>>>(static_cast<const T *>(gy), static_cast<const T *>(x), cse, ws, sse, static_cast<T *>(dx), dcse, dws, npix, hw, c, gw)
+    // blocks per sample: ~2048 lane-slots of work per block, at most ~4 blocks per SM in total
+    const long long want = std::max<long long>(1, (hw * gw + 2047) / 2048), cap = std::max<long long>(1, 4ll * pcb_num_sms() / n);
+    const int bps = static_cast<int>(std::min(want, cap));
+    const int grid = n * bps;
+    const size_t smem = sizeof(float) * 2 * c;
+#define PCB_SCSE_BWD(T, VM) scse_bwd_kernel<T, VM><<<grid, 256, smem, ST>>>(static_cast<const T *>(gy), static_cast<const T *>(x), cse, ws, sse, static_cast<T *>(dx), dcse, dws, hw, c, gw, bps)
     if (dtype == PCB_BF16) {
         if (c <= 256) PCB_SCSE_BWD(bf16, 1); else if (c <= 512) PCB_SCSE_BWD(bf16, 2); else PCB_SCSE_BWD(bf16, 4);
     } else {
