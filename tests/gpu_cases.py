@@ -92,6 +92,8 @@ CONV_CASES = {
     "tc_k3_320_64_two_odd_split": (320, 64, 3, 1, 1, 1, 1, False, False, 1, 16, 16, BF, "two64", "pc"),
     # ---- channel padding / small-Cin row-packed mode (x lives in an 8-channel-padded NHWC buffer)
     "tc_stem_rowpack_k7_s2": (3, 64, 7, 2, 3, 1, 1, True, True, 2, 40, 44, BF, "uniform3", "pc"),
+    # the same stem on a power-of-two grid: its space-to-depth 4x4 problem (conv_stem.cu) runs on the TMA-fed row-halo kernels
+    "tc_stem_s2d_k7_s2_tma": (3, 64, 7, 2, 3, 1, 1, True, True, 2, 64, 512, BF, "uniform3", "pc"),
     "tc_rowpack_k3_cin8": (8, 32, 3, 1, 1, 1, 1, False, False, 1, 20, 20, BF, "uniform", "pc"),
     "tc_rowpack_k5_d2_cin4": (4, 128, 5, 1, 4, 2, 1, True, False, 1, 24, 24, BF, "uniform", "pc"),
     "tc_cin72_padded_kblock": (72, 64, 3, 1, 1, 1, 1, True, False, 1, 16, 16, BF, "uniform", "pc"),
@@ -115,7 +117,7 @@ CONV_CASES = {
     "tma_splitk_k3_256_128_8x8": (256, 128, 3, 1, 1, 1, 1, True, False, 2, 8, 8, BF, "uniform", "pc"),
     "tma_splitk_k3_320_64_two_8x16": (320, 64, 3, 1, 1, 1, 1, False, False, 1, 8, 16, BF, "two64", "pc"),
 }
-PADDED_X = {"tc_stem_rowpack_k7_s2", "tc_rowpack_k5_d2_cin4"}
+PADDED_X = {"tc_stem_rowpack_k7_s2", "tc_stem_s2d_k7_s2_tma", "tc_rowpack_k5_d2_cin4"}
 
 
 def make_mask(kind, n, cin, h, w, seed):

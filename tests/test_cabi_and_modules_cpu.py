@@ -62,7 +62,9 @@ def test_argument_validation_without_gpu():
     c.parts[0].c = 3; c.parts[0].x_cstride = 8
     assert lib.pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)) == 1
     lib.pcb_conv_weight_layout(_lib.ctypes.byref(c), _lib.ctypes.byref(fe), _lib.ctypes.byref(de))
-    assert (fe.value, de.value) == (64 * 7 * 64, 0)
+    # row-packed operand, then the 4x4 space-to-depth problem of conv_stem.cu: 64 x (16 taps x 64-wide K blocks) bf16 + its fp32
+    # staging 64 x 16 x 32 (two bf16 elements each)
+    assert (fe.value, de.value) == (64 * 7 * 64 + 64 * 16 * 64 + 2 * 64 * 16 * 32, 0)
     c.parts[0].x_cstride = 3                                           # dense 3-channel pixels: not 16-byte chunks
     assert lib.pcb_conv_uses_tensor_cores(_lib.ctypes.byref(c)) == 0
 

@@ -418,8 +418,9 @@ int pcb_k2r_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, 
     K2rParams P;
     base(P, c, K);
     P.dc = static_cast<const bf16 *>(dc); P.dc_cstride = dc_cstride; P.d = d; P.dw = dw;
-    if (K.cs <= 3) k2r_dbuild_kernel<true, 3><<<grid_for(c, 2), 256, 0, st>>>(P);
-    else k2r_dbuild_kernel<true, 4><<<grid_for(c, 2), 256, 0, st>>>(P);
+    // 170 registers per thread: 128-thread blocks keep three of them resident per SM (256-thread blocks: one, 12 % of the warp slots)
+    if (K.cs <= 3) k2r_dbuild_kernel<true, 3><<<grid_for(c, 3), 128, 0, st>>>(P);
+    else k2r_dbuild_kernel<true, 4><<<grid_for(c, 2), 128, 0, st>>>(P);
     PCB_LAUNCH_CHECK();
     if (int rc = pcb_tc_wgrad(&K.sub, d, K2R_N, dwsub, sub_ws, true, st)) return rc;
     k2r_dw_scatter_kernel<<<(K2R_TAPS * K2R_CO * K.cu + 255) / 256, 256, 0, st>>>(dwsub, dw, c->cout, c->cin, K.choff_u, K.cu);

@@ -2781,8 +2781,13 @@ static void k2r_bases(const Layout &L, size_t *fe, size_t *de) {
     *de = (static_cast<size_t>(rup(L.ktap, 128)) * L.kd + 63) / 64 * 64;
 }
 
+// space-to-depth stems (conv_stem.cu): the 4x4 problem's operand (+ staging) follows the row-packed operand
+static bool stem_ok(const pcb_conv *c) { return common_ok(c) && is_rowpack(c) && pcb_stem_ok(c); }
+static size_t stem_base(const Layout &L) { return (static_cast<size_t>(L.rows_f) * L.kf + 63) / 64 * 64; }
+
 size_t pcb_tc_workspace(const pcb_conv *c) {
     if (smallco_ok(c) && pcb_k2r_ok(c)) return pcb_k2r_workspace(c);
+    if (stem_ok(c)) return std::max(pcb_stem_workspace(c), tapmask_bytes(c));
     size_t bytes = tapmask_bytes(c);
     if (tma_fwd_ok(c) || tma_wgrad_ok(c))                // dense copies of the 2x-upsampled sources (TMA cannot replicate pixels)
         for (int p = 0; p < c->nparts; ++p)
@@ -2803,6 +2808,7 @@ void pcb_tc_weight_layout(const pcb_conv *c, size_t *fwd_elems, size_t *dgrad_el
         pcb_k2r_weight_layout(c, &fx, &dx);
         *fwd_elems = fb + fx; *dgrad_elems = db + dx;
     }
+    if (stem_ok(c)) *fwd_elems = stem_base(L) + pcb_stem_weight_extra(c);
 }
 
 // true when the data gradient of the 2x-upsampled part is delivered at that part's own (source) resolution
@@ -2843,6 +2849,7 @@ int pcb_tc_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd,
     tc_weight_prepare_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(w_master, W, static_cast<bf16 *>(w_fwd),
                                                                    (w_dgrad && de) ? static_cast<bf16 *>(w_dgrad) : nullptr);
     PCB_LAUNCH_CHECK();
+    if (stem_ok(c)) return pcb_stem_weight_prepare(c, w_master, static_cast<bf16 *>(w_fwd) + stem_base(L), zero_padding, st);
     if (smallco_ok(c) && pcb_k2r_ok(c)) {
         PCB_CHECK(w_dgrad != nullptr, "kernel-to-row weights need the dgrad operand buffer");
         size_t fb, db;
@@ -2863,7 +2870,7 @@ int pcb_tc_forward_mask_pass(const pcb_conv *c, uint64_t *tapmask, cudaStream_t 
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     const Layout L = layout_of(c);
-    if (smallco_ok(c)) return 0;
+    if (smallco_ok(c) || stem_ok(c)) return 0;            // (the stem applies its mask in the space-to-depth pass)
     { const SpPlan S = sp_plan(c); if (S.ok && S.fwd) return 0; }   // sub-pixel forward: its fixers read the mask planes themselves
     bool any_mask = false;
     for (int p = 0; p < c->nparts; ++p) any_mask = any_mask || (c->parts[p].mask != nullptr);
@@ -2891,6 +2898,10 @@ int pcb_tc_forward_ws(const pcb_conv *c, const void *w_fwd, const float *bias, v
     const Layout L = layout_of(c);
     if (!mask_pass_done)
         if (int rc = pcb_tc_forward_mask_pass(c, tapmask, st)) return rc;
+    if (stem_ok(c)) {
+        PCB_CHECK(bn_sums == nullptr || pcb_tc_fuses_bn_stats(c), "fused BatchNorm statistics requested from a kernel that does not produce them");
+        return pcb_stem_forward(c, static_cast<const bf16 *>(w_fwd) + stem_base(L), bias, y, y_cstride, msum, tapmask, bn_sums, st);
+    }
     if (smallco_ok(c)) {
         if (pcb_k2r_ok(c)) {
             size_t fb, db;
@@ -3177,6 +3188,7 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
     const long long m_total = static_cast<long long>(c->n) * c->ho * c->wo;
     PCB_CHECK(m_total < (1ll << 31), "problem too large");
     PCB_CHECK(dc_cstride % 8 == 0 && dc_cstride >= c->cout, "tensor-core wgrad: dc channel stride must be a multiple of 8");
+    if (stem_ok(c)) return pcb_stem_wgrad(c, dc, dc_cstride, dw, workspace, zero_dw, st);
     if (smallco_ok(c)) {
         if (pcb_k2r_ok(c)) return pcb_k2r_wgrad(c, dc, dc_cstride, dw, workspace, zero_dw, st);
         return pcb_smallco_wgrad(c, smallco_layout(layout_of(c)), dc, dc_cstride, dw, zero_dw, st);

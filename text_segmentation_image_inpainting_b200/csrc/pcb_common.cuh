@@ -174,6 +174,14 @@ int pcb_k2r_forward(const pcb_conv *c, const pcb_smallco_layout &L, const void *
 int pcb_k2r_dgrad(const pcb_conv *c, const pcb_smallco_layout &L, const void *dc, int dc_cstride, const void *w_dgrad, const void *w_dg_extra,
                   void *const *dx, const int *dx_cstride, cudaStream_t st);
 int pcb_k2r_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, cudaStream_t st);
+// 7x7 stride-2 image stems as a 4x4 convolution over the space-to-depth image (conv_stem.cu)
+bool pcb_stem_ok(const pcb_conv *c);
+size_t pcb_stem_weight_extra(const pcb_conv *c);
+size_t pcb_stem_workspace(const pcb_conv *c);
+int pcb_stem_weight_prepare(const pcb_conv *c, const float *w_master, void *w_fwd_extra, bool zero_padding, cudaStream_t st);
+int pcb_stem_forward(const pcb_conv *c, const void *w_fwd_extra, const float *bias, void *y, int y_cstride, const float *msum, void *workspace,
+                     double *bn_sums, cudaStream_t st);
+int pcb_stem_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, void *workspace, bool zero_dw, cudaStream_t st);
 // depthwise fast path (dwconv.cu)
 bool pcb_dw_eligible(const pcb_conv *c);
 int pcb_dw_weight_prepare(const pcb_conv *c, const float *w_master, void *w_t, cudaStream_t st);

@@ -17,7 +17,7 @@ def family(name):
         return "tc_wgrad"
     if "dw4_s1_wgrad" in n or "dw3_wgrad" in n or "dw_wgrad" in n:
         return "dw_wgrad"
-    m = re.search(r"pconv_tc_(tma|sp|persistent)_kernel<\s*\(?int\)?\s*(\d+),\s*\(?int\)?\s*(\d+)", n)
+    m = re.search(r"pconv_tc_(tma|sp|persistent)_kernel<\s*(?:\(int\))?\s*(\d+),\s*(?:\(int\))?\s*(\d+)", n)
     if m:
         return "tc_dgrad" if m.group(3) == "1" else "tc_fwd"
     if "smallco_fwd" in n or "k2r_combine" in n:
@@ -25,8 +25,8 @@ def family(name):
     if "smallco_dgrad" in n:
         return "tc_dgrad"
     if "k2r_dbuild" in n:
-        return "tc_dgrad" if "false" in n or "<0" in n or "(bool)0" in n else "tc_wgrad"
-    m = re.search(r"dw4_s1_kernel<[^,]+,\s*\(?bool\)?\s*(\w+)", n)
+        return "tc_dgrad" if re.search(r"k2r_dbuild_kernel<\s*(?:\(bool\))?\s*(0|false)", n) else "tc_wgrad"
+    m = re.search(r"dw4_s1_kernel<[^,]+,\s*(?:\(bool\))?\s*(\w+)", n)
     if m:
         return "dw_dgrad" if m.group(1) in ("1", "true") else "dw_fwd"
     if "dw3_fwd" in n or "dw_fwd" in n:
@@ -55,7 +55,8 @@ def main():
         return v * scale
 
     fams = {}
-    print(f"{'family':9s} {'us':>8s} {'rd MB':>8s} {'wr MB':>8s} {'SM%':>6s} {'tensor%':>8s} {'L2%':>6s} {'grid':>16s}  kernel")
+    print("# one eager training step under ncu (--clock-control none; serialised, cold caches): per launch time, DRAM bytes, SM and L2 throughput % of peak")
+    print(f"{'family':9s} {'us':>8s} {'rd MB':>8s} {'wr MB':>8s} {'SM%':>6s} {'L2%':>6s} {'grid':>16s}  kernel")
     for r in rows[hi + 2:]:
         if len(r) <= col["Kernel Name"]:
             continue
@@ -64,12 +65,10 @@ def main():
         t = get(r, "gpu__time_duration.sum")
         rd, wr = get(r, "dram__bytes_read.sum"), get(r, "dram__bytes_write.sum")
         sm = get(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed")
-        tp = get(r, "sm__pipe_tensor_subunit_op_utcmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
-                 get(r, "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", float("nan")))
         l2 = get(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed")
         grid = r[col["Grid Size"]] if "Grid Size" in col else ""
         short = re.sub(r"void <unnamed>::|\(.*$", "", name)[:70]
-        print(f"{f or '-':9s} {t:8.1f} {rd / 1e6:8.2f} {wr / 1e6:8.2f} {sm:6.1f} {tp:8.1f} {l2:6.1f} {grid:>16s}  {short}")
+        print(f"{f or '-':9s} {t:8.1f} {rd / 1e6:8.2f} {wr / 1e6:8.2f} {sm:6.1f} {l2:6.1f} {grid:>16s}  {short}")
         if f:
             d = fams.setdefault(f, {"launches": 0, "dram_bytes": 0.0, "time_us_under_ncu": 0.0})
             d["launches"] += 1
