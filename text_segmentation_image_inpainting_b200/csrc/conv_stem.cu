@@ -139,6 +139,9 @@ int pcb_stem_forward(const pcb_conv *c, const void *w_fwd_extra, const float *bi
     if (int rc = run_s2d(c, xs, st)) return rc;
     K.sub.parts[0].x = xs;
     uint64_t *sub_ws = reinterpret_cast<uint64_t *>(ws + s2d_bytes(c) + dwsub_bytes(c));
+    // tap-validity words of the 4x4 problem (in-bounds bits only: no holes) where its kernel wants them (the gather kernels of
+    // non-power-of-two grids; the TMA-fed kernels zero-fill out-of-range coordinates themselves)
+    if (int rc = pcb_tc_forward_mask_pass(&K.sub, sub_ws, st)) return rc;
     // the layer's own mask sums drive the epilogue (renormalise, zero at holes, bias, BatchNorm statistics); no hole rows in the GEMM
     return pcb_tc_forward_ws(&K.sub, w_fwd_extra, bias, y, y_cstride, msum, sub_ws, true, bn_sums, st);
 }

@@ -3212,8 +3212,9 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
     if (int rc = make_tmap_2d(&tm, dc, m_total, c->cout, dc_cstride, 64)) return rc;
     if (tma_wgrad_ok(c)) {
         kblock_box(c->wo, c->ho, &P.box_w, &P.box_h, &P.box_n);
-        const bool halo = !getenv("PCB_DISABLE_TMA_HALO") && c->stride == 1 && c->kw == 3 && P.box_w == 64 && P.box_h == 1 && P.box_n == 1 &&
-                          64 + 2 * c->dil <= 256;
+        // row-halo tiles: kw == 3, or the 4x4 space-to-depth stem problem (kw == 4, N = 64: four accumulators = 256 TMEM columns)
+        const bool halo = !getenv("PCB_DISABLE_TMA_HALO") && c->stride == 1 && (c->kw == 3 || (c->kw == 4 && c->cout <= 64)) && P.box_w == 64 &&
+                          P.box_h == 1 && P.box_n == 1 && 64 + (c->kw - 1) * c->dil <= 256;
         const int hx = halo ? (c->kw - 1) * c->dil : 0;
         CUtensorMap ta[TC_MAX_PARTS];
         memset(ta, 0, sizeof(ta));
@@ -3237,6 +3238,7 @@ int pcb_tc_wgrad(const pcb_conv *c, const void *dc, int dc_cstride, float *dw, v
         }
         if (c->nparts < 2) ta[1] = ta[0];
         if (halo) {
+            if (c->kw == 4) return launch_wgrad_tma<64, 4, true>(P, tm, ta[0], ta[1], st);
             if (c->cout % 128 == 0) return launch_wgrad_tma<128, 3, true>(P, tm, ta[0], ta[1], st);
             return launch_wgrad_tma<64, 3, true>(P, tm, ta[0], ta[1], st);
         }
