@@ -78,6 +78,7 @@ struct TcParams {
     const bf16 *dc; int dc_cstride, dc_c8, dc_kext;
     int *abort_flag;
     long long *dbg;           // optional [grid][8] cycle counters written by the MMA thread (PCB_TC_DEBUG_TIMING)
+    int l2pf;                 // TMA-fed fwd/dgrad: request the next tile's A boxes into L2 one tile ahead (PCB_TMA_L2_PREFETCH)
     // TMA-fed kernel: the 128 pixels of an M tile form the box {box_w, box_h, box_n} of the (x, y, image) pixel grid
     int box_w, box_h, box_n, stages, use_fix;
     int wk_base, wk_row, wk_col;   // weight-matrix K index of tap (a, b) of this launch: wk_base + a*wk_row + b*wk_col (+ part / block offset)
@@ -799,6 +800,19 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             // leftmost / topmost source coordinate of tap column 0 (fwd) -- dgrad walks its taps right to left
             const int x_org = (MODE == 0) ? ox * P.stride - P.pad_w : (HALO ? ox + P.pad_w - hx : ox + P.pad_w);
             const int y_org = (MODE == 0) ? oy * P.stride - P.pad_h : oy + P.pad_h;
+            // optional L2 prefetch (P.l2pf): while tile t is loaded, the A boxes of this CTA's NEXT tile are requested into L2, one
+            // tile's worth of stages ahead, so that their loads find L2 instead of DRAM (the ring is round-trip-latency bound)
+            int nx_org = 0, ny_org = 0, nimg = -1;
+            if (P.l2pf && tile + tstep < num_tiles) {
+                const int nmn = (tile + tstep) / KS;
+                const int nm0 = m0_of(nmn / n_tiles);
+                if (nm0 != m0) {
+                    nimg = nm0 / plane;
+                    const int nrem = nm0 - nimg * plane, noy = nrem / pwid, nox = nrem - noy * pwid;
+                    nx_org = (MODE == 0) ? nox * P.stride - P.pad_w : (HALO ? nox + P.pad_w - hx : nox + P.pad_w);
+                    ny_org = (MODE == 0) ? noy * P.stride - P.pad_h : noy + P.pad_h;
+                }
+            }
             int krow = P.wk_base;                                      // weight K index of (tr, tap column 0, part 0, block 0)
             for (int tr = 0, y = y_org; tr < P.kh && !dead; ++tr, y += dstep, krow += row_k)
                 for (int ti = 0, x = x_org, kidx = krow; ti < kwi && !dead; ++ti, x += dstep, kidx = krow + ti * col_k) {
@@ -824,6 +838,7 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                                 uint32_t bdst = dst + A_ROOM;
                                 for (int tc = 0, kb = kidx; tc < nB; ++tc, kb += col_k, bdst += B_BYTES)
                                     ptx::tma_load_2d(bdst, &tmap_w, kb, n0 + (PAIR ? static_cast<int>(rank) * (BLOCK_N / 2) : 0), full);
+                                if (nimg >= 0) ptx::tma_prefetch_4d(ma, c0, nx_org + ti * dstep, ny_org + tr * dstep, nimg);
                             }
                             __syncwarp();
 #ifdef PCB_TC_TIMING
@@ -2127,6 +2142,7 @@ void base_params(TcParams &P, const pcb_conv *c, const Layout &L) {
     P.pad_h = c->pad_h; P.pad_w = c->pad_w; P.dil = c->dil; P.ho = c->ho; P.wo = c->wo;
     P.nparts = c->nparts; P.no_guard = c->no_guard; P.rowpack = L.rowpack; P.ktap = L.ktap;
     P.sub = 1; P.py = 0; P.px = 0; P.fh = c->h; P.fw = c->w;
+    P.l2pf = getenv("PCB_TMA_L2_PREFETCH") != nullptr;
 }
 
 // row-halo eligibility: stride 1, output rows made of whole groups of 8 pixels, halo small enough
