@@ -16,12 +16,15 @@ LAYERS = {  # name: (parts [(c, up)], cout, k, s, p, hw_out_res_in, same_holes)
     "enc2_128_256": ([(128, 0)], 256, 5, 2, 2, 128, True),
     "enc3_256_512": ([(256, 0)], 512, 3, 2, 1, 64, True),
     "tail_67_3": ([(64, 1), (8, 0)], 8, 3, 1, 1, 512, False),
+    # pointwise convolutions of the segmentation family (XceptionTextSegment middle flow at batch 16 = 65536 pixels)
+    "pw_512_512": ([(512, 0)], 512, 1, 1, 0, 64, False, 16),
+    "pw_256_256": ([(256, 0)], 256, 1, 1, 0, 128, False, 16),
 }
 ONCE = "--once" in sys.argv
 names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(LAYERS)
 for name in names:
-    parts, cout, k, s, p, hw, sh = LAYERS[name]
-    n = 8
+    parts, cout, k, s, p, hw, sh = LAYERS[name][:7]
+    n = LAYERS[name][7] if len(LAYERS[name]) > 7 else 8
     xs, ms = [], []
     for c, up in parts:
         r = hw >> up
@@ -30,8 +33,13 @@ for name in names:
     mod = PC.PartialConv(sum(c for c, _ in parts), cout, k, s, p, 1, 1, False, sh).to(dev)
     x = ops.LazyCat(xs, [u for _, u in parts]) if len(xs) > 1 else xs[0]
     m = torch.cat(ms, 1) if len(ms) > 1 else ms[0]
-    def fwd():
-        return mod((x, m))[0]
+    if name.startswith("pw_"):                     # plain nn.Conv2d semantics (no masks, no fixer warps), as the segmentation nets run them
+        wgt = mod.feature_conv.weight
+        def fwd():
+            return ops.conv2d(x, wgt, None, s, p, 1, 1)
+    else:
+        def fwd():
+            return mod((x, m))[0]
     y = fwd(); gy = torch.randn_like(y)
     y.backward(gy); torch.cuda.synchronize()
     if ONCE:
