@@ -122,8 +122,11 @@ __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) &
 // -------------------------------------------------------------------------------------------------
 // epilogue shared by the forward / dgrad kernels: TMEM -> registers -> renormalise / mask -> bf16 NHWC
 // -------------------------------------------------------------------------------------------------
+// Columns [cb, ce) of the tile (multiples of 32): the kernels with eight epilogue warps give each TMEM lane quadrant to two warps
+// that split the columns.  s_stat: this warp's accumulators [sums of its columns | squares at offset sq_off].
 template <int BLOCK_N, int MODE>
-__device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_base, int warp, int lane, int m0, int n0, float *s_stat) {
+__device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_base, int warp, int lane, int m0, int n0, float *s_stat,
+                                            int cb = 0, int ce = BLOCK_N, int sq_off = 256) {
                 ptx::tc_fence_after();
                 const int row = warp * 32 + lane;
                 const int m = m0 + row;
@@ -148,7 +151,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                 }
                 if (P.partial != nullptr) {                // split-K: raw accumulators, reduced across CTAs with fp32 adds
     #pragma unroll 1
-                    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    for (int c0 = cb; c0 < ce; c0 += 32) {
                         uint32_t r[32];
                         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
                         ptx::tmem_ld_wait();
@@ -161,7 +164,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                     return;
                 }
     #pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
                     ptx::tmem_ld_wait();
@@ -203,10 +206,21 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                             ob[j] = __floats2bfloat162_rn(a, b);
                         }
                         if (nstore > 0) {
+                            // a lane owns one output row: its 64 bytes of this chunk go out as two 32-byte sectors (STG.256) when the
+                            // row is 32-byte aligned -- the 16-byte version issued twice as many half-sector requests, and the
+                            // row-scattered store traffic is what bounds the epilogue (4096 requests per 128 x 256 tile)
                             uint4 *dst = reinterpret_cast<uint4 *>(orow);
+                            if ((reinterpret_cast<uintptr_t>(orow) & 31) == 0) {
     #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (j * 8 < nstore) dst[j] = o[j];
+                                for (int j = 0; j < 4; j += 2) {
+                                    if ((j + 1) * 8 < nstore) ptx::st_global_256(dst + j, o[j], o[j + 1]);
+                                    else if (j * 8 < nstore) dst[j] = o[j];
+                                }
+                            } else {
+    #pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j * 8 < nstore) dst[j] = o[j];
+                            }
                         }
                         if (stats) {
                             // per-channel sum and sum of squares of what was just stored (rows past the tensor contribute 0)
@@ -218,8 +232,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                                 q[2 * j] = v[2 * j] * v[2 * j]; q[2 * j + 1] = v[2 * j + 1] * v[2 * j + 1];
                             }
                             const float cs = warp_transpose_sum(v, lane), cq = warp_transpose_sum(q, lane);
-                            s_stat[c0 + lane] += cs;                          // this warp's private accumulators: no atomics needed
-                            s_stat[256 + c0 + lane] += cq;
+                            s_stat[c0 - cb + lane] += cs;                     // this warp's private accumulators: no atomics needed
+                            s_stat[sq_off + c0 - cb + lane] += cq;
                         }
                     }
                 }
@@ -227,16 +241,15 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
 
 // flush one warp's per-column statistics of the N tile starting at n0 into the global fp64 sums, and clear them
 template <int BLOCK_N>
-__device__ __forceinline__ void tc_stats_flush(const TcParams &P, float *s_stat, int lane, int n0) {
+__device__ __forceinline__ void tc_stats_flush(const TcParams &P, float *s_stat, int lane, int n0, int cb = 0, int ce = BLOCK_N, int sq_off = 256) {
     __syncwarp();
-#pragma unroll
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
         const int co = n0 + c0 + lane;
         if (co < P.bn_c) {
-            atomicAdd(P.bn_sums + co, static_cast<double>(s_stat[c0 + lane]));
-            atomicAdd(P.bn_sums + P.bn_c + co, static_cast<double>(s_stat[256 + c0 + lane]));
+            atomicAdd(P.bn_sums + co, static_cast<double>(s_stat[c0 - cb + lane]));
+            atomicAdd(P.bn_sums + P.bn_c + co, static_cast<double>(s_stat[sq_off + c0 - cb + lane]));
         }
-        s_stat[c0 + lane] = 0.f; s_stat[256 + c0 + lane] = 0.f;
+        s_stat[c0 - cb + lane] = 0.f; s_stat[sq_off + c0 - cb + lane] = 0.f;
     }
     __syncwarp();
 }
@@ -707,8 +720,14 @@ constexpr int TMA_THREADS = 320;
 // round trips per MMA.  K steps that only cover channel padding (c8 <= 16*k) are skipped.
 // PAIR: two CTAs of a cluster work on two adjacent M tiles with cta_group::2 MMAs (M = 256) issued by the leader (rank 0); each
 // CTA stages its own A tile and HALF of every weight tile.  The peer's MMA warp only relays "my stage is ready" to the leader.
+// EIGHT epilogue warps (6..13): TMEM lane quadrant q = warp & 3 is drained by two warps, each taking half of the tile's columns.
+// With four, a 128 x 256 tile took ~9.6 k cycles to drain (tcgen05.ld, renormalise, bf16, 16-byte stores, statistics butterfly) --
+// longer than the main loop of every K <= 512 problem (the pointwise convolutions of the segmentation nets: the MMA thread waited
+// 500..1700 cycles per K block for a free accumulator, profiles/r02_tc_timing.txt).
+constexpr int TMA_EPI_WARPS = 8;
+constexpr int TMA_THREADS8 = (6 + TMA_EPI_WARPS) * 32;
 template <int BLOCK_N, int MODE, bool HALO, bool PAIR>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+__global__ void __launch_bounds__(TMA_THREADS8, 1)
 pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
     constexpr uint32_t B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // this CTA's share of one weight tile
@@ -756,7 +775,10 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             ptx::mbar_init(bar_peer + 8 * s, 1);
         }
         // PAIR: the leader's accumulator-drained barrier collects the epilogue threads of both CTAs
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_tmem_full + 8 * s, 1); ptx::mbar_init(bar_tmem_empty + 8 * s, PAIR ? 256 : 128); }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(bar_tmem_full + 8 * s, 1);
+            ptx::mbar_init(bar_tmem_empty + 8 * s, (PAIR ? 2 : 1) * TMA_EPI_WARPS * 32);
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_w); ptx::prefetch_tmap(&tmap_a0); if (np > 1) ptx::prefetch_tmap(&tmap_a1); }
@@ -1089,13 +1111,17 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             }
         }
     } else {
-        // ================================ epilogue warps (6-9) ================================
+        // ================================ epilogue warps (6-13) ================================
         int tile_iter = 0;
-        // fused BatchNorm statistics (see pconv_tc_persistent_kernel)
+        // this warp's half of the tile's columns (a 32-column tile is not split: the second warp of the quadrant only arrives)
+        constexpr int HN = (BLOCK_N >= 64) ? BLOCK_N / 2 : BLOCK_N;
+        const int half = (warp - 6) >> 2;
+        const int cb = half * HN, ce = (cb + HN <= BLOCK_N) ? cb + HN : cb;
+        // fused BatchNorm statistics (see pconv_tc_persistent_kernel): eight private slices of [128 sums | 128 squares]
         s_stat = (MODE == 0 && P.bn_sums != nullptr && P.partial == nullptr)
-                     ? reinterpret_cast<float *>(smem_gen + (((s_tmem_ptr + 32u) & ~15u) - smem_base)) + (warp & 3) * STAT_FLOATS_PER_WARP : nullptr;
+                     ? reinterpret_cast<float *>(smem_gen + (((s_tmem_ptr + 32u) & ~15u) - smem_base)) + (half * 4 + (warp & 3)) * 256 : nullptr;
         if (s_stat) {
-            for (int i = lane; i < STAT_FLOATS_PER_WARP; i += 32) s_stat[i] = 0.f;
+            for (int i = lane; i < 256; i += 32) s_stat[i] = 0.f;
             __syncwarp();
         }
         for (int tile = tile0; tile < num_tiles; tile += tstep) {
@@ -1104,11 +1130,11 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             if (!tile_active(n0)) continue;
             const int acc = tile_iter & 1;
             if (s_stat && n0 != stat_n0) {
-                if (stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0);
+                if (stat_n0 >= 0) tc_stats_flush<BLOCK_N>(P, s_stat, lane, stat_n0, cb, ce, 128);
                 stat_n0 = n0;
             }
             if (!ptx::mbar_wait(bar_tmem_full + 8 * acc, (tile_iter >> 1) & 1, P.abort_flag, 123)) { stat_n0 = -1; break; }
-            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0, s_stat);
+            tc_epilogue<BLOCK_N, MODE>(P, tmem_base + acc * BLOCK_N, warp & 3, lane, m0, n0, s_stat, cb, ce, 128);
             ptx::tc_fence_before();
             if (PAIR && rank == 1) ptx::mbar_arrive_cluster(ptx::mapa(bar_tmem_empty + 8 * acc, 0));   // the leader waits for both epilogues
             else ptx::mbar_arrive(bar_tmem_empty + 8 * acc);
@@ -1121,13 +1147,15 @@ pconv_tc_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     // last N tile's BatchNorm statistics: the four epilogue warps' partials are summed here, after the CTA-wide barrier, so the
     // global sums receive ONE atomic per channel per CTA (148 per address instead of 592)
     if (s_stat != nullptr && stat_n0 >= 0) {
-        const float *base = s_stat - (warp & 3) * STAT_FLOATS_PER_WARP;
-        for (int col = (warp & 3) * 32 + lane; col < BLOCK_N; col += 128) {
+        constexpr int HN = (BLOCK_N >= 64) ? BLOCK_N / 2 : BLOCK_N;
+        const float *base = s_stat - (((warp - 6) >> 2) * 4 + (warp & 3)) * 256;
+        for (int col = (warp - 6) * 32 + lane; col < BLOCK_N; col += TMA_EPI_WARPS * 32) {
             const int co = stat_n0 + col;
             if (co < P.bn_c) {
+                const int h = col / HN, lc = col - h * HN;
                 float a = 0.f, q = 0.f;
 #pragma unroll
-                for (int w4 = 0; w4 < 4; ++w4) { a += base[w4 * STAT_FLOATS_PER_WARP + col]; q += base[w4 * STAT_FLOATS_PER_WARP + 256 + col]; }
+                for (int w4 = 0; w4 < 4; ++w4) { a += base[(h * 4 + w4) * 256 + lc]; q += base[(h * 4 + w4) * 256 + 128 + lc]; }
                 atomicAdd(P.bn_sums + co, static_cast<double>(a));
                 atomicAdd(P.bn_sums + P.bn_c + co, static_cast<double>(q));
             }
@@ -2338,7 +2366,7 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
         grid = 2 * std::min(pair_tiles, pcb_num_sms() / 2);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TMA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TMA_THREADS8); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -2348,7 +2376,7 @@ int launch_tma_n(TcParams &P, const CUtensorMap &tw, const CUtensorMap &ta0, con
     } else {
         const int num_tiles = m_tiles * (P.ncols / BLOCK_N) * P.ksplit;
         grid = std::min(num_tiles, pcb_num_sms());
-        kern<<<grid, TMA_THREADS, smem, st>>>(P, tw, ta0, ta1);
+        kern<<<grid, TMA_THREADS8, smem, st>>>(P, tw, ta0, ta1);
         PCB_LAUNCH_CHECK();
     }
     if (P.dbg) {

@@ -81,6 +81,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *m, 
         : "memory");
 }
 // 4-D tile (channels, x, y, image): out-of-range coordinates (negative included) are zero-filled -- the conv padding
+// 256-bit global store (STG.256, sm_100): one full 32-byte sector per lane and instruction.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 // L2 prefetch of a tile (no shared-memory destination, no barrier): turns the later load of the same box into an L2 hit
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
