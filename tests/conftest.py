@@ -23,7 +23,12 @@ def pytest_collection_modifyitems(config, items):
         have_gpu = torch.cuda.is_available()
     except Exception:  # pragma: no cover
         have_gpu = False
+    # a GPU test that deadlocks (a device-side wait that never returns blocks the host in a CUDA call) must not take the whole
+    # session with it for longer than this: pytest-timeout's thread method ends the process (default per-test budget, overridable)
+    have_timeout = config.pluginmanager.hasplugin("timeout") and not config.getoption("timeout", None)
     for it in items:
+        if have_timeout and "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+            it.add_marker(pytest.mark.timeout(300, method="thread"))
         if "reference" in it.keywords and not have_ref:
             it.add_marker(pytest.mark.skip(reason="/root/reference not present on this box"))
         if "gpu" in it.keywords and not have_gpu:

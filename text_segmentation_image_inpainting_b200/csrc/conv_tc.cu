@@ -188,18 +188,31 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                         }
                     }
                     const bool stats = (MODE == 0) && (s_stat != nullptr);
-                    if (nstore > 0 || stats) {
+                    // warp-uniform: the block below shuffles (bias broadcast, statistics butterfly); lanes of rows past the end of the
+                    // tensor have nothing to store but must take part
+                    if (__any_sync(0xffffffffu, nstore > 0) || stats) {
                         uint4 o[4];
                         __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(o);
+                        // The per-element work is kept to a multiply-add, a select and the conversion: the epilogue of the K <= 512
+                        // problems is ISSUE-bound (it measured 24 instructions per element with per-element bias loads and bounds
+                        // tests), so everything uniform over the chunk is decided here.  Lane l fetches the bias of column col + l
+                        // once; elements get theirs by shuffle.  Columns past cout only exist in the last chunk of a layer.
+                        float bl = 0.f;
+                        const bool has_bias = (MODE == 0) && (P.bias != nullptr);
+                        if (has_bias && col + lane < P.cout) bl = P.bias[col + lane];
+                        const bool edge = (MODE == 0) && (col + 32 > P.cout);
     #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
                             if (MODE == 0) {
-                                const int co = col + 2 * j;
-                                const float b0 = (P.bias && co < P.cout) ? P.bias[co] : 0.f;
-                                const float b1 = (P.bias && co + 1 < P.cout) ? P.bias[co + 1] : 0.f;
-                                a = (hole || co >= P.cout) ? 0.f : a * scale + b0;
-                                b = (hole || co + 1 >= P.cout) ? 0.f : b * scale + b1;
+                                const float b0 = has_bias ? __shfl_sync(0xffffffffu, bl, 2 * j) : 0.f;
+                                const float b1 = has_bias ? __shfl_sync(0xffffffffu, bl, 2 * j + 1) : 0.f;
+                                a = hole ? 0.f : fmaf(a, scale, b0);
+                                b = hole ? 0.f : fmaf(b, scale, b1);
+                                if (edge) {
+                                    if (col + 2 * j >= P.cout) a = 0.f;
+                                    if (col + 2 * j + 1 >= P.cout) b = 0.f;
+                                }
                             } else {
                                 a *= scale; b *= scale;
                             }
@@ -225,10 +238,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &P, uint32_t tmem_bas
                         if (stats) {
                             // per-channel sum and sum of squares of what was just stored (rows past the tensor contribute 0)
                             float v[32], q[32];
+                            const float live = rvalid ? 1.f : 0.f;          // rows past the end of the tensor (last M tile only)
     #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const float2 f = __bfloat1622float2(ob[j]);
-                                v[2 * j] = rvalid ? f.x : 0.f; v[2 * j + 1] = rvalid ? f.y : 0.f;
+                                v[2 * j] = f.x * live; v[2 * j + 1] = f.y * live;
                                 q[2 * j] = v[2 * j] * v[2 * j]; q[2 * j + 1] = v[2 * j + 1] * v[2 * j + 1];
                             }
                             const float cs = warp_transpose_sum(v, lane), cq = warp_transpose_sum(q, lane);
