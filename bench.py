@@ -257,9 +257,9 @@ WORKLOADS = {
     "xception": {"metric": "XceptionTextSegment 512x512 images/sec (fwd+bwd)", "net": ("text_segmentation", "XceptionTextSegment"),
                  "batch": 16, "fwd_gf": 148.70, "no_dgrad_gf": 0.0, "masks": False, "label": "XceptionTextSegment (Xception + ASP)"},
 }
-KERNEL_OF = {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ conv_k2r 1x1 GEMM + k2r_combine for the RGB tail, pconv_tc_persistent_kernel for the stem)",
+KERNEL_OF = {"tc_fwd": "pconv_tc_tma_kernel<MODE=0> (+ conv_k2r 1x1 GEMM + k2r_combine for the RGB tail, s2d_kernel + the same kernel for the space-to-depth stem)",
              "tc_dgrad": "pconv_tc_tma_kernel<MODE=1> / pconv_tc_sp_kernel<MODE=1> (+ k2r_dbuild + 1x1 dgrad for the tail)",
-             "tc_wgrad": "pconv_tc_wgrad_tma_kernel (+ k2r_dbuild + 1x1 wgrad for the tail, pconv_tc_wgrad_kernel for the stem)",
+             "tc_wgrad": "pconv_tc_wgrad_tma_kernel (+ k2r_dbuild + 1x1 wgrad for the tail, s2d_kernel + <64,4,true> for the stem)",
              "dw_fwd": "dw4_s1_kernel<FLIP=0> (dwconv.cu)", "dw_dgrad": "dw4_s1_kernel<FLIP=1> (dwconv.cu)", "dw_wgrad": "dw4_s1_wgrad_kernel (dwconv.cu)"}
 
 
