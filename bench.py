@@ -18,8 +18,15 @@ import time
 
 # The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL's version banner under torchrun, the reference's
 # constructors): keep a handle on the real stdout for that line and point fd 1 at stderr for everything else.
-_REAL_STDOUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_REAL_STDOUT = sys.stdout
+
+
+def _isolate_stdout():
+    """(script entry only) keep a handle on the real stdout for the JSON line; fd 1 -> stderr for every library underneath"""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -516,6 +523,7 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse()
+    _isolate_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -327,9 +327,11 @@ bf16 *dgrad_scratch(size_t bytes) {
     static size_t cap[PCB_MAX_DEVICES] = {};
     const int dev = pcb_cur_device();
     if (cap[dev] < bytes) {
-        if (buf[dev]) cudaFree(buf[dev]);
-        buf[dev] = nullptr; cap[dev] = 0;
-        if (cudaMalloc(&buf[dev], bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        // a smaller buffer handed out earlier is NOT freed: a captured CUDA graph may still replay launches that point into it
+        // (growth happens a handful of times per process, at most one buffer per distinct problem size)
+        void *fresh = nullptr;
+        if (cudaMalloc(&fresh, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        buf[dev] = fresh;
         cap[dev] = bytes;
     }
     return static_cast<bf16 *>(buf[dev]);

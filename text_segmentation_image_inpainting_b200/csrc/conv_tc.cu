@@ -2242,10 +2242,11 @@ float *splitk_scratch(size_t bytes) {
     static size_t cap[PCB_MAX_DEVICES] = {};
     const int dev = pcb_cur_device();
     if (bytes > cap[dev]) {
-        if (buf[dev]) cudaFree(buf[dev]);
-        buf[dev] = nullptr; cap[dev] = 0;
+        // the previous (smaller) buffer is deliberately not freed: a captured CUDA graph may still point into it
         const size_t want = std::max<size_t>(bytes, 16u << 20);
-        if (cudaMalloc(&buf[dev], want) == cudaSuccess) cap[dev] = want;
+        float *fresh = nullptr;
+        if (cudaMalloc(&fresh, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        buf[dev] = fresh; cap[dev] = want;
     }
     return buf[dev];
 }
