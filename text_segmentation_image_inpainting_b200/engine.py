@@ -129,6 +129,9 @@ class TrainStep:
                 self._bucket_of[i] = b
 
     def _install_hooks(self):
+        """A parameter reports ONCE per step (its sink's first write, or its autograd accumulation).  A weight used twice in one
+        forward would therefore be exchanged before its second contribution lands: the reference's networks share no weights;
+        construct with overlap_allreduce=False for models that do."""
         if self._hooks_installed:
             return
         self._hooks_installed = True
