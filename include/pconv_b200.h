@@ -123,7 +123,8 @@ int pcb_pconv_backward_data(const pcb_conv *c, const void *dc, int dc_cstride, c
                             void *const *dx, const int32_t *dx_cstride, pcb_stream_t stream);
 /* 1 when pcb_pconv_backward_data computes the gradient of a 2x-UPSAMPLED source part (x_up == 1) directly at that source's own
  * (half) resolution -- dx[p] is then a [n, h/2, w/2, dx_cstride] buffer and no 2x2 reduction pass follows (sub-pixel path of the
- * tcgen05 kernels: image_inpainting.py:183-185 + partial_convolution.py:229-231 folded into the convolution).  0: dx[p] of
+ * tcgen05 kernels and the kernel-to-row path of the RGB tails: image_inpainting.py:183-185 + partial_convolution.py:229-231
+ * folded into the convolution).  0: dx[p] of
  * every part is a full-resolution [n, h, w, dx_cstride] buffer and the caller reduces 2x2 blocks itself. */
 int pcb_conv_dgrad_at_source_resolution(const pcb_conv *c);
 
